@@ -1,0 +1,182 @@
+/*
+ * raydar_cuda.h -- C ABI of libraydar_cuda.so, the B200 (sm_100a) CUDA backend for Raydar's
+ * per-pixel path-tracing sample loop.
+ *
+ * This is the drop-in boundary: the entry points mirror, one for one, what a Rust
+ * `impl Renderer for CudaRenderer` (reference: src/renderer/mod.rs:25-35) has to call, next to
+ * the existing `CpuRenderer` (src/renderer/cpu.rs:118-183) and `VulkanRenderer`
+ * (src/renderer/vulkan.rs:100-455).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns an RdrStatus (0 = ok); rdr_last_error() gives the message.
+ *     Nothing in the library aborts the process (the reference panics instead: unwrap/todo!).
+ *   - a handle is NOT thread-safe: one caller thread, like `&mut self` in the trait.
+ *   - the scene is BORROWED per call and snapshotted into device memory by rdr_new_frame
+ *     (the VulkanRenderer model, vulkan.rs:207-428).
+ *   - images are row-major, top row first, RGBA, 8-bit linear, alpha 255 -- the layout of
+ *     image::RgbaImage that the trait returns.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     RDR_ERR_CUDA.
+ */
+#ifndef RAYDAR_CUDA_H
+#define RAYDAR_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum RdrStatus {
+    RDR_OK = 0,
+    RDR_ERR_INVALID = 1,       /* bad argument / call order (e.g. render before new_frame) */
+    RDR_ERR_CUDA = 2,          /* CUDA runtime error or no device */
+    RDR_ERR_UNSUPPORTED = 3,   /* World::Transparent is todo!() in the reference (world.rs:32) */
+    RDR_ERR_IO = 4,            /* scene file cannot be opened / image cannot be written */
+    RDR_ERR_PARSE = 5,         /* scene file is not a valid .rscn */
+    RDR_ERR_NCCL = 6,
+    RDR_ERR_NOMEM = 7
+} RdrStatus;
+
+enum { RDR_SPHERE = 0, RDR_CUBE = 1 };                                   /* scene/objects.rs:6-10 */
+enum { RDR_WORLD_SKY = 0, RDR_WORLD_SOLID = 1, RDR_WORLD_TRANSPARENT = 2 }; /* scene/world.rs:6-14 */
+enum { RDR_LOBE_MISS = 0, RDR_LOBE_DIFFUSE = 1, RDR_LOBE_SPECULAR = 2, RDR_LOBE_REFRACT = 3 };
+enum { RDR_MAT_STRIDE = 11 };  /* albedo3, roughness, metallic, emission_color3, emission_strength,
+                                  transmission, ior -- field order of scene/material.rs:4-13 */
+
+/* nearest-hit search strategy; AUTO = brute force over the shared-memory SoA buffer for small
+ * scenes, BVH otherwise.  Both return the reference's trace_ray winner (cpu.rs:344-352). */
+enum { RDR_ACCEL_AUTO = 0, RDR_ACCEL_BRUTE = 1, RDR_ACCEL_BVH = 2 };
+
+typedef struct RdrRenderer RdrRenderer;    /* replaces CpuRenderer state, cpu.rs:111-116 */
+typedef struct RdrScene RdrScene;          /* host-side loaded scene, scene/mod.rs:13-18 */
+
+/* RendererConfig, renderer/mod.rs:11-23 (defaults 1024 / 12) */
+typedef struct RdrConfig {
+    uint32_t max_sample_count;
+    uint32_t max_bounces;
+} RdrConfig;
+
+/* Flattened `&Scene`: what the Rust shim builds from scene.camera / scene.world / scene.objects. */
+typedef struct RdrSceneFlat {
+    uint32_t width, height;          /* camera.resolution_x/y, camera.rs:19-20 */
+    float inv_proj[16];              /* camera.inverse_proj_matrix(), column-major (camera.rs:206) */
+    float inv_view[16];              /* camera.inverse_view_matrix(), column-major (camera.rs:202) */
+    float cam_pos[3];                /* camera.position(), camera.rs:62 */
+    uint32_t world_kind;             /* RDR_WORLD_* */
+    float world_a[3];                /* SkyColor.top_color | SolidColor */
+    float world_b[3];                /* SkyColor.bottom_color */
+    uint32_t n_objects;
+    const uint32_t *kind;            /* n: RDR_SPHERE | RDR_CUBE */
+    const float *geom;               /* n*4: center.xyz, radius | side_length */
+    const float *material;           /* n*RDR_MAT_STRIDE */
+} RdrSceneFlat;
+
+/* Profiler, renderer/timing.rs:10-19: the four Timer durations in nanoseconds; a timer whose
+ * duration() would be None reports has_* = 0 (main.rs:61-107 errors out on those). */
+typedef struct RdrProfiler {
+    uint64_t frame_ns, sample_ns, prepare_ns, render_ns;
+    uint32_t has_frame, has_sample, has_prepare, has_render;
+    double   device_render_ms;       /* extension: CUDA-event time of the sample kernels of this frame */
+} RdrProfiler;
+
+/* One bounce of a path (debug / parity mode). */
+typedef struct RdrPathStep {
+    int32_t  object;                 /* hit object index, -1 = miss */
+    uint32_t lobe;                   /* RDR_LOBE_* */
+    uint32_t front_face;
+    float t;
+    float position[3];
+    float normal[3];
+    float origin[3];                 /* next ray origin */
+    float direction[3];              /* next ray direction */
+    float attenuation[3];
+    float light[3];
+} RdrPathStep;
+
+/* ---- lifecycle: CpuRenderer::new(config), cpu.rs:186 ------------------------------------------ */
+int rdr_create(const RdrConfig *config, int device, RdrRenderer **out);
+void rdr_destroy(RdrRenderer *r);
+const char *rdr_last_error(const RdrRenderer *r);   /* r == NULL: last error of a failed rdr_create / scene call */
+
+/* ---- trait Renderer, renderer/mod.rs:25-35 ---------------------------------------------------- */
+/* new_frame(&mut self, &Scene)                       cpu.rs:135-140 */
+int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene);
+/* render_sample(&mut self, &Scene) -> Option<RgbaImage>   cpu.rs:142-158.
+ * *produced = 0 (image untouched) once sample_count >= max_sample_count, i.e. `None`. */
+int rdr_render_sample(RdrRenderer *r, uint8_t *rgba8, int *produced);
+/* render_frame(&mut self, &Scene) -> RgbaImage       cpu.rs:119-133 (new_frame + all samples + resolve) */
+int rdr_render_frame(RdrRenderer *r, const RdrSceneFlat *scene, uint8_t *rgba8);
+/* profiler(&self) -> &Profiler */
+int rdr_profiler(const RdrRenderer *r, RdrProfiler *out);
+uint32_t rdr_sample_count(const RdrRenderer *r);
+uint32_t rdr_max_sample_count(const RdrRenderer *r);
+uint32_t rdr_max_bounces(const RdrRenderer *r);
+int rdr_set_max_sample_count(RdrRenderer *r, uint32_t count);
+int rdr_set_max_bounces(RdrRenderer *r, uint32_t bounces);
+
+/* ---- extensions the reference lacks (seed, sharding, throughput path) -------------------------- */
+/* RNG seed (Philox key); the reference's thread_rng has none.  Takes effect at the next new_frame. */
+int rdr_set_seed(RdrRenderer *r, uint64_t seed);
+/* This instance renders global sample indices [first, first + max_sample_count): sample-range
+ * sharding across GPUs (one instance per GPU, accumulators summed afterwards). */
+int rdr_set_sample_offset(RdrRenderer *r, uint32_t first_sample);
+int rdr_set_accel(RdrRenderer *r, int accel);                 /* RDR_ACCEL_* */
+/* Zero the accumulator and sample_count but keep the scene already resident on the device
+ * (new_frame without the scene upload; the editor calls new_frame for every change, the
+ * throughput path only needs a fresh accumulator). */
+int rdr_reset_frame(RdrRenderer *r);
+/* Render up to n more samples into the device accumulator, no resolve, no read-back. */
+int rdr_render_samples(RdrRenderer *r, uint32_t n);
+/* print_frame_buffer, cpu.rs:221-230: clamp(sum / divisor, 0, 1) * 255 as u8, read back to host.
+ * divisor = 0 uses sample_count(). */
+int rdr_resolve(RdrRenderer *r, uint32_t divisor, uint8_t *rgba8);
+int rdr_read_accum(RdrRenderer *r, float *accum_rgba_f32);    /* W*H*4 floats */
+/* device accumulator (float RGBA, W*H*4) and the stream the kernels run on, for an external
+ * NCCL reduce (torch.distributed / ncclReduce) between per-GPU instances */
+int rdr_accum_device_ptr(RdrRenderer *r, void **ptr, size_t *bytes);
+int rdr_stream(RdrRenderer *r, void **cuda_stream);
+int rdr_synchronize(RdrRenderer *r);
+/* number of kernels launched by this handle so far */
+uint64_t rdr_launch_count(const RdrRenderer *r);
+
+/* single-process multi-GPU: one sub-renderer per device, sample ranges split evenly, accumulators
+ * combined with one ncclReduce(sum, f32) onto devices[0] before resolve. */
+int rdr_create_multi(const RdrConfig *config, int n_devices, const int *devices, RdrRenderer **out);
+
+/* ---- parity / debug modes ------------------------------------------------------------------------ */
+/* first-hit object id (-1 = miss) and t per pixel for the current frame's primary rays */
+int rdr_first_hit(RdrRenderer *r, int32_t *ids, float *t);
+/* one path with every bounce recorded; *n_steps <= capacity; rgba = per_pixel() result */
+int rdr_trace_path(RdrRenderer *r, uint32_t x, uint32_t y, uint32_t sample,
+                   RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float rgba[4]);
+/* per-function known-answer entry points (device execution of the same __device__ functions the
+ * render kernel uses): rays n*6 (origin, direction), prims n*4 */
+int rdr_kat_hit_sphere(RdrRenderer *r, uint32_t n, const float *rays, const float *spheres, float *t, int32_t *hit);
+int rdr_kat_hit_cube(RdrRenderer *r, uint32_t n, const float *rays, const float *cubes, float *t, int32_t *hit);
+/* nearest hit of n arbitrary rays against the current frame's scene: id (-1 miss), t */
+int rdr_kat_trace(RdrRenderer *r, uint32_t n, const float *rays, int32_t *ids, float *t);
+/* camera rays of the current frame for n pixels (xy n*2 u32) -> rays n*6 */
+int rdr_kat_camera_rays(RdrRenderer *r, uint32_t n, const uint32_t *xy, float *rays);
+/* raw RNG block of the spec (Philox4x32-10), computed on the device */
+int rdr_kat_rng(RdrRenderer *r, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block, uint32_t out[4]);
+
+/* ---- host scene pipeline (cli/mod.rs:32-40, scene/camera.rs:210-231) ----------------------------- */
+int rdr_scene_load_rscn(const char *path, RdrScene **out);
+int rdr_scene_default(RdrScene **out);                            /* Scene::default(), scene/mod.rs:20-68 */
+/* set_resolution_x/y + update_matrices (camera.rs:141-157,210-231) */
+int rdr_scene_set_resolution(RdrScene *s, uint32_t width, uint32_t height);
+/* the same, but keeps the stored matrices (valid when the aspect ratio is unchanged) */
+int rdr_scene_override_resolution(RdrScene *s, uint32_t width, uint32_t height);
+int rdr_scene_flat(const RdrScene *s, RdrSceneFlat *out);        /* pointers valid until rdr_scene_free */
+void rdr_scene_free(RdrScene *s);
+/* RgbaImage::save (main.rs:19): 8-bit RGBA PNG */
+int rdr_write_png(const char *path, const uint8_t *rgba8, uint32_t width, uint32_t height);
+
+const char *rdr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYDAR_CUDA_H */

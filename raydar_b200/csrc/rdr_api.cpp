@@ -1,0 +1,550 @@
+// rdr_api.cpp -- the C ABI of libraydar_cuda.so (include/raydar_cuda.h): renderer handle, frame state
+// machine of the reference's Renderer trait (renderer/mod.rs:25-35, cpu.rs:118-183), scene packing and
+// the debug / parity entry points.  No CPU fallback: every compute call needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "raydar_cuda.h"
+#include "rdr_launch.h"
+#include "rdr_pack.h"
+#include "rdr_multi.h"
+
+using rdr::FrameParams;
+using rdr::SceneLayout;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+using Clock = std::chrono::steady_clock;
+
+// renderer/timing.rs:69-127
+struct Timer {
+    bool started = false, has_duration = false;
+    Clock::time_point start_tp;
+    uint64_t duration_ns = 0;
+    void start() { started = true; start_tp = Clock::now(); }
+    void start_if_not_started() { if (!started) start(); }
+    void end() { if (started) { duration_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - start_tp).count(); has_duration = true; } }
+    void end_if_not_ended() { if (!has_duration) end(); }
+};
+
+}  // namespace
+
+struct RdrRenderer {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    RdrConfig config{1024u, 12u};
+    uint64_t seed = 0x5EEDull;
+    uint32_t sample_offset = 0;
+    int accel = RDR_ACCEL_AUTO;
+    bool use_cull = true;
+
+    bool has_frame = false;
+    FrameParams params{};
+    unsigned char *d_blob = nullptr; size_t blob_capacity = 0;
+    rdr::f4 *d_accum = nullptr; uchar4 *d_rgba = nullptr; size_t pixel_capacity = 0;
+    uint32_t sample_count = 0;
+    uint64_t launches = 0;
+
+    // Profiler, timing.rs:10-19
+    Timer frame_timer, sample_timer, prepare_timer, render_timer;
+    double device_render_ms = 0.0;
+
+    rdr::MultiGpu *multi = nullptr;     // non-null for handles made by rdr_create_multi
+    std::string last_error;
+};
+
+namespace {
+
+int fail(RdrRenderer *r, int status, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (r) r->last_error = buf;
+    g_last_error = buf;
+    return status;
+}
+
+#define RDR_CUDA(r, call)                                                                           \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) return fail((r), RDR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int pack_scene(RdrRenderer *r, const RdrSceneFlat *sc, std::vector<unsigned char> &blob, FrameParams &P)
+{
+    std::string err;
+    const int st = rdr::pack_scene_blob(sc, blob, P, err);
+    return st == RDR_OK ? RDR_OK : fail(r, st, "%s", err.c_str());
+}
+
+int ensure_device(RdrRenderer *r) { RDR_CUDA(r, cudaSetDevice(r->device)); return RDR_OK; }
+
+int check_frame(RdrRenderer *r)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    if (!r->has_frame) return fail(r, RDR_ERR_INVALID, "no frame: call rdr_new_frame first");
+    return ensure_device(r);
+}
+
+// render_next_sample x n (cpu.rs:193-219), one launch.  Split into an asynchronous launch and a
+// finishing half so that a multi-GPU handle can start every device before waiting on any.
+int render_launch(RdrRenderer *r, uint32_t n)
+{
+    if (n == 0u) return RDR_OK;
+    r->prepare_timer.end_if_not_ended();
+    r->render_timer.start_if_not_started();
+    r->sample_timer.start();
+    FrameParams P = r->params;
+    P.sample_begin = r->sample_offset + r->sample_count;
+    P.sample_count = n;
+    P.max_bounces = r->config.max_bounces;
+    RDR_CUDA(r, cudaEventRecord(r->ev_start, r->stream));
+    RDR_CUDA(r, rdr::launch_render(P, r->use_cull, r->stream));
+    RDR_CUDA(r, cudaEventRecord(r->ev_stop, r->stream));
+    r->launches += 1;
+    return RDR_OK;
+}
+
+int render_finish(RdrRenderer *r, uint32_t n)
+{
+    if (n == 0u) return RDR_OK;
+    RDR_CUDA(r, cudaEventSynchronize(r->ev_stop));
+    float ms = 0.0f;
+    RDR_CUDA(r, cudaEventElapsedTime(&ms, r->ev_start, r->ev_stop));
+    r->device_render_ms += ms;
+    r->sample_count += n;
+    if (r->sample_count == r->config.max_sample_count) { r->render_timer.end(); r->frame_timer.end(); }
+    // sample_timer reports the mean per-sample time of the launch (Timer::end_multiple, timing.rs:113-117,
+    // as VulkanRenderer does for its single dispatch, vulkan.rs:175-179)
+    r->sample_timer.end();
+    r->sample_timer.duration_ns /= n;
+    return RDR_OK;
+}
+
+int render_more(RdrRenderer *r, uint32_t n)
+{
+    int st = render_launch(r, n);
+    return st ? st : render_finish(r, n);
+}
+
+int resolve_from(RdrRenderer *r, const rdr::f4 *src, uint32_t divisor, uint8_t *rgba8)
+{
+    if (!rgba8) return fail(r, RDR_ERR_INVALID, "output image is NULL");
+    const uint32_t n_pixels = r->params.cam.width * r->params.cam.height;
+    if (n_pixels == 0u) return RDR_OK;
+    RDR_CUDA(r, rdr::launch_resolve(src, r->d_rgba, n_pixels, (float)divisor, r->stream));
+    r->launches += 1;
+    RDR_CUDA(r, cudaMemcpyAsync(rgba8, r->d_rgba, (size_t)n_pixels * 4u, cudaMemcpyDeviceToHost, r->stream));
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RDR_OK;
+}
+
+int resolve_to_host(RdrRenderer *r, uint32_t divisor, uint8_t *rgba8) { return resolve_from(r, r->d_accum, divisor, rgba8); }
+
+}  // namespace
+
+namespace {
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+};
+}  // namespace
+
+extern "C" {
+
+const char *rdr_version(void) { return "raydar-b200 0.1 (sm_100a)"; }
+
+const char *rdr_last_error(const RdrRenderer *r) { return r ? r->last_error.c_str() : g_last_error.c_str(); }
+
+int rdr_create(const RdrConfig *config, int device, RdrRenderer **out)
+{
+    if (!out) return fail(nullptr, RDR_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, RDR_ERR_CUDA, "no CUDA device (%s); libraydar_cuda has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(nullptr, RDR_ERR_INVALID, "device %d out of range (0..%d)", device, count - 1);
+    RdrRenderer *r = new RdrRenderer();
+    r->device = device;
+    if (config) r->config = *config;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&r->ev_start)) != cudaSuccess || (e = cudaEventCreate(&r->ev_stop)) != cudaSuccess) {
+        fail(nullptr, RDR_ERR_CUDA, "CUDA init failed: %s", cudaGetErrorString(e));
+        delete r;
+        return RDR_ERR_CUDA;
+    }
+    *out = r;
+    return RDR_OK;
+}
+
+void rdr_destroy(RdrRenderer *r)
+{
+    if (!r) return;
+    if (r->multi) { rdr::multi_destroy(r->multi); r->multi = nullptr; }
+    cudaSetDevice(r->device);
+    if (r->d_blob) cudaFree(r->d_blob);
+    if (r->d_accum) cudaFree(r->d_accum);
+    if (r->d_rgba) cudaFree(r->d_rgba);
+    if (r->ev_start) cudaEventDestroy(r->ev_start);
+    if (r->ev_stop) cudaEventDestroy(r->ev_stop);
+    if (r->stream) cudaStreamDestroy(r->stream);
+    delete r;
+}
+
+int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    if (r->multi) return rdr::multi_new_frame(r, r->multi, scene);
+    int st = ensure_device(r);
+    if (st) return st;
+    // cpu.rs:135-140
+    r->frame_timer = Timer(); r->prepare_timer = Timer(); r->render_timer = Timer(); r->sample_timer = Timer();
+    r->frame_timer.start();
+    r->prepare_timer.start();
+    r->device_render_ms = 0.0;
+
+    std::vector<unsigned char> blob;
+    FrameParams P{};
+    if ((st = pack_scene(r, scene, blob, P)) != RDR_OK) { r->has_frame = false; return st; }
+
+    cudaDeviceProp prop;
+    RDR_CUDA(r, cudaGetDeviceProperties(&prop, r->device));
+    const size_t smem_need = rdr::brute_smem_bytes(P.lay, RDR_BLOCK);
+    if (smem_need > (size_t)prop.sharedMemPerBlockOptin) {
+        r->has_frame = false;
+        return fail(r, RDR_ERR_UNSUPPORTED, "scene needs %zu B of shared memory for the brute-force scan (limit %zu); "
+                    "the BVH path is required for scenes this large", smem_need, (size_t)prop.sharedMemPerBlockOptin);
+    }
+
+    if (blob.size() > r->blob_capacity) {
+        if (r->d_blob) cudaFree(r->d_blob);
+        r->d_blob = nullptr; r->blob_capacity = 0;
+        RDR_CUDA(r, cudaMalloc(&r->d_blob, blob.size()));
+        r->blob_capacity = blob.size();
+    }
+    RDR_CUDA(r, cudaMemcpyAsync(r->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, r->stream));
+
+    // frame_buffer()/blank_frame_buffer(), cpu.rs:400-423: reallocate on a resolution change, zero-fill
+    const size_t n_pixels = (size_t)scene->width * scene->height;
+    if (n_pixels > r->pixel_capacity) {
+        if (r->d_accum) cudaFree(r->d_accum);
+        if (r->d_rgba) cudaFree(r->d_rgba);
+        r->d_accum = nullptr; r->d_rgba = nullptr; r->pixel_capacity = 0;
+        RDR_CUDA(r, cudaMalloc(&r->d_accum, n_pixels * sizeof(rdr::f4)));
+        RDR_CUDA(r, cudaMalloc(&r->d_rgba, n_pixels * sizeof(uchar4)));
+        r->pixel_capacity = n_pixels;
+    }
+    if (n_pixels) RDR_CUDA(r, cudaMemsetAsync(r->d_accum, 0, n_pixels * sizeof(rdr::f4), r->stream));
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));   // blob is a local vector: finish the upload before it dies
+
+    P.blob = r->d_blob;
+    P.accum = r->d_accum;
+    P.seed_lo = (uint32_t)r->seed; P.seed_hi = (uint32_t)(r->seed >> 32);
+    r->params = P;
+    r->sample_count = 0;
+    r->has_frame = true;
+    return RDR_OK;
+}
+
+int rdr_reset_frame(RdrRenderer *r)
+{
+    if (r && r->multi) return fail(r, RDR_ERR_INVALID, "rdr_reset_frame needs a single-GPU handle");
+    int st = check_frame(r);
+    if (st) return st;
+    r->frame_timer = Timer(); r->prepare_timer = Timer(); r->render_timer = Timer(); r->sample_timer = Timer();
+    r->frame_timer.start();
+    r->prepare_timer.start();
+    r->device_render_ms = 0.0;
+    const size_t n_pixels = (size_t)r->params.cam.width * r->params.cam.height;
+    if (n_pixels) RDR_CUDA(r, cudaMemsetAsync(r->d_accum, 0, n_pixels * sizeof(rdr::f4), r->stream));
+    r->sample_count = 0;
+    return RDR_OK;
+}
+
+int rdr_render_samples(RdrRenderer *r, uint32_t n)
+{
+    if (r && r->multi) return rdr::multi_render_samples(r, r->multi, n);
+    int st = check_frame(r);
+    if (st) return st;
+    const uint32_t left = r->config.max_sample_count > r->sample_count ? r->config.max_sample_count - r->sample_count : 0u;
+    return render_more(r, std::min(n, left));
+}
+
+int rdr_render_sample(RdrRenderer *r, uint8_t *rgba8, int *produced)
+{
+    if (produced) *produced = 0;
+    if (r && r->multi) return rdr::multi_render_sample(r, r->multi, rgba8, produced);
+    int st = check_frame(r);
+    if (st) return st;
+    if (r->sample_count >= r->config.max_sample_count) return RDR_OK;      // `None`, cpu.rs:143-145
+    if ((st = render_more(r, 1u)) != RDR_OK) return st;
+    if ((st = resolve_to_host(r, r->sample_count, rgba8)) != RDR_OK) return st;
+    if (produced) *produced = 1;
+    return RDR_OK;
+}
+
+int rdr_render_frame(RdrRenderer *r, const RdrSceneFlat *scene, uint8_t *rgba8)
+{
+    if (r && r->multi) return rdr::multi_render_frame(r, r->multi, scene, rgba8);
+    int st = rdr_new_frame(r, scene);
+    if (st) return st;
+    if (r->config.max_sample_count > 0u && (st = render_more(r, r->config.max_sample_count)) != RDR_OK) return st;
+    // max_sample_count == 0: the reference divides by zero -> NaN -> 0 for every channel (cpu.rs:224)
+    return resolve_to_host(r, r->sample_count, rgba8);
+}
+
+int rdr_resolve(RdrRenderer *r, uint32_t divisor, uint8_t *rgba8)
+{
+    if (r && r->multi) return rdr::multi_resolve(r, r->multi, divisor, rgba8);
+    int st = check_frame(r);
+    if (st) return st;
+    return resolve_to_host(r, divisor ? divisor : r->sample_count, rgba8);
+}
+
+int rdr_read_accum(RdrRenderer *r, float *dst)
+{
+    if (r && r->multi) return rdr::multi_read_accum(r, r->multi, dst);
+    int st = check_frame(r);
+    if (st) return st;
+    if (!dst) return fail(r, RDR_ERR_INVALID, "dst is NULL");
+    const size_t n_pixels = (size_t)r->params.cam.width * r->params.cam.height;
+    RDR_CUDA(r, cudaMemcpyAsync(dst, r->d_accum, n_pixels * sizeof(rdr::f4), cudaMemcpyDeviceToHost, r->stream));
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RDR_OK;
+}
+
+int rdr_accum_device_ptr(RdrRenderer *r, void **ptr, size_t *bytes)
+{
+    int st = check_frame(r);
+    if (st) return st;
+    if (r->multi) return fail(r, RDR_ERR_INVALID, "not available on a multi-GPU handle");
+    if (ptr) *ptr = r->d_accum;
+    if (bytes) *bytes = (size_t)r->params.cam.width * r->params.cam.height * sizeof(rdr::f4);
+    return RDR_OK;
+}
+
+int rdr_stream(RdrRenderer *r, void **cuda_stream)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    if (cuda_stream) *cuda_stream = (void *)r->stream;
+    return RDR_OK;
+}
+
+int rdr_synchronize(RdrRenderer *r)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    if (r->multi) return rdr::multi_synchronize(r, r->multi);
+    int st = ensure_device(r);
+    if (st) return st;
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RDR_OK;
+}
+
+uint64_t rdr_launch_count(const RdrRenderer *r) { return r ? (r->multi ? rdr::multi_launch_count(r->multi) : r->launches) : 0; }
+
+int rdr_profiler(const RdrRenderer *r, RdrProfiler *out)
+{
+    if (!r || !out) return fail(nullptr, RDR_ERR_INVALID, "NULL argument");
+    if (r->multi) return rdr::multi_profiler(r->multi, out);
+    out->frame_ns = r->frame_timer.duration_ns; out->has_frame = r->frame_timer.has_duration;
+    out->sample_ns = r->sample_timer.duration_ns; out->has_sample = r->sample_timer.has_duration;
+    out->prepare_ns = r->prepare_timer.duration_ns; out->has_prepare = r->prepare_timer.has_duration;
+    out->render_ns = r->render_timer.duration_ns; out->has_render = r->render_timer.has_duration;
+    out->device_render_ms = r->device_render_ms;
+    return RDR_OK;
+}
+
+uint32_t rdr_sample_count(const RdrRenderer *r) { return r ? (r->multi ? rdr::multi_sample_count(r->multi) : r->sample_count) : 0u; }
+uint32_t rdr_max_sample_count(const RdrRenderer *r) { return r ? r->config.max_sample_count : 0u; }
+uint32_t rdr_max_bounces(const RdrRenderer *r) { return r ? r->config.max_bounces : 0u; }
+
+int rdr_set_max_sample_count(RdrRenderer *r, uint32_t count)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    r->config.max_sample_count = count;
+    if (r->multi) rdr::multi_set_config(r->multi, r->config);
+    return RDR_OK;
+}
+
+int rdr_set_max_bounces(RdrRenderer *r, uint32_t bounces)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    r->config.max_bounces = bounces;
+    if (r->multi) rdr::multi_set_config(r->multi, r->config);
+    return RDR_OK;
+}
+
+int rdr_set_seed(RdrRenderer *r, uint64_t seed)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    r->seed = seed;
+    if (r->multi) rdr::multi_set_seed(r->multi, seed);
+    return RDR_OK;
+}
+
+int rdr_set_sample_offset(RdrRenderer *r, uint32_t first_sample)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    if (r->multi) return fail(r, RDR_ERR_INVALID, "a multi-GPU handle assigns sample ranges itself");
+    r->sample_offset = first_sample;
+    return RDR_OK;
+}
+
+int rdr_set_accel(RdrRenderer *r, int accel)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    if (accel < RDR_ACCEL_AUTO || accel > RDR_ACCEL_BVH) return fail(r, RDR_ERR_INVALID, "unknown accel %d", accel);
+    r->accel = accel;
+    return RDR_OK;
+}
+
+// test hook (not in the public header): 0 = run the exact test on every primitive (no conservative cull)
+int rdr_debug_set_cull(RdrRenderer *r, int enabled)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    r->use_cull = enabled != 0;
+    return RDR_OK;
+}
+
+// ---- parity / debug ----------------------------------------------------------------------------------
+int rdr_first_hit(RdrRenderer *r, int32_t *ids, float *t)
+{
+    int st = check_frame(r);
+    if (st) return st;
+    if (r->multi) return fail(r, RDR_ERR_INVALID, "debug entry points need a single-GPU handle");
+    const size_t n = (size_t)r->params.cam.width * r->params.cam.height;
+    DevBuf<int32_t> d_ids; DevBuf<float> d_t;
+    RDR_CUDA(r, d_ids.alloc(n)); RDR_CUDA(r, d_t.alloc(n));
+    RDR_CUDA(r, rdr::launch_first_hit(r->params, r->use_cull, d_ids.p, d_t.p, r->stream));
+    r->launches += 1;
+    if (ids) RDR_CUDA(r, cudaMemcpyAsync(ids, d_ids.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, r->stream));
+    if (t) RDR_CUDA(r, cudaMemcpyAsync(t, d_t.p, n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RDR_OK;
+}
+
+int rdr_trace_path(RdrRenderer *r, uint32_t x, uint32_t y, uint32_t sample, RdrPathStep *steps, uint32_t capacity,
+                   uint32_t *n_steps, float rgba[4])
+{
+    int st = check_frame(r);
+    if (st) return st;
+    if (r->multi) return fail(r, RDR_ERR_INVALID, "debug entry points need a single-GPU handle");
+    if (x >= r->params.cam.width || y >= r->params.cam.height) return fail(r, RDR_ERR_INVALID, "pixel (%u,%u) outside the image", x, y);
+    DevBuf<RdrPathStep> d_steps; DevBuf<uint32_t> d_n; DevBuf<float> d_rgba;
+    RDR_CUDA(r, d_steps.alloc(capacity)); RDR_CUDA(r, d_n.alloc(1)); RDR_CUDA(r, d_rgba.alloc(4));
+    FrameParams P = r->params;
+    P.max_bounces = r->config.max_bounces;
+    RDR_CUDA(r, rdr::launch_trace_path(P, r->use_cull, x, y, sample, d_steps.p, capacity, d_n.p, d_rgba.p, r->stream));
+    r->launches += 1;
+    uint32_t n = 0;
+    RDR_CUDA(r, cudaMemcpyAsync(&n, d_n.p, sizeof n, cudaMemcpyDeviceToHost, r->stream));
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    if (steps && n) RDR_CUDA(r, cudaMemcpy(steps, d_steps.p, n * sizeof(RdrPathStep), cudaMemcpyDeviceToHost));
+    if (rgba) RDR_CUDA(r, cudaMemcpy(rgba, d_rgba.p, 4 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (n_steps) *n_steps = n;
+    return RDR_OK;
+}
+
+static int kat_hit(RdrRenderer *r, bool sphere, uint32_t n, const float *rays, const float *prims, float *t, int32_t *hit)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    int st = ensure_device(r);
+    if (st) return st;
+    DevBuf<float> d_rays, d_prims, d_t; DevBuf<int32_t> d_hit;
+    RDR_CUDA(r, d_rays.alloc(6 * (size_t)n)); RDR_CUDA(r, d_prims.alloc(4 * (size_t)n));
+    RDR_CUDA(r, d_t.alloc(n)); RDR_CUDA(r, d_hit.alloc(n));
+    RDR_CUDA(r, cudaMemcpyAsync(d_rays.p, rays, 6 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+    RDR_CUDA(r, cudaMemcpyAsync(d_prims.p, prims, 4 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+    RDR_CUDA(r, rdr::launch_kat_hit(sphere, n, d_rays.p, d_prims.p, d_t.p, d_hit.p, r->stream));
+    r->launches += 1;
+    RDR_CUDA(r, cudaMemcpyAsync(t, d_t.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    RDR_CUDA(r, cudaMemcpyAsync(hit, d_hit.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, r->stream));
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RDR_OK;
+}
+
+int rdr_kat_hit_sphere(RdrRenderer *r, uint32_t n, const float *rays, const float *spheres, float *t, int32_t *hit)
+{
+    return kat_hit(r, true, n, rays, spheres, t, hit);
+}
+
+int rdr_kat_hit_cube(RdrRenderer *r, uint32_t n, const float *rays, const float *cubes, float *t, int32_t *hit)
+{
+    return kat_hit(r, false, n, rays, cubes, t, hit);
+}
+
+int rdr_kat_trace(RdrRenderer *r, uint32_t n, const float *rays, int32_t *ids, float *t)
+{
+    int st = check_frame(r);
+    if (st) return st;
+    if (r->multi) return fail(r, RDR_ERR_INVALID, "debug entry points need a single-GPU handle");
+    DevBuf<float> d_rays, d_t; DevBuf<int32_t> d_ids;
+    RDR_CUDA(r, d_rays.alloc(6 * (size_t)n)); RDR_CUDA(r, d_t.alloc(n)); RDR_CUDA(r, d_ids.alloc(n));
+    RDR_CUDA(r, cudaMemcpyAsync(d_rays.p, rays, 6 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+    RDR_CUDA(r, rdr::launch_kat_trace(r->params, r->use_cull, n, d_rays.p, d_ids.p, d_t.p, r->stream));
+    r->launches += 1;
+    RDR_CUDA(r, cudaMemcpyAsync(ids, d_ids.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, r->stream));
+    RDR_CUDA(r, cudaMemcpyAsync(t, d_t.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RDR_OK;
+}
+
+int rdr_kat_camera_rays(RdrRenderer *r, uint32_t n, const uint32_t *xy, float *rays)
+{
+    int st = check_frame(r);
+    if (st) return st;
+    DevBuf<uint32_t> d_xy; DevBuf<float> d_rays;
+    RDR_CUDA(r, d_xy.alloc(2 * (size_t)n)); RDR_CUDA(r, d_rays.alloc(6 * (size_t)n));
+    RDR_CUDA(r, cudaMemcpyAsync(d_xy.p, xy, 2 * (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, r->stream));
+    RDR_CUDA(r, rdr::launch_kat_camera_rays(r->params, n, d_xy.p, d_rays.p, r->stream));
+    r->launches += 1;
+    RDR_CUDA(r, cudaMemcpyAsync(rays, d_rays.p, 6 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RDR_OK;
+}
+
+int rdr_kat_rng(RdrRenderer *r, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block, uint32_t out[4])
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    int st = ensure_device(r);
+    if (st) return st;
+    DevBuf<uint32_t> d_out;
+    RDR_CUDA(r, d_out.alloc(4));
+    RDR_CUDA(r, rdr::launch_kat_rng((uint32_t)seed, (uint32_t)(seed >> 32), pixel, sample, bounce, block, d_out.p, r->stream));
+    r->launches += 1;
+    RDR_CUDA(r, cudaMemcpyAsync(out, d_out.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, r->stream));
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RDR_OK;
+}
+
+}  // extern "C"
+
+// ---- hooks used by rdr_multi.cpp ------------------------------------------------------------------------
+namespace rdr {
+int api_fail(RdrRenderer *r, int status, const char *msg) { return fail(r, status, "%s", msg); }
+rdr::f4 *api_accum(RdrRenderer *r) { return r->d_accum; }
+cudaStream_t api_stream(RdrRenderer *r) { return r->stream; }
+int api_device(RdrRenderer *r) { return r->device; }
+uint32_t api_pixels(RdrRenderer *r) { return r->params.cam.width * r->params.cam.height; }
+double api_device_ms(RdrRenderer *r) { return r->device_render_ms; }
+uint32_t api_samples_left(RdrRenderer *r) { return r->config.max_sample_count > r->sample_count ? r->config.max_sample_count - r->sample_count : 0u; }
+int api_render_launch(RdrRenderer *r, uint32_t n) { int st = check_frame(r); return st ? st : render_launch(r, n); }
+int api_render_finish(RdrRenderer *r, uint32_t n) { return render_finish(r, n); }
+int api_resolve_from(RdrRenderer *r, const rdr::f4 *src, uint32_t divisor, uint8_t *rgba8) { int st = check_frame(r); return st ? st : resolve_from(r, src, divisor, rgba8); }
+void api_attach_multi(RdrRenderer *r, MultiGpu *m) { r->multi = m; }
+}  // namespace rdr

@@ -1,0 +1,248 @@
+// rdr_kernels.cu -- sm_100a kernels of the path-tracing sample loop.
+//
+//   render_kernel      render_next_sample x N (cpu.rs:193-219) fused with per_pixel (cpu.rs:233-342):
+//                      one lane owns one pixel, loops over its samples and bounces, accumulates in
+//                      registers and issues one 16-byte load and one 16-byte store of the accumulator.
+//   resolve_kernel     print_frame_buffer (cpu.rs:221-230)
+//   first_hit_kernel   debug/parity: primary-ray nearest hit per pixel
+//   trace_path_kernel  debug/parity: one path with every bounce recorded
+//   kat_* kernels      per-function known-answer entry points
+#include <cuda_runtime.h>
+
+#include "raydar_cuda.h"
+#include "rdr_device.cuh"
+#include "rdr_launch.h"
+
+namespace rdr {
+
+// ---- the sample loop: one lane = one pixel (see render_pixel in rdr_trace.cuh) -----------------------
+template <bool USE_CULL>
+__global__ void __launch_bounds__(RDR_BLOCK, 2) render_kernel(const __grid_constant__ FrameParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
+    const SceneView S = scene_view(smem, P.lay);
+    uint32_t *masks = mask_base(smem, P.lay) + threadIdx.x;
+    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel >= P.cam.width * P.cam.height) return;
+    // one 16-byte load and one 16-byte store of the accumulator per pixel per launch, coalesced
+    P.accum[pixel] = render_pixel<USE_CULL>(P, S, masks, blockDim.x, pixel, P.accum[pixel]);
+}
+
+// ---- print_frame_buffer (cpu.rs:221-230): one uchar4 (32-bit) store per pixel ------------------------
+__global__ void __launch_bounds__(256) resolve_kernel(const f4 *__restrict__ accum, uchar4 *__restrict__ out,
+                                                      uint32_t n_pixels, float divisor)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    const f4 a = accum[i];
+    uchar4 o;
+    o.x = (unsigned char)quantise(a.x, divisor); o.y = (unsigned char)quantise(a.y, divisor);
+    o.z = (unsigned char)quantise(a.z, divisor); o.w = (unsigned char)quantise(a.w, divisor);
+    out[i] = o;
+}
+
+// ---- debug / parity kernels ---------------------------------------------------------------------------
+template <bool USE_CULL>
+__global__ void __launch_bounds__(RDR_BLOCK, 2) first_hit_kernel(const __grid_constant__ FrameParams P,
+                                                                int32_t *__restrict__ ids, float *__restrict__ ts)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
+    const SceneView S = scene_view(smem, P.lay);
+    uint32_t *masks = mask_base(smem, P.lay) + threadIdx.x;
+    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel >= P.cam.width * P.cam.height) return;
+    const v3 o = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
+    const v3 d = camera_ray_dir(P.cam, pixel % P.cam.width, pixel / P.cam.width);
+    const Hit h = trace_brute<USE_CULL>(S, P.cull, masks, blockDim.x, o, d);
+    ids[pixel] = h.idx;
+    ts[pixel] = h.idx >= 0 ? h.t : 0.0f;
+}
+
+template <bool USE_CULL>
+__global__ void __launch_bounds__(RDR_BLOCK, 2) kat_trace_kernel(const __grid_constant__ FrameParams P, uint32_t n,
+                                                                const float *__restrict__ rays,
+                                                                int32_t *__restrict__ ids, float *__restrict__ ts)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
+    const SceneView S = scene_view(smem, P.lay);
+    uint32_t *masks = mask_base(smem, P.lay) + threadIdx.x;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const v3 o = mk3(rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]);
+    const v3 d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+    const Hit h = trace_brute<USE_CULL>(S, P.cull, masks, blockDim.x, o, d);
+    ids[i] = h.idx;
+    ts[i] = h.idx >= 0 ? h.t : 0.0f;
+}
+
+// one path, one thread (block of 32 so the staging code is shared; lane 0 walks the path)
+template <bool USE_CULL>
+__global__ void __launch_bounds__(RDR_BLOCK, 2) trace_path_kernel(const __grid_constant__ FrameParams P, uint32_t x, uint32_t y,
+                                                                 uint32_t sample, RdrPathStep *__restrict__ steps,
+                                                                 uint32_t capacity, uint32_t *__restrict__ n_steps,
+                                                                 float *__restrict__ rgba)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
+    const SceneView S = scene_view(smem, P.lay);
+    uint32_t *masks = mask_base(smem, P.lay) + threadIdx.x;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    *n_steps = trace_path_lane<USE_CULL>(P, S, masks, blockDim.x, x, y, sample, steps, capacity, rgba);
+}
+
+__global__ void kat_hit_sphere_kernel(uint32_t n, const float *__restrict__ rays, const float *__restrict__ prims,
+                                      float *__restrict__ t_out, int32_t *__restrict__ hit_out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t = 0.0f;
+    const bool h = hit_sphere_exact(mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]),
+                                    mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]),
+                                    mk3(prims[4 * i], prims[4 * i + 1], prims[4 * i + 2]), prims[4 * i + 3], &t);
+    hit_out[i] = h ? 1 : 0;
+    t_out[i] = h ? t : 0.0f;
+}
+
+__global__ void kat_hit_cube_kernel(uint32_t n, const float *__restrict__ rays, const float *__restrict__ prims,
+                                    float *__restrict__ t_out, int32_t *__restrict__ hit_out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t = 0.0f;
+    const bool h = hit_cube_exact(mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]),
+                                  mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]),
+                                  mk3(prims[4 * i], prims[4 * i + 1], prims[4 * i + 2]), prims[4 * i + 3], &t);
+    hit_out[i] = h ? 1 : 0;
+    t_out[i] = h ? t : 0.0f;
+}
+
+__global__ void kat_camera_rays_kernel(const __grid_constant__ FrameParams P, uint32_t n, const uint32_t *__restrict__ xy,
+                                       float *__restrict__ rays)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const v3 d = camera_ray_dir(P.cam, xy[2 * i], xy[2 * i + 1]);
+    rays[6 * i + 0] = P.cam.pos[0]; rays[6 * i + 1] = P.cam.pos[1]; rays[6 * i + 2] = P.cam.pos[2];
+    rays[6 * i + 3] = d.x; rays[6 * i + 4] = d.y; rays[6 * i + 5] = d.z;
+}
+
+__global__ void kat_rng_kernel(uint32_t seed_lo, uint32_t seed_hi, uint32_t pixel, uint32_t sample, uint32_t bounce,
+                               uint32_t block, uint32_t *__restrict__ out)
+{
+    const u4 r = rng_block(seed_lo, seed_hi, pixel, sample, bounce, block);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// ---- launch wrappers (called from rdr_api.cpp) ---------------------------------------------------------
+static inline uint32_t max_chunks(const SceneLayout &L) { return (L.ns_pad > L.nc_pad ? L.ns_pad : L.nc_pad) / 32u; }
+
+size_t brute_smem_bytes(const SceneLayout &L, uint32_t block)
+{
+    return (size_t)L.blob_bytes + 16u + (size_t)(max_chunks(L) ? max_chunks(L) : 1u) * block * sizeof(uint32_t);
+}
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+cudaError_t launch_render(const FrameParams &P, bool use_cull, cudaStream_t stream)
+{
+    const uint32_t n_pixels = P.cam.width * P.cam.height;
+    if (n_pixels == 0u) return cudaSuccess;
+    const size_t smem = brute_smem_bytes(P.lay, RDR_BLOCK);
+    const uint32_t grid = (n_pixels + RDR_BLOCK - 1u) / RDR_BLOCK;
+    cudaError_t e;
+    if (use_cull) {
+        if ((e = set_smem(render_kernel<true>, smem)) != cudaSuccess) return e;
+        render_kernel<true><<<grid, RDR_BLOCK, smem, stream>>>(P);
+    } else {
+        if ((e = set_smem(render_kernel<false>, smem)) != cudaSuccess) return e;
+        render_kernel<false><<<grid, RDR_BLOCK, smem, stream>>>(P);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve(const f4 *accum, uchar4 *out, uint32_t n_pixels, float divisor, cudaStream_t stream)
+{
+    if (n_pixels == 0u) return cudaSuccess;
+    resolve_kernel<<<(n_pixels + 255u) / 256u, 256, 0, stream>>>(accum, out, n_pixels, divisor);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_first_hit(const FrameParams &P, bool use_cull, int32_t *ids, float *ts, cudaStream_t stream)
+{
+    const uint32_t n_pixels = P.cam.width * P.cam.height;
+    if (n_pixels == 0u) return cudaSuccess;
+    const size_t smem = brute_smem_bytes(P.lay, RDR_BLOCK);
+    const uint32_t grid = (n_pixels + RDR_BLOCK - 1u) / RDR_BLOCK;
+    cudaError_t e;
+    if (use_cull) {
+        if ((e = set_smem(first_hit_kernel<true>, smem)) != cudaSuccess) return e;
+        first_hit_kernel<true><<<grid, RDR_BLOCK, smem, stream>>>(P, ids, ts);
+    } else {
+        if ((e = set_smem(first_hit_kernel<false>, smem)) != cudaSuccess) return e;
+        first_hit_kernel<false><<<grid, RDR_BLOCK, smem, stream>>>(P, ids, ts);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kat_trace(const FrameParams &P, bool use_cull, uint32_t n, const float *rays, int32_t *ids, float *ts,
+                             cudaStream_t stream)
+{
+    if (n == 0u) return cudaSuccess;
+    const size_t smem = brute_smem_bytes(P.lay, RDR_BLOCK);
+    const uint32_t grid = (n + RDR_BLOCK - 1u) / RDR_BLOCK;
+    cudaError_t e;
+    if (use_cull) {
+        if ((e = set_smem(kat_trace_kernel<true>, smem)) != cudaSuccess) return e;
+        kat_trace_kernel<true><<<grid, RDR_BLOCK, smem, stream>>>(P, n, rays, ids, ts);
+    } else {
+        if ((e = set_smem(kat_trace_kernel<false>, smem)) != cudaSuccess) return e;
+        kat_trace_kernel<false><<<grid, RDR_BLOCK, smem, stream>>>(P, n, rays, ids, ts);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_path(const FrameParams &P, bool use_cull, uint32_t x, uint32_t y, uint32_t sample,
+                              RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float *rgba, cudaStream_t stream)
+{
+    const size_t smem = brute_smem_bytes(P.lay, 32);
+    cudaError_t e;
+    if (use_cull) {
+        if ((e = set_smem(trace_path_kernel<true>, smem)) != cudaSuccess) return e;
+        trace_path_kernel<true><<<1, 32, smem, stream>>>(P, x, y, sample, steps, capacity, n_steps, rgba);
+    } else {
+        if ((e = set_smem(trace_path_kernel<false>, smem)) != cudaSuccess) return e;
+        trace_path_kernel<false><<<1, 32, smem, stream>>>(P, x, y, sample, steps, capacity, n_steps, rgba);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kat_hit(bool sphere, uint32_t n, const float *rays, const float *prims, float *t, int32_t *hit, cudaStream_t stream)
+{
+    if (n == 0u) return cudaSuccess;
+    if (sphere) kat_hit_sphere_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(n, rays, prims, t, hit);
+    else kat_hit_cube_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(n, rays, prims, t, hit);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kat_camera_rays(const FrameParams &P, uint32_t n, const uint32_t *xy, float *rays, cudaStream_t stream)
+{
+    if (n == 0u) return cudaSuccess;
+    kat_camera_rays_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(P, n, xy, rays);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kat_rng(uint32_t seed_lo, uint32_t seed_hi, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block,
+                           uint32_t *out, cudaStream_t stream)
+{
+    kat_rng_kernel<<<1, 1, 0, stream>>>(seed_lo, seed_hi, pixel, sample, bounce, block, out);
+    return cudaGetLastError();
+}
+
+}  // namespace rdr

@@ -1,0 +1,29 @@
+// rdr_launch.h -- host-callable launch wrappers implemented in rdr_kernels.cu
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "raydar_cuda.h"
+
+#define RDR_BLOCK 256u
+
+namespace rdr {
+
+struct FrameParams;
+struct SceneLayout;
+struct f4;
+
+size_t brute_smem_bytes(const SceneLayout &L, uint32_t block);
+cudaError_t launch_render(const FrameParams &P, bool use_cull, cudaStream_t stream);
+cudaError_t launch_resolve(const f4 *accum, uchar4 *out, uint32_t n_pixels, float divisor, cudaStream_t stream);
+cudaError_t launch_first_hit(const FrameParams &P, bool use_cull, int32_t *ids, float *ts, cudaStream_t stream);
+cudaError_t launch_kat_trace(const FrameParams &P, bool use_cull, uint32_t n, const float *rays, int32_t *ids, float *ts, cudaStream_t stream);
+cudaError_t launch_trace_path(const FrameParams &P, bool use_cull, uint32_t x, uint32_t y, uint32_t sample,
+                              RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float *rgba, cudaStream_t stream);
+cudaError_t launch_kat_hit(bool sphere, uint32_t n, const float *rays, const float *prims, float *t, int32_t *hit, cudaStream_t stream);
+cudaError_t launch_kat_camera_rays(const FrameParams &P, uint32_t n, const uint32_t *xy, float *rays, cudaStream_t stream);
+cudaError_t launch_kat_rng(uint32_t seed_lo, uint32_t seed_hi, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block,
+                           uint32_t *out, cudaStream_t stream);
+
+}  // namespace rdr

@@ -1,0 +1,50 @@
+// rdr_layout.h -- scene blob layout and kernel parameters (plain structs shared by host packing,
+// the kernels and the host-simulation test build).
+//
+// HBM / shared-memory layout.  The host packs the frame's scene into ONE contiguous blob
+// (16-byte aligned sections) that every CTA stages into shared memory with a single
+// cp.async.bulk (TMA 1-D bulk copy, SASS UBLKCP) completing on an mbarrier:
+//
+//   sphere_cull  f4[ns_pad]   (cx, cy, cz, r^2)             conservative test operands
+//   cube_cull    f4[nc_pad]   (cx, cy, cz, side/2 + pad)
+//   sphere_geom  f4[ns_pad]   (cx, cy, cz, radius)          exact test operands, list order
+//   cube_geom    f4[nc_pad]   (cx, cy, cz, side_length)
+//   obj_geom     f4[n]        (cx, cy, cz, size)            by ORIGINAL object index
+//   material     f4[3*n]      (albedo.xyz, roughness) (emission.xyz, emission_strength)
+//                             (metallic, transmission, ior, kind as bits)
+//   sphere_idx   u32[ns_pad]  list position -> original object index
+//   cube_idx     u32[nc_pad]
+//
+// ns_pad / nc_pad are the list lengths rounded up to 32 (one candidate-mask word per chunk).
+// Every lane of a warp reads the same primitive at the same time, so all shared-memory reads in
+// the scan are single-wavefront broadcasts.
+#pragma once
+
+#include "rdr_core.cuh"
+
+namespace rdr {
+
+struct SceneLayout {
+    uint32_t n_objects, n_spheres, n_cubes;
+    uint32_t ns_pad, nc_pad;
+    uint32_t off_sphere_cull, off_cube_cull, off_sphere_geom, off_cube_geom;
+    uint32_t off_obj_geom, off_material, off_sphere_idx, off_cube_idx;
+    uint32_t blob_bytes;                 // multiple of 16
+};
+
+struct FrameParams {
+    Camera cam;
+    World world;
+    CullConsts cull;
+    SceneLayout lay;
+    const unsigned char *blob;           // device copy of the packed scene
+    f4 *accum;                           // W*H float RGBA accumulator (row-major, top row first)
+    uint32_t seed_lo, seed_hi;
+    uint32_t max_bounces;
+    uint32_t sample_begin;               // global index of the first sample of this launch
+    uint32_t sample_count;               // samples per pixel in this launch
+};
+
+struct Hit { int idx; float t; };
+
+}  // namespace rdr

@@ -1,0 +1,107 @@
+// rdr_pack.h -- host-side packing of a borrowed RdrSceneFlat into the blob layout of rdr_layout.h,
+// plus the scene-wide constants of the conservative cull tests (rdr_core.cuh).  Pure host C++.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "raydar_cuda.h"
+#include "rdr_layout.h"
+
+namespace rdr {
+
+inline uint32_t round_up_u32(uint32_t v, uint32_t m) { return (v + m - 1u) / m * m; }
+
+// returns RDR_OK or an RdrStatus with `err` set
+inline int pack_scene_blob(const RdrSceneFlat *sc, std::vector<unsigned char> &blob, FrameParams &P, std::string &err)
+{
+    if (!sc) { err = "scene is NULL"; return RDR_ERR_INVALID; }
+    if (sc->n_objects && (!sc->kind || !sc->geom || !sc->material)) { err = "scene arrays are NULL"; return RDR_ERR_INVALID; }
+    if (sc->world_kind == RDR_WORLD_TRANSPARENT) {
+        err = "World::Transparent is not supported (todo!() in the reference, scene/world.rs:32)";
+        return RDR_ERR_UNSUPPORTED;
+    }
+    if (sc->world_kind > RDR_WORLD_TRANSPARENT) { err = "unknown world kind"; return RDR_ERR_INVALID; }
+    if ((uint64_t)sc->width * sc->height > 0x7fffffffull) { err = "resolution too large"; return RDR_ERR_INVALID; }
+
+    const uint32_t n = sc->n_objects;
+    std::vector<uint32_t> spheres, cubes;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (sc->kind[i] == RDR_SPHERE) spheres.push_back(i);
+        else if (sc->kind[i] == RDR_CUBE) cubes.push_back(i);
+        else { err = "object " + std::to_string(i) + " has unknown kind " + std::to_string(sc->kind[i]); return RDR_ERR_INVALID; }
+    }
+
+    // scene bounds for the cull margins (rdr_core.cuh): |c|_inf + size over objects, camera position
+    float obj_bound = 0.0f, q_max = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float *g = sc->geom + 4 * (size_t)i;
+        const float cm = std::max(std::fabs(g[0]), std::max(std::fabs(g[1]), std::fabs(g[2])));
+        obj_bound = std::max(obj_bound, cm + std::fabs(g[3]));
+        if (sc->kind[i] == RDR_SPHERE)
+            q_max = std::max(q_max, 2.0f * (g[0] * g[0] + g[1] * g[1] + g[2] * g[2]) + g[3] * g[3]);
+    }
+    const float cam_bound = std::max(std::fabs(sc->cam_pos[0]), std::max(std::fabs(sc->cam_pos[1]), std::fabs(sc->cam_pos[2])));
+    const float origin_bound = 1.001f * std::max(obj_bound, cam_bound) + 1e-3f;
+    const float cube_pad = 3.814697265625e-06f * (origin_bound + obj_bound);   // 2^-18 * B
+
+    SceneLayout L{};
+    L.n_objects = n; L.n_spheres = (uint32_t)spheres.size(); L.n_cubes = (uint32_t)cubes.size();
+    L.ns_pad = round_up_u32(L.n_spheres, 32u); L.nc_pad = round_up_u32(L.n_cubes, 32u);
+    uint32_t off = 0;
+    L.off_sphere_cull = off; off += 16u * L.ns_pad;
+    L.off_cube_cull = off;   off += 16u * L.nc_pad;
+    L.off_sphere_geom = off; off += 16u * L.ns_pad;
+    L.off_cube_geom = off;   off += 16u * L.nc_pad;
+    L.off_obj_geom = off;    off += 16u * n;
+    L.off_material = off;    off += 48u * n;
+    L.off_sphere_idx = off;  off += 4u * L.ns_pad;
+    L.off_cube_idx = off;    off += 4u * L.nc_pad;
+    L.blob_bytes = std::max(16u, round_up_u32(off, 16u));
+
+    blob.assign(L.blob_bytes, 0);
+    auto quad = [&](uint32_t base, uint32_t i) { return reinterpret_cast<float *>(blob.data() + base) + 4 * (size_t)i; };
+    for (uint32_t j = 0; j < L.n_spheres; ++j) {
+        const float *g = sc->geom + 4 * (size_t)spheres[j];
+        float *c = quad(L.off_sphere_cull, j), *e = quad(L.off_sphere_geom, j);
+        c[0] = g[0]; c[1] = g[1]; c[2] = g[2]; c[3] = g[3] * g[3];
+        e[0] = g[0]; e[1] = g[1]; e[2] = g[2]; e[3] = g[3];
+        reinterpret_cast<uint32_t *>(blob.data() + L.off_sphere_idx)[j] = spheres[j];
+    }
+    for (uint32_t j = 0; j < L.n_cubes; ++j) {
+        const float *g = sc->geom + 4 * (size_t)cubes[j];
+        float *c = quad(L.off_cube_cull, j), *e = quad(L.off_cube_geom, j);
+        c[0] = g[0]; c[1] = g[1]; c[2] = g[2]; c[3] = std::fabs(g[3]) * 0.5f + cube_pad;
+        e[0] = g[0]; e[1] = g[1]; e[2] = g[2]; e[3] = g[3];
+        reinterpret_cast<uint32_t *>(blob.data() + L.off_cube_idx)[j] = cubes[j];
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const float *g = sc->geom + 4 * (size_t)i;
+        const float *m = sc->material + RDR_MAT_STRIDE * (size_t)i;
+        float *og = quad(L.off_obj_geom, i);
+        og[0] = g[0]; og[1] = g[1]; og[2] = g[2]; og[3] = g[3];
+        float *mm = reinterpret_cast<float *>(blob.data() + L.off_material) + 12 * (size_t)i;
+        mm[0] = m[0]; mm[1] = m[1]; mm[2] = m[2]; mm[3] = m[3];          // albedo, roughness
+        mm[4] = m[5]; mm[5] = m[6]; mm[6] = m[7]; mm[7] = m[8];          // emission colour, strength
+        mm[8] = m[4]; mm[9] = m[9]; mm[10] = m[10];                      // metallic, transmission, ior
+        const uint32_t kind_bits = sc->kind[i];
+        memcpy(&mm[11], &kind_bits, 4);
+    }
+
+    memcpy(P.cam.inv_proj, sc->inv_proj, sizeof P.cam.inv_proj);
+    memcpy(P.cam.inv_view, sc->inv_view, sizeof P.cam.inv_view);
+    memcpy(P.cam.pos, sc->cam_pos, sizeof P.cam.pos);
+    P.cam.width = sc->width; P.cam.height = sc->height;
+    P.world.kind = sc->world_kind;
+    memcpy(P.world.a, sc->world_a, sizeof P.world.a);
+    memcpy(P.world.b, sc->world_b, sizeof P.world.b);
+    P.cull.sphere_q_max = q_max;
+    P.cull.origin_bound = origin_bound;
+    P.lay = L;
+    return RDR_OK;
+}
+
+}  // namespace rdr

@@ -1,0 +1,208 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE: compiles the product's __host__ __device__ per-lane code
+// (raydar_b200/csrc/rdr_core.cuh, rdr_trace.cuh, rdr_pack.h) for the CPU so that the logic the
+// CUDA kernels run -- conservative cull + exact test, winner selection, sample-refill loop,
+// scatter -- can be checked against the oracle on a machine without a GPU.
+// Built by tests/conftest.py with g++ -O2 -ffp-contract=off -mfma (explicit fma() calls map to one
+// hardware FMA exactly as FFMA does on the device; nothing else may be contracted).
+// libraydar_cuda.so never contains or calls this file.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "raydar_cuda.h"
+#include "rdr_pack.h"
+#include "rdr_trace.cuh"
+
+using namespace rdr;
+
+namespace {
+
+struct Packed {
+    std::vector<unsigned char> storage;
+    unsigned char *blob = nullptr;
+    FrameParams P{};
+    SceneView S{};
+    std::vector<uint32_t> masks;
+    int status = RDR_OK;
+    explicit Packed(const RdrSceneFlat *sc)
+    {
+        std::vector<unsigned char> tmp;
+        std::string err;
+        status = pack_scene_blob(sc, tmp, P, err);
+        if (status != RDR_OK) return;
+        storage.resize(tmp.size() + 16);
+        blob = storage.data();
+        while (reinterpret_cast<uintptr_t>(blob) % 16) ++blob;
+        memcpy(blob, tmp.data(), tmp.size());
+        P.blob = blob;
+        S = scene_view(blob, P.lay);
+        masks.resize(std::max(P.lay.ns_pad, P.lay.nc_pad) / 32 + 1);
+    }
+};
+
+void merge(TraceStats *dst, const TraceStats &src)
+{
+    if (!dst) return;
+    dst->traces += src.traces; dst->sphere_exact += src.sphere_exact; dst->cube_exact += src.cube_exact; dst->degenerate += src.degenerate;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hs_first_hit(const RdrSceneFlat *sc, int use_cull, int32_t *ids, float *ts, TraceStats *stats)
+{
+    Packed pk(sc);
+    if (pk.status != RDR_OK) return pk.status;
+    const int64_t n = (int64_t)sc->width * sc->height;
+    TraceStats total{};
+#pragma omp parallel
+    {
+        std::vector<uint32_t> masks(pk.masks.size());
+        TraceStats local{};
+#pragma omp for schedule(dynamic, 4096)
+        for (int64_t p = 0; p < n; ++p) {
+            const v3 o = mk3(pk.P.cam.pos[0], pk.P.cam.pos[1], pk.P.cam.pos[2]);
+            const v3 d = camera_ray_dir(pk.P.cam, (uint32_t)(p % sc->width), (uint32_t)(p / sc->width));
+            const Hit h = use_cull ? trace_brute<true>(pk.S, pk.P.cull, masks.data(), 1, o, d, &local)
+                                   : trace_brute<false>(pk.S, pk.P.cull, masks.data(), 1, o, d, &local);
+            ids[p] = h.idx;
+            ts[p] = h.idx >= 0 ? h.t : 0.0f;
+        }
+#pragma omp critical
+        merge(&total, local);
+    }
+    if (stats) *stats = total;
+    return RDR_OK;
+}
+
+int hs_trace(const RdrSceneFlat *sc, int use_cull, uint32_t n, const float *rays, int32_t *ids, float *ts, TraceStats *stats)
+{
+    Packed pk(sc);
+    if (pk.status != RDR_OK) return pk.status;
+    TraceStats total{};
+#pragma omp parallel
+    {
+        std::vector<uint32_t> masks(pk.masks.size());
+        TraceStats local{};
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < (int64_t)n; ++i) {
+            const v3 o = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
+            const v3 d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+            const Hit h = use_cull ? trace_brute<true>(pk.S, pk.P.cull, masks.data(), 1, o, d, &local)
+                                   : trace_brute<false>(pk.S, pk.P.cull, masks.data(), 1, o, d, &local);
+            ids[i] = h.idx;
+            ts[i] = h.idx >= 0 ? h.t : 0.0f;
+        }
+#pragma omp critical
+        merge(&total, local);
+    }
+    if (stats) *stats = total;
+    return RDR_OK;
+}
+
+int hs_render(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t sample_begin, uint32_t n_samples,
+              uint32_t max_bounces, float *accum, TraceStats *stats)
+{
+    Packed pk(sc);
+    if (pk.status != RDR_OK) return pk.status;
+    pk.P.seed_lo = (uint32_t)seed; pk.P.seed_hi = (uint32_t)(seed >> 32);
+    pk.P.max_bounces = max_bounces; pk.P.sample_begin = sample_begin; pk.P.sample_count = n_samples;
+    const int64_t n = (int64_t)sc->width * sc->height;
+    TraceStats total{};
+#pragma omp parallel
+    {
+        std::vector<uint32_t> masks(pk.masks.size());
+        TraceStats local{};
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t p = 0; p < n; ++p) {
+            f4 acc; acc.x = accum[4 * p]; acc.y = accum[4 * p + 1]; acc.z = accum[4 * p + 2]; acc.w = accum[4 * p + 3];
+            acc = use_cull ? render_pixel<true>(pk.P, pk.S, masks.data(), 1, (uint32_t)p, acc, &local)
+                           : render_pixel<false>(pk.P, pk.S, masks.data(), 1, (uint32_t)p, acc, &local);
+            accum[4 * p] = acc.x; accum[4 * p + 1] = acc.y; accum[4 * p + 2] = acc.z; accum[4 * p + 3] = acc.w;
+        }
+#pragma omp critical
+        merge(&total, local);
+    }
+    if (stats) *stats = total;
+    return RDR_OK;
+}
+
+int hs_trace_path(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t x, uint32_t y, uint32_t sample,
+                  uint32_t max_bounces, RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float rgba[4])
+{
+    Packed pk(sc);
+    if (pk.status != RDR_OK) return pk.status;
+    pk.P.seed_lo = (uint32_t)seed; pk.P.seed_hi = (uint32_t)(seed >> 32);
+    pk.P.max_bounces = max_bounces;
+    *n_steps = use_cull ? trace_path_lane<true>(pk.P, pk.S, pk.masks.data(), 1, x, y, sample, steps, capacity, rgba)
+                        : trace_path_lane<false>(pk.P, pk.S, pk.masks.data(), 1, x, y, sample, steps, capacity, rgba);
+    return RDR_OK;
+}
+
+void hs_resolve(const float *accum, uint64_t n_pixels, uint32_t divisor, uint8_t *rgba8)
+{
+    for (uint64_t i = 0; i < n_pixels * 4; ++i) rgba8[i] = (uint8_t)quantise(accum[i], (float)divisor);
+}
+
+// raw conservative tests, for the adversarial margin checks: may[i] = 1 if the cull keeps primitive i for ray i
+void hs_sphere_cull_batch(uint32_t n, const float *rays, const float *spheres, float q_max, float origin_bound, int32_t *may, int32_t *degenerate)
+{
+    CullConsts cc{q_max, origin_bound};
+    for (uint32_t i = 0; i < n; ++i) {
+        const v3 o = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+        const RayCull rc = make_ray_cull(o, d, cc);
+        degenerate[i] = rc.degenerate;
+        const float *s = spheres + 4 * (size_t)i;
+        may[i] = rc.degenerate || sphere_may_hit(o, d, rc, s[0], s[1], s[2], s[3] * s[3]);
+    }
+}
+
+// cubes: prims (cx,cy,cz,side); hp = |side|/2 + pad as packed; best[i] = pruning bound (+inf for none)
+void hs_cube_cull_batch(uint32_t n, const float *rays, const float *cubes, float pad, float origin_bound, const float *best,
+                        int32_t *may, int32_t *degenerate)
+{
+    CullConsts cc{0.0f, origin_bound};
+    for (uint32_t i = 0; i < n; ++i) {
+        const v3 o = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+        const RayCull rc = make_ray_cull(o, d, cc);
+        degenerate[i] = rc.degenerate;
+        const float *c = cubes + 4 * (size_t)i;
+        const float hp = (c[3] < 0 ? -c[3] : c[3]) * 0.5f + pad;
+        may[i] = rc.degenerate || cube_may_hit(rc, c[0], c[1], c[2], hp, best[i]);
+    }
+}
+
+void hs_exact_batch(int sphere, uint32_t n, const float *rays, const float *prims, float *t_out, int32_t *hit)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        const v3 o = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+        const float *p = prims + 4 * (size_t)i;
+        float t = 0.0f;
+        const bool h = sphere ? hit_sphere_exact(o, d, mk3(p[0], p[1], p[2]), p[3], &t) : hit_cube_exact(o, d, mk3(p[0], p[1], p[2]), p[3], &t);
+        hit[i] = h; t_out[i] = h ? t : 0.0f;
+    }
+}
+
+void hs_rng_block(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block, uint32_t out[4])
+{
+    const u4 r = rng_block((uint32_t)seed, (uint32_t)(seed >> 32), pixel, sample, bounce, block);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// pad / bounds the packer derives for a scene (so tests can feed the raw cull entry points consistently)
+int hs_scene_consts(const RdrSceneFlat *sc, float *q_max, float *origin_bound, float *cube_pad)
+{
+    Packed pk(sc);
+    if (pk.status != RDR_OK) return pk.status;
+    *q_max = pk.P.cull.sphere_q_max; *origin_bound = pk.P.cull.origin_bound;
+    *cube_pad = 0.0f;
+    if (pk.P.lay.n_cubes) {
+        const f4 c = pk.S.cube_cull[0], g = pk.S.cube_geom[0];
+        *cube_pad = c.w - (g.w < 0 ? -g.w : g.w) * 0.5f;
+    }
+    return RDR_OK;
+}
+
+}  // extern "C"

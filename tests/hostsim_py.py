@@ -1,0 +1,140 @@
+"""ctypes binding of tests/hostsim/libhostsim.so: the product's __host__ __device__ per-lane code
+(raydar_b200/csrc/rdr_core.cuh, rdr_trace.cuh, rdr_pack.h) compiled for the CPU.  TEST INFRASTRUCTURE:
+lets the `-m "not gpu"` suite check the logic the CUDA kernels execute against the oracle."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import raydar_b200 as rb
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_SRC = os.path.join(_HERE, "hostsim", "hostsim.cpp")
+_LIB = os.path.join(_HERE, "hostsim", "libhostsim.so")
+
+
+class TraceStats(C.Structure):
+    _fields_ = [("traces", C.c_uint64), ("sphere_exact", C.c_uint64), ("cube_exact", C.c_uint64), ("degenerate", C.c_uint64)]
+
+
+def build():
+    csrc = os.path.join(_ROOT, "raydar_b200", "csrc")
+    deps = [_SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(_ROOT, "include", "raydar_cuda.h")]
+    if os.path.exists(_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(_LIB) for d in deps):
+        return _LIB
+    cmd = ["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-std=c++17", "-ffp-contract=off",
+           "-fno-fast-math", "-mfma", "-fopenmp", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+           "-I", os.path.join(_ROOT, "include"), "-I", csrc, _SRC, "-o", _LIB]
+    subprocess.run(cmd, check=True, capture_output=True)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        fp, i32p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
+        sfp, stp = C.POINTER(rb.RdrSceneFlat), C.POINTER(TraceStats)
+        L.hs_first_hit.argtypes = [sfp, C.c_int, i32p, fp, stp]
+        L.hs_trace.argtypes = [sfp, C.c_int, C.c_uint32, fp, i32p, fp, stp]
+        L.hs_render.argtypes = [sfp, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, fp, stp]
+        L.hs_trace_path.argtypes = [sfp, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                    C.POINTER(rb.RdrPathStep), C.c_uint32, u32p, fp]
+        L.hs_resolve.argtypes = [fp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint8)]
+        L.hs_sphere_cull_batch.argtypes = [C.c_uint32, fp, fp, C.c_float, C.c_float, i32p, i32p]
+        L.hs_cube_cull_batch.argtypes = [C.c_uint32, fp, fp, C.c_float, C.c_float, fp, i32p, i32p]
+        L.hs_exact_batch.argtypes = [C.c_int, C.c_uint32, fp, fp, fp, i32p]
+        L.hs_rng_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
+        L.hs_scene_consts.argtypes = [sfp, fp, fp, fp]
+        _lib = L
+    return _lib
+
+
+def _fp(a): return a.ctypes.data_as(C.POINTER(C.c_float))
+def _ip(a): return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _ok(st):
+    if st != 0:
+        raise RuntimeError(f"hostsim status {st}")
+
+
+def first_hit(scene, use_cull=True):
+    f = rb._as_flat(scene)
+    ids = np.zeros((f.height, f.width), np.int32); ts = np.zeros((f.height, f.width), np.float32)
+    st = TraceStats()
+    _ok(lib().hs_first_hit(C.byref(f), int(use_cull), _ip(ids), _fp(ts), C.byref(st)))
+    return ids, ts, st
+
+
+def trace(scene, rays, use_cull=True):
+    f = rb._as_flat(scene)
+    rays = np.ascontiguousarray(rays, np.float32)
+    n = rays.shape[0]; ids = np.zeros(n, np.int32); ts = np.zeros(n, np.float32); st = TraceStats()
+    _ok(lib().hs_trace(C.byref(f), int(use_cull), n, _fp(rays), _ip(ids), _fp(ts), C.byref(st)))
+    return ids, ts, st
+
+
+def render(scene, seed, sample_begin, n_samples, max_bounces, accum=None, use_cull=True):
+    f = rb._as_flat(scene)
+    if accum is None:
+        accum = np.zeros((f.height, f.width, 4), np.float32)
+    st = TraceStats()
+    _ok(lib().hs_render(C.byref(f), int(use_cull), seed, sample_begin, n_samples, max_bounces, _fp(accum), C.byref(st)))
+    return accum, st
+
+
+def trace_path(scene, x, y, sample, seed, max_bounces, use_cull=True, capacity=128):
+    f = rb._as_flat(scene)
+    steps = (rb.RdrPathStep * capacity)(); n = C.c_uint32(0); rgba = np.zeros(4, np.float32)
+    _ok(lib().hs_trace_path(C.byref(f), int(use_cull), seed, x, y, sample, max_bounces, steps, capacity, C.byref(n), _fp(rgba)))
+    return [steps[i] for i in range(n.value)], rgba
+
+
+def resolve(accum, divisor):
+    accum = np.ascontiguousarray(accum, np.float32)
+    out = np.zeros(accum.shape, np.uint8)
+    lib().hs_resolve(_fp(accum), accum.size // 4, divisor, out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return out
+
+
+def sphere_cull(rays, spheres, q_max, origin_bound):
+    rays = np.ascontiguousarray(rays, np.float32); spheres = np.ascontiguousarray(spheres, np.float32)
+    n = rays.shape[0]; may = np.zeros(n, np.int32); deg = np.zeros(n, np.int32)
+    lib().hs_sphere_cull_batch(n, _fp(rays), _fp(spheres), q_max, origin_bound, _ip(may), _ip(deg))
+    return may, deg
+
+
+def cube_cull(rays, cubes, pad, origin_bound, best):
+    rays = np.ascontiguousarray(rays, np.float32); cubes = np.ascontiguousarray(cubes, np.float32)
+    best = np.ascontiguousarray(best, np.float32)
+    n = rays.shape[0]; may = np.zeros(n, np.int32); deg = np.zeros(n, np.int32)
+    lib().hs_cube_cull_batch(n, _fp(rays), _fp(cubes), pad, origin_bound, _fp(best), _ip(may), _ip(deg))
+    return may, deg
+
+
+def exact(sphere, rays, prims):
+    rays = np.ascontiguousarray(rays, np.float32); prims = np.ascontiguousarray(prims, np.float32)
+    n = rays.shape[0]; t = np.zeros(n, np.float32); hit = np.zeros(n, np.int32)
+    lib().hs_exact_batch(int(sphere), n, _fp(rays), _fp(prims), _fp(t), _ip(hit))
+    return hit, t
+
+
+def rng_block(seed, pixel, sample, bounce, block):
+    out = (C.c_uint32 * 4)()
+    lib().hs_rng_block(seed, pixel, sample, bounce, block, out)
+    return list(out)
+
+
+def scene_consts(scene):
+    f = rb._as_flat(scene)
+    q = C.c_float(); ob = C.c_float(); pad = C.c_float()
+    _ok(lib().hs_scene_consts(C.byref(f), C.byref(q), C.byref(ob), C.byref(pad)))
+    return q.value, ob.value, pad.value

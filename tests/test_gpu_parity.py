@@ -1,0 +1,211 @@
+"""-m gpu: the CUDA path (through the C ABI) against the oracle.  Bit-exact everywhere: the kernels
+evaluate the reference's f32 expression trees with one rounding per operation."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def u32(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def renderer(rb):
+    r = rb.Renderer(rb.RendererConfig(max_sample_count=8, max_bounces=12))
+    yield r
+    r.close()
+
+
+def random_rays(rng, n, scale=10.0):
+    o = rng.uniform(-scale, scale, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d *= rng.uniform(0.05, 2.0, (n, 1)).astype(np.float32)          # bounce directions are not unit length
+    return np.concatenate([o, d], axis=1).astype(np.float32)
+
+
+def test_rng_kat(renderer, orc):
+    for args in [(0, 0, 0, 0, 0), (0x5EED, 12345, 7, 3, 2), (0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 11, 3)]:
+        assert renderer.kat_rng(*args) == orc.rng_block(*args)
+
+
+@pytest.mark.parametrize("sphere", [True, False])
+def test_intersection_kat(renderer, orc, sphere):
+    rng = np.random.default_rng(7 + sphere)
+    n = 200_000
+    rays = random_rays(rng, n)
+    prims = np.concatenate([rng.uniform(-10, 10, (n, 3)), rng.uniform(0.05, 6.0, (n, 1))], axis=1).astype(np.float32)
+    # a share of rays aimed at their primitive (hits, grazing hits), and axis-aligned directions (division by zero)
+    aim = rng.random(n) < 0.6
+    tgt = prims[:, :3] + rng.normal(size=(n, 3)).astype(np.float32) * prims[:, 3:4] * 0.6
+    rays[aim, 3:] = (tgt - rays[:, :3])[aim] * rng.uniform(0.1, 1.5, (aim.sum(), 1)).astype(np.float32)
+    axis = rng.random(n) < 0.05
+    rays[axis, 3 + rng.integers(0, 3)] = 0.0
+    inside = rng.random(n) < 0.05
+    rays[inside, :3] = prims[inside, :3]
+    h_o, t_o = (orc.hit_sphere_batch if sphere else orc.hit_cube_batch)(rays, prims)
+    h_g, t_g = renderer.kat_hit(sphere, rays, prims)
+    assert h_o.sum() > n // 10
+    assert np.array_equal(h_o, h_g)
+    assert np.array_equal(u32(t_o), u32(t_g))
+
+
+@pytest.mark.parametrize("name,res", [("default", None), ("benchmark", (1920, 1080)), ("benchmark", None)])
+@pytest.mark.parametrize("cull", [True, False])
+def test_first_hit_ids_bit_exact(renderer, orc, default_scene, benchmark_scene, name, res, cull):
+    scene = default_scene if name == "default" else benchmark_scene
+    if res:
+        scene = scene.with_resolution(*res)
+    if not cull and scene.width > 1920:
+        pytest.skip("exact-everything reference run only up to 1080p")
+    ids_o, t_o = orc.first_hit(scene)
+    renderer.debug_set_cull(cull)
+    try:
+        renderer.new_frame(scene)
+        ids_g, t_g = renderer.first_hit()
+    finally:
+        renderer.debug_set_cull(True)
+    assert np.array_equal(ids_o, ids_g)
+    assert np.array_equal(u32(t_o), u32(t_g))
+
+
+def test_camera_rays(renderer, orc, default_scene, benchmark_scene):
+    for scene in (default_scene, benchmark_scene):
+        renderer.new_frame(scene)
+        rng = np.random.default_rng(3)
+        xy = np.stack([rng.integers(0, scene.width, 500), rng.integers(0, scene.height, 500)], axis=1).astype(np.uint32)
+        rays = renderer.kat_camera_rays(xy)
+        for (x, y), ray in zip(xy, rays):
+            o, d = orc.camera_ray(scene, int(x), int(y))
+            assert np.array_equal(u32(o), u32(ray[:3])) and np.array_equal(u32(d), u32(ray[3:]))
+
+
+def test_trace_arbitrary_rays(renderer, orc, benchmark_scene):
+    rng = np.random.default_rng(11)
+    rays = random_rays(rng, 20_000, scale=8.0)
+    rays[:, 1] = np.abs(rays[:, 1])                       # origins above the floor
+    renderer.new_frame(benchmark_scene.with_resolution(64, 36))
+    ids_g, t_g = renderer.kat_trace(rays)
+    for i in range(0, len(rays), 7):
+        idx, t = orc.trace(benchmark_scene, rays[i, :3], rays[i, 3:])
+        assert idx == ids_g[i]
+        if idx >= 0:
+            assert u32(np.float32(t)) == u32(t_g[i])
+
+
+@pytest.mark.parametrize("name", ["default", "benchmark"])
+def test_single_path_debug_mode(rb, orc, default_scene, benchmark_scene, name):
+    scene = (default_scene if name == "default" else benchmark_scene.with_resolution(480, 270))
+    seed = 0xC0FFEE
+    r = rb.Renderer(rb.RendererConfig(max_sample_count=4, max_bounces=12))
+    r.set_seed(seed)
+    r.new_frame(scene)
+    rng = np.random.default_rng(5)
+    fields = ["position", "normal", "origin", "direction", "attenuation", "light"]
+    n_steps = 0
+    for _ in range(300):
+        x, y, s = int(rng.integers(0, scene.width)), int(rng.integers(0, scene.height)), int(rng.integers(0, 1000))
+        steps_o, rgba_o = orc.trace_path(scene, x, y, s, seed, 12)
+        steps_g, rgba_g = r.trace_path(x, y, s)
+        assert len(steps_o) == len(steps_g)
+        for a, b in zip(steps_o, steps_g):
+            assert (a.object, a.lobe, a.front_face) == (b.object, b.lobe, b.front_face)
+            assert u32(np.float32(a.t)) == u32(np.float32(b.t))
+            for f in fields:
+                assert np.array_equal(u32(np.array(getattr(a, f)[:])), u32(np.array(getattr(b, f)[:]))), f
+            n_steps += 1
+        # north-star tolerance: fixed-seed single path within 1e-4 relative -- met exactly
+        assert np.array_equal(u32(rgba_o), u32(rgba_g))
+    assert n_steps > 400
+    r.close()
+
+
+@pytest.mark.parametrize("name,res,spp", [("default", (427, 240), 16), ("benchmark", (320, 180), 8)])
+def test_accumulator_bit_exact(rb, orc, default_scene, benchmark_scene, name, res, spp):
+    scene = (default_scene if name == "default" else benchmark_scene).with_resolution(*res)
+    seed = 99
+    acc_o = orc.render(scene, seed, 0, spp, 12, n_threads=orc.max_threads())
+    r = rb.Renderer(rb.RendererConfig(max_sample_count=spp, max_bounces=12))
+    r.set_seed(seed)
+    img = r.render_frame(scene)
+    acc_g = r.read_accum()
+    assert np.array_equal(u32(acc_o), u32(acc_g))
+    assert np.array_equal(orc.resolve(acc_o, spp), img)
+    assert r.sample_count() == spp
+    r.close()
+
+
+def test_progressive_equals_one_shot_and_sharding(rb, benchmark_scene):
+    """Size-independent properties at 1080p: (1) render_sample x n == render_frame(n) bit for bit,
+    (2) two sample-range shards sum to the single render up to f32 summation order."""
+    scene = benchmark_scene.with_resolution(1920, 1080)
+    spp = 4
+    a = rb.Renderer(rb.RendererConfig(spp, 12)); a.set_seed(5)
+    img_a = a.render_frame(scene); acc_a = a.read_accum()
+    b = rb.Renderer(rb.RendererConfig(spp, 12)); b.set_seed(5)
+    b.new_frame(scene)
+    last = None
+    for i in range(spp):
+        last = b.render_sample(scene)
+        assert last is not None and b.sample_count() == i + 1
+    assert b.render_sample(scene) is None
+    assert np.array_equal(u32(acc_a), u32(b.read_accum()))
+    assert np.array_equal(img_a, last)
+    shards = []
+    for g in range(2):
+        c = rb.Renderer(rb.RendererConfig(spp // 2, 12)); c.set_seed(5); c.set_sample_offset(g * spp // 2)
+        c.new_frame(scene); c.render_samples(spp // 2); shards.append(c.read_accum()); c.close()
+    total = shards[0] + shards[1]
+    assert np.allclose(total, acc_a, rtol=1e-5, atol=1e-5)
+    assert np.array_equal(total[..., 3], acc_a[..., 3])
+    a.close(); b.close()
+
+
+def test_converged_psnr_independent_streams(rb, orc, default_scene):
+    """Independent RNG streams (GPU seed A vs oracle seed B) converge to the same image:
+    PSNR >= 40 dB on the resolved 8-bit image is not reachable at test-sized spp for the pixels lit by the
+    30x emitter, so the gate here is on the float mean with a bounded per-channel mean error; the same-stream
+    comparison above is bit-exact (PSNR = inf)."""
+    scene = default_scene.with_resolution(214, 120)
+    spp = 256
+    r = rb.Renderer(rb.RendererConfig(spp, 12)); r.set_seed(1)
+    r.render_frame(scene)
+    gpu = r.read_accum()[..., :3] / spp
+    cpu = orc.render(scene, 2, 0, spp, 12, n_threads=orc.max_threads())[..., :3] / spp
+    assert abs(gpu.mean() - cpu.mean()) / cpu.mean() < 0.01
+    for c in range(3):
+        assert abs(gpu[..., c].mean() - cpu[..., c].mean()) / cpu[..., c].mean() < 0.015
+    g8 = np.clip(gpu, 0, 1); c8 = np.clip(cpu, 0, 1)
+    mse = float(((g8 - c8) ** 2).mean())
+    psnr = 10 * np.log10(1.0 / mse)
+    assert psnr > 25.0            # 256 spp each side, independent noise; see test_psnr_converged for the 40 dB gate
+    r.close()
+
+
+def test_edge_cases(rb, orc, default_scene):
+    # zero objects: every sample is the sky
+    empty = default_scene.with_resolution(32, 16)
+    import copy
+    empty = copy.copy(empty)
+    empty.kind = empty.kind[:0]; empty.geom = empty.geom[:0]; empty.material = empty.material[:0]
+    r = rb.Renderer(rb.RendererConfig(3, 12)); r.set_seed(1)
+    img = r.render_frame(empty)
+    acc_o = orc.render(empty, 1, 0, 3, 12)
+    assert np.array_equal(u32(acc_o), u32(r.read_accum()))
+    assert np.array_equal(orc.resolve(acc_o, 3), img)
+    # max_bounces = 0 and 1
+    for mb in (0, 1, 2):
+        r.set_max_bounces(mb)
+        s = default_scene.with_resolution(64, 36)
+        r.render_frame(s)
+        assert np.array_equal(u32(orc.render(s, 1, 0, 3, mb)), u32(r.read_accum())), mb
+    # max_sample_count = 0: the reference divides by zero -> all-zero image
+    r.set_max_sample_count(0); r.set_max_bounces(12)
+    img0 = r.render_frame(default_scene.with_resolution(16, 8))
+    assert img0.max() == 0
+    # transparent world is todo!() in the reference -> error status, no abort
+    t = copy.copy(default_scene); t.world_kind = rb.WORLD_TRANSPARENT
+    with pytest.raises(rb.RaydarError) as e:
+        r.new_frame(t)
+    assert e.value.status == rb.ERR_UNSUPPORTED
+    r.close()
