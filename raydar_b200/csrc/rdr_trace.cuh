@@ -140,6 +140,14 @@ RDR_HD Hit trace_brute(const SceneView &S, const CullConsts &cc, uint32_t *masks
     return best;
 }
 
+// 0, but opaque to the compiler's uniformity analysis (see render_pixel)
+RDR_HD uint32_t lane_varying_zero(uint32_t *scratch)
+{
+    volatile uint32_t *v = scratch;
+    *v = 0u;
+    return *v;
+}
+
 // ---- the sample loop of one pixel ----------------------------------------------------------------------
 // Loop structure ("sample refill"): the reference nests samples > pixels > bounces.  A lane here owns a
 // pixel and runs ONE loop whose body is "trace the lane's current ray, then shade".  When a path ends
@@ -166,7 +174,14 @@ RDR_HD f4 render_pixel(const FrameParams &P, const SceneView &S, uint32_t *masks
     const v3 cam_d = camera_ray_dir(P.cam, x, y);
     const Hit h0 = trace_brute<USE_CULL>(S, P.cull, masks, stride, cam_o, cam_d, stats);
 
-    uint32_t s = 0u, bounce = 0u;
+    // ptxas 12.9 (sm_100a) promotes a loop counter that starts from a constant and is stepped by a constant
+    // to a UNIFORM register even when, as here, lanes step it at different times (observed: `s` in UR4,
+    // UIADD3/UISETP/BRA.U, every lane of a warp sharing one sample counter -> too few samples per pixel).
+    // Starting the per-lane counters from a value the compiler must treat as lane-varying (a volatile
+    // shared-memory read-back of this lane's scratch word) keeps them in vector registers.
+    // tests/test_gpu_parity.py::test_accumulator_bit_exact guards this.
+    const uint32_t lane_zero = lane_varying_zero(masks);
+    uint32_t s = lane_zero, bounce = lane_zero;
     v3 ro = cam_o, rd = cam_d;
     v3 light = mk3(0.0f, 0.0f, 0.0f), atten = mk3(1.0f, 1.0f, 1.0f);
     Hit hit = h0;
@@ -192,7 +207,7 @@ RDR_HD f4 render_pixel(const FrameParams &P, const SceneView &S, uint32_t *masks
             if (!terminated) break;
             acc.x = fadd(acc.x, light.x); acc.y = fadd(acc.y, light.y); acc.z = fadd(acc.z, light.z); acc.w = fadd(acc.w, 1.0f);
             if (++s >= n) { alive = false; break; }
-            bounce = 0u; ro = cam_o; rd = cam_d; hit = h0;
+            bounce = lane_zero; ro = cam_o; rd = cam_d; hit = h0;
             light = mk3(0.0f, 0.0f, 0.0f); atten = mk3(1.0f, 1.0f, 1.0f);
         }
         if (!alive) break;
