@@ -15,7 +15,11 @@
 
 namespace rdr {
 
-// ---- the sample loop: one lane = one pixel (see render_pixel in rdr_trace.cuh) -----------------------
+// ---- the sample loop: one lane = one pixel (LaneState / lane_shade / trace_brute in rdr_trace.cuh) ---------
+// Warp lock-step: each iteration every lane with work left shades until it holds a ray, the warp votes
+// (__any_sync is also the reconvergence point -- without it Volta+ independent thread scheduling lets the
+// lanes drift apart until each executes the scan alone), then the live lanes run the scan together.
+// No lane returns early: lanes past the end of the image take part in the votes with alive = false.
 template <bool USE_CULL>
 __global__ void __launch_bounds__(RDR_BLOCK, 2) render_kernel(const __grid_constant__ FrameParams P)
 {
@@ -24,9 +28,18 @@ __global__ void __launch_bounds__(RDR_BLOCK, 2) render_kernel(const __grid_const
     const SceneView S = scene_view(smem, P.lay);
     uint32_t *masks = mask_base(smem, P.lay) + threadIdx.x;
     const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pixel >= P.cam.width * P.cam.height) return;
-    // one 16-byte load and one 16-byte store of the accumulator per pixel per launch, coalesced
-    P.accum[pixel] = render_pixel<USE_CULL>(P, S, masks, blockDim.x, pixel, P.accum[pixel]);
+    const bool valid = pixel < P.cam.width * P.cam.height;
+
+    LaneState st;
+    f4 acc; acc.x = acc.y = acc.z = acc.w = 0.0f;
+    if (valid) acc = P.accum[pixel];                     // one coalesced 16-byte load per pixel per launch
+    lane_begin<USE_CULL>(P, S, masks, blockDim.x, pixel, valid, acc, st);
+    for (;;) {
+        if (st.alive) lane_shade(P, S, pixel, st);
+        if (!__any_sync(0xffffffffu, st.alive)) break;
+        if (st.alive) st.hit = trace_brute<USE_CULL>(S, P.cull, masks, blockDim.x, st.ro, st.rd);
+    }
+    if (valid) P.accum[pixel] = st.acc;                  // ... and one 16-byte store
 }
 
 // ---- print_frame_buffer (cpu.rs:221-230): one uchar4 (32-bit) store per pixel ------------------------

@@ -140,7 +140,7 @@ RDR_HD Hit trace_brute(const SceneView &S, const CullConsts &cc, uint32_t *masks
     return best;
 }
 
-// 0, but opaque to the compiler's uniformity analysis (see render_pixel)
+// 0, but opaque to the compiler's uniformity analysis (see LaneState)
 RDR_HD uint32_t lane_varying_zero(uint32_t *scratch)
 {
     volatile uint32_t *v = scratch;
@@ -150,70 +150,103 @@ RDR_HD uint32_t lane_varying_zero(uint32_t *scratch)
 
 // ---- the sample loop of one pixel ----------------------------------------------------------------------
 // Loop structure ("sample refill"): the reference nests samples > pixels > bounces.  A lane here owns a
-// pixel and runs ONE loop whose body is "trace the lane's current ray, then shade".  When a path ends
-// (miss, or max_bounces traces used) the lane immediately starts its pixel's next sample inside the
-// same iteration, so every lane enters every trace with a live ray and the scan -- >90 % of the
-// work -- runs with all 32 lanes active regardless of how path lengths differ.
+// pixel and alternates two phases until its samples are used up:
+//   lane_shade  shade the lane's current hit; when the path ends (miss, or max_bounces traces used) finish
+//               the sample and immediately start the pixel's next one, shading its cached primary hit, until
+//               the lane holds a ray that needs tracing (or has no samples left);
+//   trace       nearest hit of that ray.
+// The render kernel runs the two phases in warp lock-step (one __any_sync per iteration is the reconvergence
+// point), so every lane that still has work enters every trace with a live ray and the scan -- >90 % of the
+// instructions -- runs converged no matter how path lengths differ between the lanes of a warp.
 //
-// The camera ray has no jitter (cpu.rs:199-202), so all samples of a pixel share the primary ray and
-// its nearest hit; it is traced once per launch and reused (bit-identical results).
+// The camera ray has no jitter (cpu.rs:199-202), so all samples of a pixel share the primary ray and its
+// nearest hit; it is traced once per launch and reused (bit-identical results).
 //
 // Per-pixel accumulation order is sample-ascending, as in the reference, so a launch over samples
 // [s0, s0+n) on top of an accumulator that already holds [0, s0) is bit-identical to one launch.
+struct LaneState {
+    f4 acc;                 // running accumulator of the pixel (registers)
+    v3 cam_d;               // primary ray direction
+    Hit h0;                 // cached primary hit
+    Hit hit;                // hit to shade next
+    v3 ro, rd, light, atten;
+    uint32_t s, bounce, lane_zero;
+    bool alive;             // the lane holds (or will hold) a ray to trace
+};
+
+template <bool USE_CULL>
+RDR_HD void lane_begin(const FrameParams &P, const SceneView &S, uint32_t *masks, uint32_t stride, uint32_t pixel,
+                       bool valid, f4 acc, LaneState &st, TraceStats *stats = nullptr)
+{
+    // ptxas 12.9 (sm_100a) promotes a counter that starts from a constant and is stepped by a constant to a
+    // UNIFORM register even when lanes step it at different times (observed: the sample counter in UR4 with
+    // UIADD3/UISETP/BRA.U, all lanes of a warp sharing it -> too few samples per pixel).  Starting the per-lane
+    // counters from a value the compiler must treat as lane-varying (a volatile read-back of the lane's scratch
+    // word) keeps them in vector registers.  tests/test_gpu_parity.py::test_accumulator_bit_exact guards this.
+    st.lane_zero = lane_varying_zero(masks);
+    st.acc = acc;
+    st.s = st.lane_zero; st.bounce = st.lane_zero;
+    st.alive = valid && P.sample_count > 0u;
+    st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
+    st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
+    st.cam_d = st.rd = mk3(0.0f, 0.0f, 0.0f);
+    st.h0.idx = -1; st.h0.t = 0.0f;
+    if (valid && P.max_bounces == 0u) {       // `for _ in 0..0`: light stays zero, alpha still accumulates
+        for (uint32_t s = 0; s < P.sample_count; ++s) {
+            st.acc.x = fadd(st.acc.x, 0.0f); st.acc.y = fadd(st.acc.y, 0.0f); st.acc.z = fadd(st.acc.z, 0.0f); st.acc.w = fadd(st.acc.w, 1.0f);
+        }
+        st.alive = false;
+    }
+    if (st.alive) {
+        st.cam_d = st.rd = camera_ray_dir(P.cam, pixel % P.cam.width, pixel / P.cam.width);
+        st.h0 = trace_brute<USE_CULL>(S, P.cull, masks, stride, st.ro, st.rd, stats);
+    }
+    st.hit = st.h0;
+}
+
+// runs until the lane has a ray that needs tracing (st.alive) or has used all its samples (!st.alive)
+RDR_HD void lane_shade(const FrameParams &P, const SceneView &S, uint32_t pixel, LaneState &st)
+{
+    for (;;) {
+        bool terminated;
+        if (st.hit.idx >= 0) {
+            bool is_sphere;
+            const Material m = load_material(S, st.hit.idx, &is_sphere);
+            const f4 g = S.obj_geom[st.hit.idx];
+            const Surface sf = closest_hit(st.ro, st.rd, st.hit.t, is_sphere, mk3(g.x, g.y, g.z), g.w);
+            const Scatter sc = scatter(st.rd, sf, m, P.seed_lo, P.seed_hi, pixel, P.sample_begin + st.s, st.bounce);
+            st.ro = sc.origin; st.rd = sc.dir;
+            st.atten = mul3(st.atten, m.albedo);
+            st.light = add3(st.light, scale3(m.emission, m.emission_strength));
+            ++st.bounce;
+            terminated = st.bounce >= P.max_bounces;
+        } else {
+            st.light = add3(st.light, mul3(world_sample(P.world, st.rd), st.atten));
+            terminated = true;
+        }
+        if (!terminated) return;
+        st.acc.x = fadd(st.acc.x, st.light.x); st.acc.y = fadd(st.acc.y, st.light.y);
+        st.acc.z = fadd(st.acc.z, st.light.z); st.acc.w = fadd(st.acc.w, 1.0f);
+        if (++st.s >= P.sample_count) { st.alive = false; return; }
+        st.bounce = st.lane_zero; st.hit = st.h0;
+        st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]); st.rd = st.cam_d;
+        st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
+    }
+}
+
+// scalar driver of the two phases (host simulation; the kernel drives them in warp lock-step instead)
 template <bool USE_CULL>
 RDR_HD f4 render_pixel(const FrameParams &P, const SceneView &S, uint32_t *masks, uint32_t stride, uint32_t pixel, f4 acc,
                        TraceStats *stats = nullptr)
 {
-    const uint32_t n = P.sample_count;
-    if (P.max_bounces == 0u) {            // `for _ in 0..0`: light stays zero, alpha still accumulates
-        for (uint32_t s = 0; s < n; ++s) { acc.x = fadd(acc.x, 0.0f); acc.y = fadd(acc.y, 0.0f); acc.z = fadd(acc.z, 0.0f); acc.w = fadd(acc.w, 1.0f); }
-        return acc;
+    LaneState st;
+    lane_begin<USE_CULL>(P, S, masks, stride, pixel, true, acc, st, stats);
+    while (st.alive) {
+        lane_shade(P, S, pixel, st);
+        if (!st.alive) break;
+        st.hit = trace_brute<USE_CULL>(S, P.cull, masks, stride, st.ro, st.rd, stats);
     }
-    const uint32_t x = pixel % P.cam.width, y = pixel / P.cam.width;
-    const v3 cam_o = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
-    const v3 cam_d = camera_ray_dir(P.cam, x, y);
-    const Hit h0 = trace_brute<USE_CULL>(S, P.cull, masks, stride, cam_o, cam_d, stats);
-
-    // ptxas 12.9 (sm_100a) promotes a loop counter that starts from a constant and is stepped by a constant
-    // to a UNIFORM register even when, as here, lanes step it at different times (observed: `s` in UR4,
-    // UIADD3/UISETP/BRA.U, every lane of a warp sharing one sample counter -> too few samples per pixel).
-    // Starting the per-lane counters from a value the compiler must treat as lane-varying (a volatile
-    // shared-memory read-back of this lane's scratch word) keeps them in vector registers.
-    // tests/test_gpu_parity.py::test_accumulator_bit_exact guards this.
-    const uint32_t lane_zero = lane_varying_zero(masks);
-    uint32_t s = lane_zero, bounce = lane_zero;
-    v3 ro = cam_o, rd = cam_d;
-    v3 light = mk3(0.0f, 0.0f, 0.0f), atten = mk3(1.0f, 1.0f, 1.0f);
-    Hit hit = h0;
-    bool alive = n > 0u;
-    while (alive) {
-        for (;;) {                         // shade; on termination start the next sample and shade its primary hit
-            bool terminated;
-            if (hit.idx >= 0) {
-                bool is_sphere;
-                const Material m = load_material(S, hit.idx, &is_sphere);
-                const f4 g = S.obj_geom[hit.idx];
-                const Surface sf = closest_hit(ro, rd, hit.t, is_sphere, mk3(g.x, g.y, g.z), g.w);
-                const Scatter sc = scatter(rd, sf, m, P.seed_lo, P.seed_hi, pixel, P.sample_begin + s, bounce);
-                ro = sc.origin; rd = sc.dir;
-                atten = mul3(atten, m.albedo);
-                light = add3(light, scale3(m.emission, m.emission_strength));
-                ++bounce;
-                terminated = bounce >= P.max_bounces;
-            } else {
-                light = add3(light, mul3(world_sample(P.world, rd), atten));
-                terminated = true;
-            }
-            if (!terminated) break;
-            acc.x = fadd(acc.x, light.x); acc.y = fadd(acc.y, light.y); acc.z = fadd(acc.z, light.z); acc.w = fadd(acc.w, 1.0f);
-            if (++s >= n) { alive = false; break; }
-            bounce = lane_zero; ro = cam_o; rd = cam_d; hit = h0;
-            light = mk3(0.0f, 0.0f, 0.0f); atten = mk3(1.0f, 1.0f, 1.0f);
-        }
-        if (!alive) break;
-        hit = trace_brute<USE_CULL>(S, P.cull, masks, stride, ro, rd, stats);
-    }
-    return acc;
+    return st.acc;
 }
 
 // one path with every bounce recorded (debug / parity); returns the number of steps taken

@@ -1,0 +1,36 @@
+"""Multi-GPU plumbing for the one-process-per-GPU launch (torchrun): sample-range sharding and the single
+reduce of the per-GPU accumulators.  torch.distributed is plumbing only; the reduce is one
+NCCL `reduce(sum, f32)` over NVLink on GPUs and the same call over gloo in the CPU tests."""
+from __future__ import annotations
+
+
+def weak_sample_range(rank: int, spp_per_rank: int) -> tuple[int, int]:
+    """Weak scaling: every rank renders spp_per_rank samples; rank g owns global samples [g*spp, (g+1)*spp)."""
+    return rank * spp_per_rank, spp_per_rank
+
+
+def strong_sample_range(rank: int, world: int, total_spp: int) -> tuple[int, int]:
+    """Strong scaling: total_spp split evenly (the same split rdr_create_multi uses, rdr_multi.cpp)."""
+    b = total_spp * rank // world
+    e = total_spp * (rank + 1) // world
+    return b, e - b
+
+
+def reduce_accum(accum, dst: int = 0):
+    """Sums the per-rank float RGBA accumulators onto rank `dst` (in place on dst)."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
+    return accum
+
+
+def device_accum_tensor(renderer, n_pixels: int, device_index: int):
+    """Wraps the renderer's device accumulator (rdr_accum_device_ptr) as a torch tensor without copying."""
+    import torch
+    ptr, nbytes = renderer.accum_device_ptr()
+    assert nbytes == n_pixels * 16
+
+    class _Arr:
+        __cuda_array_interface__ = {"shape": (n_pixels * 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+    return torch.as_tensor(_Arr(), device=f"cuda:{device_index}")

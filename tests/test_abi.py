@@ -1,0 +1,74 @@
+"""The C-ABI boundary: libraydar_cuda.so loads, exports every symbol include/raydar_cuda.h declares, its structs
+have the layout the Python / Rust bindings assume, and without a GPU it fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "raydar_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rdr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(rb):
+    declared = header_functions()
+    assert len(declared) >= 35
+    out = subprocess.run(["nm", "-D", "--defined-only", rb.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (rdr_[a-z0-9_]+)", out))
+    missing = [f for f in declared if f not in exported]
+    assert not missing, missing
+    assert sorted(rb.EXPORTS) == declared
+    L = rb.load_library()
+    for name in declared:
+        assert getattr(L, name) is not None
+
+
+def test_struct_layouts(rb, orc):
+    assert C.sizeof(rb.RdrConfig) == 8
+    assert C.sizeof(rb.RdrPathStep) == 88 and C.sizeof(orc.PathStep) == 88
+    assert C.sizeof(rb.RdrSceneFlat) == C.sizeof(orc._Scene) == 208
+    assert C.sizeof(rb.RdrProfiler) == 56
+    assert rb.RdrSceneFlat.kind.offset == 184 and rb.RdrSceneFlat.cam_pos.offset == 136
+
+
+def test_library_has_sm100a_code_and_tma(rb):
+    out = subprocess.run(["cuobjdump", "-lelf", rb.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", rb.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass            # cp.async.bulk staging of the scene blob
+    assert "render_kernel" in sass
+
+
+def test_no_cpu_fallback(rb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(rb.RaydarError) as e:
+        rb.Renderer(rb.RendererConfig(1, 1))
+    assert e.value.status == rb.ERR_CUDA and "no CPU fallback" in e.value.message
+    h = C.c_void_p()
+    dev = (C.c_int * 2)(0, 1)
+    assert rb.load_library().rdr_create_multi(None, 2, dev, C.byref(h)) == rb.ERR_CUDA
+    # NULL handles are rejected, not dereferenced
+    L = rb.load_library()
+    assert L.rdr_new_frame(None, None) == rb.ERR_INVALID
+    assert L.rdr_render_samples(None, 1) == rb.ERR_INVALID
+    assert L.rdr_sample_count(None) == 0
+
+
+def test_product_does_not_reference_the_oracle(rb):
+    """The oracle is test infrastructure: nothing under raydar_b200/ may import, link or load it."""
+    pkg = os.path.join(ROOT, "raydar_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "libraydar_oracle" not in text and "import orc" not in text and "from oracle" not in text, f
+    needed = subprocess.run(["readelf", "-d", rb.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in needed and "hostsim" not in needed

@@ -162,23 +162,21 @@ def test_progressive_equals_one_shot_and_sharding(rb, benchmark_scene):
 
 
 def test_converged_psnr_independent_streams(rb, orc, default_scene):
-    """Independent RNG streams (GPU seed A vs oracle seed B) converge to the same image:
-    PSNR >= 40 dB on the resolved 8-bit image is not reachable at test-sized spp for the pixels lit by the
-    30x emitter, so the gate here is on the float mean with a bounded per-channel mean error; the same-stream
-    comparison above is bit-exact (PSNR = inf)."""
-    scene = default_scene.with_resolution(214, 120)
-    spp = 256
+    """North-star gate: at high spp the converged GPU image reaches PSNR >= 40 dB against the CPU backend's
+    converged image, with bounded per-channel mean error.  The two sides use DIFFERENT RNG seeds (independent
+    streams), so this checks convergence to the same expectation; the same-stream comparison
+    (test_accumulator_bit_exact) is bit-exact.  64x36 so that the CPU side finishes in seconds at 32768 spp."""
+    scene = default_scene.with_resolution(64, 36)
+    spp = 32768
     r = rb.Renderer(rb.RendererConfig(spp, 12)); r.set_seed(1)
     r.render_frame(scene)
     gpu = r.read_accum()[..., :3] / spp
     cpu = orc.render(scene, 2, 0, spp, 12, n_threads=orc.max_threads())[..., :3] / spp
-    assert abs(gpu.mean() - cpu.mean()) / cpu.mean() < 0.01
     for c in range(3):
-        assert abs(gpu[..., c].mean() - cpu[..., c].mean()) / cpu[..., c].mean() < 0.015
-    g8 = np.clip(gpu, 0, 1); c8 = np.clip(cpu, 0, 1)
-    mse = float(((g8 - c8) ** 2).mean())
+        assert abs(gpu[..., c].mean() - cpu[..., c].mean()) / cpu[..., c].mean() < 2e-3
+    mse = float(((np.clip(gpu, 0, 1) - np.clip(cpu, 0, 1)) ** 2).mean())
     psnr = 10 * np.log10(1.0 / mse)
-    assert psnr > 25.0            # 256 spp each side, independent noise; see test_psnr_converged for the 40 dB gate
+    assert psnr >= 40.0, psnr
     r.close()
 
 
