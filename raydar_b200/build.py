@@ -24,7 +24,10 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "raydar_cuda.h"), __file__]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "raydar_cuda.h"), __file__,
+            os.path.join(HERE, "host", "raydar_cuda_main.cpp")]
+    if not os.path.exists(os.path.join(HERE, "host", "raydar-cuda")):
+        return True
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -46,7 +49,20 @@ def build(force: bool = False, verbose: bool = False, extra: list[str] | None = 
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
+    build_cli()
     return LIB
+
+
+def build_cli() -> str:
+    """raydar-cuda: the headless driver (mirror of the reference's `raydar` binary) linked against the library."""
+    exe = os.path.join(HERE, "host", "raydar-cuda")
+    cmd = ["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-std=c++17", "-Wall",
+           "-I", os.path.join(ROOT, "include"), os.path.join(HERE, "host", "raydar_cuda_main.cpp"),
+           "-L", HERE, "-lraydar_cuda", "-Wl,-rpath,$ORIGIN/..", "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return exe
 
 
 if __name__ == "__main__":

@@ -53,6 +53,8 @@ struct RdrRenderer {
     FrameParams params{};
     unsigned char *d_blob = nullptr; size_t blob_capacity = 0;
     rdr::f4 *d_accum = nullptr; uchar4 *d_rgba = nullptr; size_t pixel_capacity = 0;
+    uint32_t *d_counter = nullptr;       // pixel hand-out counter of the persistent render kernel
+    int resident_ctas = 0;
     uint32_t sample_count = 0;
     uint64_t launches = 0;
 
@@ -110,7 +112,8 @@ int render_launch(RdrRenderer *r, uint32_t n)
     P.sample_count = n;
     P.max_bounces = r->config.max_bounces;
     RDR_CUDA(r, cudaEventRecord(r->ev_start, r->stream));
-    RDR_CUDA(r, rdr::launch_render(P, r->use_cull, r->stream));
+    if (r->resident_ctas <= 0) RDR_CUDA(r, rdr::render_resident_ctas(P.lay, r->use_cull, &r->resident_ctas));
+    RDR_CUDA(r, rdr::launch_render(P, r->use_cull, r->resident_ctas, r->stream));
     RDR_CUDA(r, cudaEventRecord(r->ev_stop, r->stream));
     r->launches += 1;
     return RDR_OK;
@@ -200,6 +203,7 @@ void rdr_destroy(RdrRenderer *r)
     if (r->d_blob) cudaFree(r->d_blob);
     if (r->d_accum) cudaFree(r->d_accum);
     if (r->d_rgba) cudaFree(r->d_rgba);
+    if (r->d_counter) cudaFree(r->d_counter);
     if (r->ev_start) cudaEventDestroy(r->ev_start);
     if (r->ev_stop) cudaEventDestroy(r->ev_stop);
     if (r->stream) cudaStreamDestroy(r->stream);
@@ -252,8 +256,11 @@ int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene)
     if (n_pixels) RDR_CUDA(r, cudaMemsetAsync(r->d_accum, 0, n_pixels * sizeof(rdr::f4), r->stream));
     RDR_CUDA(r, cudaStreamSynchronize(r->stream));   // blob is a local vector: finish the upload before it dies
 
+    if (!r->d_counter) RDR_CUDA(r, cudaMalloc(&r->d_counter, sizeof(uint32_t)));
     P.blob = r->d_blob;
     P.accum = r->d_accum;
+    P.pixel_counter = r->d_counter;
+    r->resident_ctas = 0;                // depends on the scene's shared-memory footprint: recomputed at the next launch
     P.seed_lo = (uint32_t)r->seed; P.seed_hi = (uint32_t)(r->seed >> 32);
     r->params = P;
     r->sample_count = 0;
@@ -418,6 +425,7 @@ int rdr_debug_set_cull(RdrRenderer *r, int enabled)
 {
     if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
     r->use_cull = enabled != 0;
+    r->resident_ctas = 0;
     return RDR_OK;
 }
 

@@ -21,8 +21,10 @@
 #if defined(__CUDACC__)
 #define RDR_HD __host__ __device__ __forceinline__
 #define RDR_UNROLL _Pragma("unroll")
+#define RDR_NOUNROLL _Pragma("unroll 1")
 #else
 #define RDR_UNROLL
+#define RDR_NOUNROLL
 #define RDR_HD inline
 #include <math.h>
 #endif

@@ -15,11 +15,17 @@
 
 namespace rdr {
 
-// ---- the sample loop: one lane = one pixel (LaneState / lane_shade / trace_brute in rdr_trace.cuh) ---------
-// Warp lock-step: each iteration every lane with work left shades until it holds a ray, the warp votes
-// (__any_sync is also the reconvergence point -- without it Volta+ independent thread scheduling lets the
-// lanes drift apart until each executes the scan alone), then the live lanes run the scan together.
-// No lane returns early: lanes past the end of the image take part in the votes with alive = false.
+// ---- the sample loop (LaneState / lane_shade / trace_brute in rdr_trace.cuh) ------------------------------
+// Persistent lanes in warp lock-step.  The grid is sized to the machine (SMs x resident CTAs), not to the
+// image.  Each iteration:
+//   1. a lane without work claims the next unclaimed pixel (one atomicAdd on a global counter; pixels are
+//      handed out in row-major order, so a warp works on neighbouring pixels) and sets up its primary ray;
+//   2. the warp votes (__any_sync doubles as the reconvergence point -- without it Volta+ independent thread
+//      scheduling lets the lanes drift apart until each executes the scan alone);
+//   3. every lane with a ray runs the scan together, then shades; a lane whose pixel is finished writes its
+//      accumulator (one 16-byte store per pixel per launch, after one 16-byte load when it claimed it).
+// A pixel is always processed by exactly one lane with its samples in ascending order, so results do not
+// depend on the schedule (bit-identical to the per-pixel host loop).
 template <bool USE_CULL>
 __global__ void __launch_bounds__(RDR_BLOCK, 2) render_kernel(const __grid_constant__ FrameParams P)
 {
@@ -27,19 +33,25 @@ __global__ void __launch_bounds__(RDR_BLOCK, 2) render_kernel(const __grid_const
     stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
     const SceneView S = scene_view(smem, P.lay);
     uint32_t *masks = mask_base(smem, P.lay) + threadIdx.x;
-    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = pixel < P.cam.width * P.cam.height;
+    const uint32_t n_pixels = P.cam.width * P.cam.height;
 
     LaneState st;
-    f4 acc; acc.x = acc.y = acc.z = acc.w = 0.0f;
-    if (valid) acc = P.accum[pixel];                     // one coalesced 16-byte load per pixel per launch
-    lane_begin<USE_CULL>(P, S, masks, blockDim.x, pixel, valid, acc, st);
+    lane_init(st, masks);
+    bool exhausted = false;
     for (;;) {
-        if (st.alive) lane_shade(P, S, pixel, st);
+        while (!st.alive && !exhausted) {
+            const uint32_t pixel = atomicAdd(P.pixel_counter, 1u);
+            if (pixel >= n_pixels) { exhausted = true; break; }
+            lane_start_pixel(P, pixel, P.accum[pixel], st);
+            if (!st.alive) P.accum[pixel] = st.acc;      // nothing to trace (no samples or no bounces)
+        }
         if (!__any_sync(0xffffffffu, st.alive)) break;
-        if (st.alive) st.hit = trace_brute<USE_CULL>(S, P.cull, masks, blockDim.x, st.ro, st.rd);
+        if (st.alive) {
+            lane_accept_hit(st, trace_brute<USE_CULL>(S, P.cull, masks, blockDim.x, st.ro, st.rd));
+            lane_shade(P, S, st);
+            if (!st.alive) P.accum[st.pixel] = st.acc;
+        }
     }
-    if (valid) P.accum[pixel] = st.acc;                  // ... and one 16-byte store
 }
 
 // ---- print_frame_buffer (cpu.rs:221-230): one uchar4 (32-bit) store per pixel ------------------------
@@ -163,13 +175,17 @@ static cudaError_t set_smem(K kernel, size_t bytes)
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-cudaError_t launch_render(const FrameParams &P, bool use_cull, cudaStream_t stream)
+cudaError_t launch_render(const FrameParams &P, bool use_cull, int resident_ctas, cudaStream_t stream)
 {
     const uint32_t n_pixels = P.cam.width * P.cam.height;
     if (n_pixels == 0u) return cudaSuccess;
     const size_t smem = brute_smem_bytes(P.lay, RDR_BLOCK);
-    const uint32_t grid = (n_pixels + RDR_BLOCK - 1u) / RDR_BLOCK;
-    cudaError_t e;
+    // persistent grid: every resident CTA slot of the device, but no more CTAs than there are pixels to hand out
+    uint32_t grid = (uint32_t)(resident_ctas > 0 ? resident_ctas : 1);
+    const uint32_t needed = (n_pixels + RDR_BLOCK - 1u) / RDR_BLOCK;
+    if (grid > needed) grid = needed;
+    cudaError_t e = cudaMemsetAsync(P.pixel_counter, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
     if (use_cull) {
         if ((e = set_smem(render_kernel<true>, smem)) != cudaSuccess) return e;
         render_kernel<true><<<grid, RDR_BLOCK, smem, stream>>>(P);
@@ -178,6 +194,26 @@ cudaError_t launch_render(const FrameParams &P, bool use_cull, cudaStream_t stre
         render_kernel<false><<<grid, RDR_BLOCK, smem, stream>>>(P);
     }
     return cudaGetLastError();
+}
+
+// resident CTAs of render_kernel on the current device for this scene's shared-memory footprint
+cudaError_t render_resident_ctas(const SceneLayout &L, bool use_cull, int *out)
+{
+    const size_t smem = brute_smem_bytes(L, RDR_BLOCK);
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if (use_cull) {
+        if ((e = set_smem(render_kernel<true>, smem)) != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<true>, RDR_BLOCK, smem);
+    } else {
+        if ((e = set_smem(render_kernel<false>, smem)) != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<false>, RDR_BLOCK, smem);
+    }
+    if (e != cudaSuccess) return e;
+    *out = sms * (per_sm > 0 ? per_sm : 1);
+    return cudaSuccess;
 }
 
 cudaError_t launch_resolve(const f4 *accum, uchar4 *out, uint32_t n_pixels, float divisor, cudaStream_t stream)

@@ -39,6 +39,7 @@ struct FrameParams {
     SceneLayout lay;
     const unsigned char *blob;           // device copy of the packed scene
     f4 *accum;                           // W*H float RGBA accumulator (row-major, top row first)
+    uint32_t *pixel_counter;             // next unclaimed pixel of this launch (zeroed before the launch)
     uint32_t seed_lo, seed_hi;
     uint32_t max_bounces;
     uint32_t sample_begin;               // global index of the first sample of this launch

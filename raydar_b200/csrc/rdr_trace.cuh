@@ -73,12 +73,16 @@ RDR_HD Hit trace_brute(const SceneView &S, const CullConsts &cc, uint32_t *masks
         uint32_t m = 0u;
         if (USE_CULL) {
             const f4 *p = S.sphere_cull + ch * 32u;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 8
-#endif
-            for (int j = 0; j < 32; ++j) {
-                const f4 s = p[j];
-                if (sphere_may_hit(o, d, rc, s.x, s.y, s.z, s.w)) m |= (1u << j);
+            // groups of 8 with compile-time bit positions: one predicated OR-immediate per primitive
+            RDR_NOUNROLL
+            for (int g = 0; g < 4; ++g) {
+                uint32_t mm = 0u;
+                RDR_UNROLL
+                for (int j = 0; j < 8; ++j) {
+                    const f4 s = p[g * 8 + j];
+                    if (sphere_may_hit(o, d, rc, s.x, s.y, s.z, s.w)) mm |= (1u << j);
+                }
+                m |= mm << (g * 8);
             }
         }
         if (all) m = 0xffffffffu;
@@ -109,12 +113,15 @@ RDR_HD Hit trace_brute(const SceneView &S, const CullConsts &cc, uint32_t *masks
             uint32_t m = 0u;
             if (USE_CULL) {
                 const f4 *p = S.cube_cull + ch * 32u;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 8
-#endif
-                for (int j = 0; j < 32; ++j) {
-                    const f4 c = p[j];
-                    if (cube_may_hit(rc, c.x, c.y, c.z, c.w, prune)) m |= (1u << j);
+                RDR_NOUNROLL
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t mm = 0u;
+                    RDR_UNROLL
+                    for (int j = 0; j < 8; ++j) {
+                        const f4 c = p[g * 8 + j];
+                        if (cube_may_hit(rc, c.x, c.y, c.z, c.w, prune)) mm |= (1u << j);
+                    }
+                    m |= mm << (g * 8);
                 }
             }
             if (all) m = 0xffffffffu;
@@ -150,17 +157,18 @@ RDR_HD uint32_t lane_varying_zero(uint32_t *scratch)
 
 // ---- the sample loop of one pixel ----------------------------------------------------------------------
 // Loop structure ("sample refill"): the reference nests samples > pixels > bounces.  A lane here owns a
-// pixel and alternates two phases until its samples are used up:
-//   lane_shade  shade the lane's current hit; when the path ends (miss, or max_bounces traces used) finish
-//               the sample and immediately start the pixel's next one, shading its cached primary hit, until
-//               the lane holds a ray that needs tracing (or has no samples left);
-//   trace       nearest hit of that ray.
-// The render kernel runs the two phases in warp lock-step (one __any_sync per iteration is the reconvergence
-// point), so every lane that still has work enters every trace with a live ray and the scan -- >90 % of the
-// instructions -- runs converged no matter how path lengths differ between the lanes of a warp.
+// pixel and alternates two phases until the pixel's samples are used up:
+//   trace       nearest hit of the lane's current ray (the first one is the pixel's primary ray);
+//   lane_shade  shade that hit; when the path ends (miss, or max_bounces traces used) finish the sample and
+//               immediately start the pixel's next one, shading its cached primary hit, until the lane holds
+//               a ray that needs tracing (or the pixel is finished).
+// The render kernel runs the phases in warp lock-step (one __any_sync per iteration is the reconvergence
+// point) and hands a lane whose pixel is finished the next unclaimed pixel, so every lane enters every
+// trace with a live ray and the scan -- >90 % of the instructions -- runs converged no matter how path
+// lengths differ between pixels.
 //
 // The camera ray has no jitter (cpu.rs:199-202), so all samples of a pixel share the primary ray and its
-// nearest hit; it is traced once per launch and reused (bit-identical results).
+// nearest hit; it is traced once per pixel per launch and reused (bit-identical results).
 //
 // Per-pixel accumulation order is sample-ascending, as in the reference, so a launch over samples
 // [s0, s0+n) on top of an accumulator that already holds [0, s0) is bit-identical to one launch.
@@ -170,42 +178,55 @@ struct LaneState {
     Hit h0;                 // cached primary hit
     Hit hit;                // hit to shade next
     v3 ro, rd, light, atten;
-    uint32_t s, bounce, lane_zero;
-    bool alive;             // the lane holds (or will hold) a ray to trace
+    uint32_t pixel, s, bounce, lane_zero;
+    bool alive;             // the lane holds a ray to trace
+    bool primary_pending;   // that ray is the pixel's primary ray
 };
 
-template <bool USE_CULL>
-RDR_HD void lane_begin(const FrameParams &P, const SceneView &S, uint32_t *masks, uint32_t stride, uint32_t pixel,
-                       bool valid, f4 acc, LaneState &st, TraceStats *stats = nullptr)
+// ptxas 12.9 (sm_100a) promotes a counter that starts from a constant and is stepped by a constant to a
+// UNIFORM register even when lanes step it at different times (observed: the sample counter in UR4 with
+// UIADD3/UISETP/BRA.U, all lanes of a warp sharing it -> too few samples per pixel).  Starting the per-lane
+// counters from a value the compiler must treat as lane-varying (a volatile read-back of the lane's scratch
+// word) keeps them in vector registers.  tests/test_gpu_parity.py::test_accumulator_bit_exact guards this.
+RDR_HD void lane_init(LaneState &st, uint32_t *masks)
 {
-    // ptxas 12.9 (sm_100a) promotes a counter that starts from a constant and is stepped by a constant to a
-    // UNIFORM register even when lanes step it at different times (observed: the sample counter in UR4 with
-    // UIADD3/UISETP/BRA.U, all lanes of a warp sharing it -> too few samples per pixel).  Starting the per-lane
-    // counters from a value the compiler must treat as lane-varying (a volatile read-back of the lane's scratch
-    // word) keeps them in vector registers.  tests/test_gpu_parity.py::test_accumulator_bit_exact guards this.
     st.lane_zero = lane_varying_zero(masks);
-    st.acc = acc;
+    st.alive = false; st.primary_pending = false;
+    st.pixel = 0u; st.s = st.lane_zero; st.bounce = st.lane_zero;
+    st.acc.x = st.acc.y = st.acc.z = st.acc.w = 0.0f;
+    st.cam_d = st.ro = st.rd = st.light = st.atten = mk3(0.0f, 0.0f, 0.0f);
+    st.h0.idx = -1; st.h0.t = 0.0f; st.hit = st.h0;
+}
+
+// take ownership of `pixel` (acc = its current accumulator).  Afterwards either st.alive (the primary ray is
+// waiting to be traced) or the pixel is already finished (no samples / no bounces) and st.acc is final.
+RDR_HD void lane_start_pixel(const FrameParams &P, uint32_t pixel, f4 acc, LaneState &st)
+{
+    st.pixel = pixel; st.acc = acc;
     st.s = st.lane_zero; st.bounce = st.lane_zero;
-    st.alive = valid && P.sample_count > 0u;
     st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
     st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
-    st.cam_d = st.rd = mk3(0.0f, 0.0f, 0.0f);
-    st.h0.idx = -1; st.h0.t = 0.0f;
-    if (valid && P.max_bounces == 0u) {       // `for _ in 0..0`: light stays zero, alpha still accumulates
+    if (P.max_bounces == 0u) {                // `for _ in 0..0`: light stays zero, alpha still accumulates
         for (uint32_t s = 0; s < P.sample_count; ++s) {
             st.acc.x = fadd(st.acc.x, 0.0f); st.acc.y = fadd(st.acc.y, 0.0f); st.acc.z = fadd(st.acc.z, 0.0f); st.acc.w = fadd(st.acc.w, 1.0f);
         }
         st.alive = false;
+        return;
     }
-    if (st.alive) {
-        st.cam_d = st.rd = camera_ray_dir(P.cam, pixel % P.cam.width, pixel / P.cam.width);
-        st.h0 = trace_brute<USE_CULL>(S, P.cull, masks, stride, st.ro, st.rd, stats);
-    }
-    st.hit = st.h0;
+    st.alive = P.sample_count > 0u;
+    st.primary_pending = st.alive;
+    if (st.alive) st.cam_d = st.rd = camera_ray_dir(P.cam, pixel % P.cam.width, pixel / P.cam.width);
 }
 
-// runs until the lane has a ray that needs tracing (st.alive) or has used all its samples (!st.alive)
-RDR_HD void lane_shade(const FrameParams &P, const SceneView &S, uint32_t pixel, LaneState &st)
+// the traced hit of the lane's current ray arrives
+RDR_HD void lane_accept_hit(LaneState &st, Hit h)
+{
+    if (st.primary_pending) { st.h0 = h; st.primary_pending = false; }
+    st.hit = h;
+}
+
+// runs until the lane has a ray that needs tracing (st.alive) or the pixel is finished (!st.alive)
+RDR_HD void lane_shade(const FrameParams &P, const SceneView &S, LaneState &st)
 {
     for (;;) {
         bool terminated;
@@ -214,7 +235,7 @@ RDR_HD void lane_shade(const FrameParams &P, const SceneView &S, uint32_t pixel,
             const Material m = load_material(S, st.hit.idx, &is_sphere);
             const f4 g = S.obj_geom[st.hit.idx];
             const Surface sf = closest_hit(st.ro, st.rd, st.hit.t, is_sphere, mk3(g.x, g.y, g.z), g.w);
-            const Scatter sc = scatter(st.rd, sf, m, P.seed_lo, P.seed_hi, pixel, P.sample_begin + st.s, st.bounce);
+            const Scatter sc = scatter(st.rd, sf, m, P.seed_lo, P.seed_hi, st.pixel, P.sample_begin + st.s, st.bounce);
             st.ro = sc.origin; st.rd = sc.dir;
             st.atten = mul3(st.atten, m.albedo);
             st.light = add3(st.light, scale3(m.emission, m.emission_strength));
@@ -234,17 +255,17 @@ RDR_HD void lane_shade(const FrameParams &P, const SceneView &S, uint32_t pixel,
     }
 }
 
-// scalar driver of the two phases (host simulation; the kernel drives them in warp lock-step instead)
+// scalar driver of the phases for one pixel (host simulation; the kernel drives them in warp lock-step)
 template <bool USE_CULL>
 RDR_HD f4 render_pixel(const FrameParams &P, const SceneView &S, uint32_t *masks, uint32_t stride, uint32_t pixel, f4 acc,
                        TraceStats *stats = nullptr)
 {
     LaneState st;
-    lane_begin<USE_CULL>(P, S, masks, stride, pixel, true, acc, st, stats);
+    lane_init(st, masks);
+    lane_start_pixel(P, pixel, acc, st);
     while (st.alive) {
-        lane_shade(P, S, pixel, st);
-        if (!st.alive) break;
-        st.hit = trace_brute<USE_CULL>(S, P.cull, masks, stride, st.ro, st.rd, stats);
+        lane_accept_hit(st, trace_brute<USE_CULL>(S, P.cull, masks, stride, st.ro, st.rd, stats));
+        lane_shade(P, S, st);
     }
     return st.acc;
 }
