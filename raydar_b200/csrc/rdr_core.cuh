@@ -400,15 +400,16 @@ RDR_HD bool sphere_may_hit(v3 o, v3 d, const RayCull &rc, float cx, float cy, fl
 
 // cube cull datum: (cx, cy, cz, h + pad).  best = current best exact t (+inf if none):
 // a cube whose padded entry distance exceeds it cannot win (ties need tn == best: kept).
+// One comparison decides: reject when max(tn, 0) > min(tf, best), which covers "behind the origin"
+// (tf < 0 <= max(tn, 0)), "missed" (tn > tf) and "cannot win" (tn > best >= 0).
 RDR_HD bool cube_may_hit(const RayCull &rc, float cx, float cy, float cz, float hp, float best)
 {
     float tcx = fma(cx, rc.inv.x, fneg(rc.od.x));
     float tcy = fma(cy, rc.inv.y, fneg(rc.od.y));
     float tcz = fma(cz, rc.inv.z, fneg(rc.od.z));
-    float tn = fmax(fmax(fma(fneg(hp), rc.ainv.x, tcx), fma(fneg(hp), rc.ainv.y, tcy)), fma(fneg(hp), rc.ainv.z, tcz));
-    float tf = fmin(fmin(fma(hp, rc.ainv.x, tcx), fma(hp, rc.ainv.y, tcy)), fma(hp, rc.ainv.z, tcz));
-    bool reject = (tn > fmin(tf, best)) || (tf < 0.0f);
-    return !reject;
+    float tn = fmax(fmax(fma(fneg(hp), rc.ainv.x, tcx), fma(fneg(hp), rc.ainv.y, tcy)), fmax(fma(fneg(hp), rc.ainv.z, tcz), 0.0f));
+    float tf = fmin(fmin(fma(hp, rc.ainv.x, tcx), fma(hp, rc.ainv.y, tcy)), fmin(fma(hp, rc.ainv.z, tcz), best));
+    return !(tn > tf);
 }
 
 }  // namespace rdr

@@ -27,7 +27,7 @@ namespace rdr {
 // A pixel is always processed by exactly one lane with its samples in ascending order, so results do not
 // depend on the schedule (bit-identical to the per-pixel host loop).
 template <bool USE_CULL>
-__global__ void __launch_bounds__(RDR_BLOCK, 2) render_kernel(const __grid_constant__ FrameParams P)
+__global__ void __launch_bounds__(RDR_BLOCK, 3) render_kernel(const __grid_constant__ FrameParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
