@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0x5EED)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--accel", default="auto", choices=["auto", "brute", "bvh"], help="nearest-hit search of the CUDA backend")
     return ap.parse_args()
 
 
@@ -181,6 +182,7 @@ def run_b200(a):
     n_pixels = a.width * a.height
     r = rb.Renderer(rb.RendererConfig(a.spp, a.bounces), device=local)
     r.set_seed(a.seed)
+    r.set_accel({"auto": rb.ACCEL_AUTO, "brute": rb.ACCEL_BRUTE, "bvh": rb.ACCEL_BVH}[a.accel])
     r.set_sample_offset(rank * a.spp)                    # weak scaling: every rank renders spp samples of its own range
     r.new_frame(flat)
     ptr, nbytes = r.accum_device_ptr()
@@ -263,7 +265,7 @@ def run_b200(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "parallelism": f"sample-range x{world}",
+            "config": {"workload": workload_name(a), "parallelism": f"sample-range x{world}", "accel": a.accel,
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
                        "step": "fresh accumulator + spp samples/pixel in one kernel launch"
                                + (" + NCCL reduce to rank 0" if world > 1 else "") + " + resolve to RGBA8"},

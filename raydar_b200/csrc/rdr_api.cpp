@@ -20,6 +20,11 @@
 using rdr::FrameParams;
 using rdr::SceneLayout;
 
+// RDR_ACCEL_AUTO switches from the brute-force scan to the BVH above this many objects
+#ifndef RDR_AUTO_BVH_THRESHOLD
+#define RDR_AUTO_BVH_THRESHOLD 1024u
+#endif
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -86,7 +91,9 @@ int fail(RdrRenderer *r, int status, const char *fmt, ...)
 int pack_scene(RdrRenderer *r, const RdrSceneFlat *sc, std::vector<unsigned char> &blob, FrameParams &P)
 {
     std::string err;
-    const int st = rdr::pack_scene_blob(sc, blob, P, err);
+    // RDR_ACCEL_AUTO: the scan for tiny scenes (one or two list chunks), the hierarchy otherwise
+    const bool use_bvh = r->accel == RDR_ACCEL_BVH || (r->accel == RDR_ACCEL_AUTO && sc && sc->n_objects > RDR_AUTO_BVH_THRESHOLD);
+    const int st = rdr::pack_scene_blob(sc, use_bvh, blob, P, err);
     return st == RDR_OK ? RDR_OK : fail(r, st, "%s", err.c_str());
 }
 
@@ -112,7 +119,7 @@ int render_launch(RdrRenderer *r, uint32_t n)
     P.sample_count = n;
     P.max_bounces = r->config.max_bounces;
     RDR_CUDA(r, cudaEventRecord(r->ev_start, r->stream));
-    if (r->resident_ctas <= 0) RDR_CUDA(r, rdr::render_resident_ctas(P.lay, r->use_cull, &r->resident_ctas));
+    if (r->resident_ctas <= 0) RDR_CUDA(r, rdr::render_resident_ctas(P, r->use_cull, &r->resident_ctas));
     RDR_CUDA(r, rdr::launch_render(P, r->use_cull, r->resident_ctas, r->stream));
     RDR_CUDA(r, cudaEventRecord(r->ev_stop, r->stream));
     r->launches += 1;
@@ -226,13 +233,20 @@ int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene)
     FrameParams P{};
     if ((st = pack_scene(r, scene, blob, P)) != RDR_OK) { r->has_frame = false; return st; }
 
-    cudaDeviceProp prop;
-    RDR_CUDA(r, cudaGetDeviceProperties(&prop, r->device));
-    const size_t smem_need = rdr::brute_smem_bytes(P.lay, RDR_BLOCK);
-    if (smem_need > (size_t)prop.sharedMemPerBlockOptin) {
-        r->has_frame = false;
-        return fail(r, RDR_ERR_UNSUPPORTED, "scene needs %zu B of shared memory for the brute-force scan (limit %zu); "
-                    "the BVH path is required for scenes this large", smem_need, (size_t)prop.sharedMemPerBlockOptin);
+    // stage the blob in shared memory when it leaves room for >= 2 resident CTAs per SM; the scan always needs it there
+    int smem_optin = 0, smem_sm = 0;
+    RDR_CUDA(r, cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, r->device));
+    RDR_CUDA(r, cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, r->device));
+    const size_t staged_need = rdr::scene_smem_bytes(P.lay, true, RDR_BLOCK);
+    if (P.lay.mode == 1u) {
+        P.staged = (staged_need + 1024u) * 2u <= (size_t)smem_sm && staged_need <= (size_t)smem_optin ? 1u : 0u;
+    } else {
+        P.staged = 1u;
+        if (staged_need > (size_t)smem_optin) {
+            r->has_frame = false;
+            return fail(r, RDR_ERR_UNSUPPORTED, "scene needs %zu B of shared memory for the brute-force scan (limit %d); use RDR_ACCEL_BVH / AUTO",
+                        staged_need, smem_optin);
+        }
     }
 
     if (blob.size() > r->blob_capacity) {

@@ -1,0 +1,162 @@
+// rdr_bvh.h -- host-side builder of the 8-wide bounding-volume hierarchy used for scenes that are too large
+// (or simply faster that way) for the brute-force scan.  Pure host C++.
+//
+// The hierarchy only PRE-SELECTS primitives; the winner is still decided by the exact, reference-ordered
+// tests and the (t, original index) rule of trace_ray (cpu.rs:344-352), so the nearest hit -- including the
+// "first minimum wins" tie-break -- is identical to the linear scan.  For that the boxes must be conservative
+// with respect to the AS-WRITTEN f32 tests (see rdr_core.cuh):
+//   cube      half-extent = |side|/2 + cube_pad                        (cube_pad = 2^-18 * B, as in the scan)
+//   sphere    half-extent = r + cube_pad + sphere_fixed_pad, and the entry is flagged: the traversal adds a
+//             per-ray term rho(|o|) that covers the cancellation noise of the reference's expanded quadratic
+//             (up to 32u * (2|o|^2 + q_max) on r^2), which depends on the ray origin and cannot be baked in.
+//   internal  box = union of the children's boxes; flagged when any descendant is a sphere.
+//
+// Node = 8 entries of 32 bytes (two 16-byte quads):
+//   quad 0: (cx, cy, cz, ex)      quad 1: (ey, ez, payload bits, sphere flag 0.0|1.0)
+//   payload: bit 31 = primitive (else child node index), bit 30 = cube (primitive only), low 30 bits = index.
+//   unused entries have e = -1 (the slab test rejects them).
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "raydar_cuda.h"
+
+namespace rdr {
+
+constexpr uint32_t BVH_PRIM_BIT = 0x80000000u;
+constexpr uint32_t BVH_CUBE_BIT = 0x40000000u;
+constexpr uint32_t BVH_INDEX_MASK = 0x3fffffffu;
+constexpr int BVH_WIDTH = 8;
+constexpr int BVH_MAX_DEPTH = 8;            // the traversal stack (64 entries) holds 7 * depth + 8
+
+struct BvhBox { float c[3], e[3]; bool sphere; };
+
+struct BvhBuildPrim { float c[3]; float e; uint32_t index; bool cube; };
+
+class BvhBuilder {
+public:
+    std::vector<float> nodes;               // 64 floats per node
+    int max_depth = 0;
+
+    // returns false when the tree would be deeper than BVH_MAX_DEPTH (caller falls back to the scan)
+    bool build(std::vector<BvhBuildPrim> prims)
+    {
+        nodes.clear(); max_depth = 0;
+        prims_ = std::move(prims);
+        order_.resize(prims_.size());
+        for (size_t i = 0; i < order_.size(); ++i) order_[i] = (uint32_t)i;
+        alloc_node();
+        if (!prims_.empty()) fill_node(0, 0, (uint32_t)order_.size(), 1);
+        return max_depth <= BVH_MAX_DEPTH;
+    }
+
+    uint32_t n_nodes() const { return (uint32_t)(nodes.size() / 64); }
+
+private:
+    std::vector<BvhBuildPrim> prims_;
+    std::vector<uint32_t> order_;
+
+    uint32_t alloc_node()
+    {
+        const uint32_t id = n_nodes();
+        nodes.resize(nodes.size() + 64, 0.0f);
+        for (int k = 0; k < BVH_WIDTH; ++k) set_entry(id, k, BvhBox{{0, 0, 0}, {-1, -1, -1}, false}, 0u);
+        return id;
+    }
+
+    void set_entry(uint32_t node, int k, const BvhBox &b, uint32_t payload)
+    {
+        float *p = nodes.data() + (size_t)node * 64 + k * 8;
+        p[0] = b.c[0]; p[1] = b.c[1]; p[2] = b.c[2]; p[3] = b.e[0];
+        p[4] = b.e[1]; p[5] = b.e[2];
+        memcpy(&p[6], &payload, 4);
+        p[7] = b.sphere ? 1.0f : 0.0f;
+    }
+
+    BvhBox prim_box(const BvhBuildPrim &p) const
+    {
+        return BvhBox{{p.c[0], p.c[1], p.c[2]}, {p.e, p.e, p.e}, !p.cube};
+    }
+
+    // box of order_[b, e): centre/half-extent form, rounded outwards
+    BvhBox range_box(uint32_t b, uint32_t e) const
+    {
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        bool sphere = false;
+        for (uint32_t i = b; i < e; ++i) {
+            const BvhBuildPrim &p = prims_[order_[i]];
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p.c[a] - p.e); hi[a] = std::max(hi[a], p.c[a] + p.e); }
+            sphere |= !p.cube;
+        }
+        BvhBox box; box.sphere = sphere;
+        for (int a = 0; a < 3; ++a) {
+            box.c[a] = 0.5f * (lo[a] + hi[a]);
+            // outward rounding: the half-extent must cover both ends from the rounded centre
+            const float h = std::max(hi[a] - box.c[a], box.c[a] - lo[a]);
+            box.e[a] = std::nextafter(h * (1.0f + 1e-6f), INFINITY);
+        }
+        return box;
+    }
+
+    // splits order_[b, e) into k spatially coherent groups (k-way median split along the largest axis, recursively)
+    void split(uint32_t b, uint32_t e, int k, std::vector<std::pair<uint32_t, uint32_t>> &out)
+    {
+        if (k <= 1 || e - b <= 1) { out.emplace_back(b, e); return; }
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t i = b; i < e; ++i)
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], prims_[order_[i]].c[a]); hi[a] = std::max(hi[a], prims_[order_[i]].c[a]); }
+        int axis = 0;
+        if (hi[1] - lo[1] > hi[axis] - lo[axis]) axis = 1;
+        if (hi[2] - lo[2] > hi[axis] - lo[axis]) axis = 2;
+        const int kl = k / 2, kr = k - kl;
+        uint32_t mid = b + (uint32_t)(((uint64_t)(e - b) * kl) / k);
+        mid = std::max(b + 1, std::min(e - 1, mid));
+        std::nth_element(order_.begin() + b, order_.begin() + mid, order_.begin() + e,
+                         [&](uint32_t x, uint32_t y) { return prims_[x].c[axis] < prims_[y].c[axis]; });
+        split(b, mid, kl, out);
+        split(mid, e, kr, out);
+    }
+
+    void fill_node(uint32_t node, uint32_t b, uint32_t e, int depth)
+    {
+        max_depth = std::max(max_depth, depth);
+        const uint32_t n = e - b;
+        int slot = 0;
+        if (n <= (uint32_t)BVH_WIDTH) {
+            for (uint32_t i = b; i < e; ++i) emit_prim(node, slot++, prims_[order_[i]]);
+            return;
+        }
+        // primitives that are large compared with the node (a floor cube, a room) become direct entries:
+        // inside a spatial group they would blow its box up to the whole node
+        const BvhBox nb = range_box(b, e);
+        const float big = 0.3f * std::max(nb.e[0], std::max(nb.e[1], nb.e[2]));
+        uint32_t rest = b;
+        for (uint32_t i = b; i < e && slot < 3; ++i) {
+            if (prims_[order_[i]].e > big) {
+                emit_prim(node, slot++, prims_[order_[i]]);
+                std::swap(order_[i], order_[rest]);
+                ++rest;
+            }
+        }
+        std::vector<std::pair<uint32_t, uint32_t>> groups;
+        split(rest, e, BVH_WIDTH - slot, groups);
+        for (const auto &g : groups) {
+            if (g.second == g.first) continue;
+            if (g.second - g.first == 1) { emit_prim(node, slot++, prims_[order_[g.first]]); continue; }
+            const uint32_t child = alloc_node();
+            set_entry(node, slot++, range_box(g.first, g.second), child);
+            fill_node(child, g.first, g.second, depth + 1);
+        }
+    }
+
+    void emit_prim(uint32_t node, int slot, const BvhBuildPrim &p)
+    {
+        set_entry(node, slot, prim_box(p), BVH_PRIM_BIT | (p.cube ? BVH_CUBE_BIT : 0u) | (p.index & BVH_INDEX_MASK));
+    }
+};
+
+}  // namespace rdr

@@ -346,8 +346,8 @@ RDR_HD uint32_t quantise(float sum, float n)
 //     |k - d.(o-c)|        <=  4u |d| (|o|+|c|)
 //     |c - (|o-c|^2-r^2)|  <=  6u ((|o|+|c|)^2 + r^2)
 //     |disc - true|        <= 20u a S,  S = (|o|+|c|)^2 + r^2 <= 2|o|^2 + (2|c|^2 + r^2)
-//   the FMA forms below add <= 8u a S.  Margins used: M = 2^-17 a S_ray (= 128u a S_ray) on
-//   disc, Ms = 2^-17 S_ray on c, ek = 2^-19 sqrt(a S_ray) on k, with
+//   the FMA forms below add <= 8u a S.  Margins used: M = 2^-19 a S_ray (= 32u a S_ray) on
+//   disc, Ms = 2^-19 S_ray on c, ek = 2^-19 sqrt(a S_ray) on k, with
 //   S_ray = 2|o|^2 + max_spheres(2|c|^2 + r^2).
 //   cube, as written: t = ((c -+ h) - o) / d per axis, three roundings: |dt| <= 3u B' / |d_i|,
 //     B' = |c_i| + h + |o_i|; the FMA form adds <= 5u B' / |d_i|.  Cubes are padded by
@@ -359,6 +359,7 @@ RDR_HD uint32_t quantise(float sum, float n)
 struct CullConsts {
     float sphere_q_max;    // max over spheres of 2|c|^2 + r^2
     float origin_bound;    // rays with |o|_inf above this skip the cull
+    float sphere_r_min;    // smallest sphere radius (BVH: per-ray inflation of sphere boxes)
 };
 
 struct RayCull {
@@ -377,7 +378,7 @@ RDR_HD RayCull make_ray_cull(v3 o, v3 d, const CullConsts &cc)
     rc.a = fma(d.x, d.x, fma(d.y, d.y, fmul(d.z, d.z)));
     float oo = fma(o.x, o.x, fma(o.y, o.y, fmul(o.z, o.z)));
     float s_ray = fma(2.0f, oo, cc.sphere_q_max);
-    rc.Ms = fmul(7.62939453125e-06f, s_ray);                      // 2^-17 S
+    rc.Ms = fmul(1.9073486328125e-06f, s_ray);                    // 2^-19 S (32u; proven need 28u, observed 5.3u)
     rc.M = fmul(rc.a, rc.Ms);
     rc.ek = fmul(1.9073486328125e-06f, fsqrt(fmul(rc.a, s_ray))); // 2^-19 sqrt(a S)
     float omax = fmax(fmax(fabs_(o.x), fabs_(o.y)), fabs_(o.z));
@@ -409,6 +410,60 @@ RDR_HD bool cube_may_hit(const RayCull &rc, float cx, float cy, float cz, float 
     float tcz = fma(cz, rc.inv.z, fneg(rc.od.z));
     float tn = fmax(fmax(fma(fneg(hp), rc.ainv.x, tcx), fma(fneg(hp), rc.ainv.y, tcy)), fmax(fma(fneg(hp), rc.ainv.z, tcz), 0.0f));
     float tf = fmin(fmin(fma(hp, rc.ainv.x, tcx), fma(hp, rc.ainv.y, tcy)), fmin(fma(hp, rc.ainv.z, tcz), best));
+    return !(tn > tf);
+}
+
+// ---- BVH traversal helpers -------------------------------------------------------------------------------
+// Ray set-up for box tests against the 8-wide hierarchy (rdr_bvh.h).  Unlike the scan there is no O(N)
+// fallback worth taking for axis-parallel rays, so a zero / denormal direction component is handled by
+// clamping |1/d| to 1e30: the as-written slab of such an axis is (-inf, +inf) when the origin is inside it
+// and empty otherwise; the clamped slab is (-(e -+ delta) 1e30, +(e +- delta) 1e30), i.e. unbounded for every
+// hit distance below ~1e20 because the boxes are padded by >= 1e-6 (documented limit of the BVH path).
+// rho: per-ray inflation of sphere-flagged boxes, covering (a) the cancellation noise of the reference's
+// expanded sphere quadratic, r_eff^2 <= r^2 + Ms with Ms = 2^-19 (2|o|^2 + q_max), so
+// r_eff - r <= sqrt(r_min^2 + Ms) - r_min, and (b) the error of its root, <= 2^-19 sqrt(S_ray) in distance.
+struct RayBvh {
+    RayCull rc;
+    float rho;
+};
+
+RDR_HD RayBvh make_ray_bvh(v3 o, v3 d, const CullConsts &cc)
+{
+    RayBvh rb;
+    rb.rc = make_ray_cull(o, d, cc);
+    const float big = 1e30f;
+    bool clamped = false;
+    if (!(rb.rc.ainv.x < big)) { rb.rc.inv.x = u2f((f2u(d.x) & 0x80000000u) | f2u(big)); clamped = true; }
+    if (!(rb.rc.ainv.y < big)) { rb.rc.inv.y = u2f((f2u(d.y) & 0x80000000u) | f2u(big)); clamped = true; }
+    if (!(rb.rc.ainv.z < big)) { rb.rc.inv.z = u2f((f2u(d.z) & 0x80000000u) | f2u(big)); clamped = true; }
+    if (clamped) {
+        rb.rc.od = mk3(fmul(o.x, rb.rc.inv.x), fmul(o.y, rb.rc.inv.y), fmul(o.z, rb.rc.inv.z));
+        rb.rc.ainv = mk3(fabs_(rb.rc.inv.x), fabs_(rb.rc.inv.y), fabs_(rb.rc.inv.z));
+        const float omax = fmax(fmax(fabs_(o.x), fabs_(o.y)), fabs_(o.z));
+        const float s_ray = fdiv(rb.rc.Ms, 1.9073486328125e-06f);
+        // same conditions as make_ray_cull minus the 1/d test; a NaN direction component stays degenerate
+        rb.rc.degenerate = !(omax <= cc.origin_bound) || !(rb.rc.a > 1e-30f) || !(rb.rc.a < 1e30f) || !(s_ray < 1e30f) ||
+                           isnan_(d.x) || isnan_(d.y) || isnan_(d.z);
+    }
+    const float s_ray = fdiv(rb.rc.Ms, 1.9073486328125e-06f);
+    rb.rho = fadd(fsub(fsqrt(fma(cc.sphere_r_min, cc.sphere_r_min, rb.rc.Ms)), cc.sphere_r_min),
+                  fmul(1.9073486328125e-06f, fsqrt(s_ray)));
+    rb.rho = fmul(rb.rho, 1.0001f);
+    return rb;
+}
+
+// one hierarchy entry: (cx, cy, cz, ex) (ey, ez, payload, sphere flag).  Returns true when the padded box may
+// contain a hit that can still win (entry distance not beyond `best`); *tn_out = its conservative entry distance.
+RDR_HD bool bvh_entry_may_hit(const RayBvh &rb, f4 q0, f4 q1, float best, float *tn_out)
+{
+    const RayCull &rc = rb.rc;
+    const float ex = fma(q1.w, rb.rho, q0.w), ey = fma(q1.w, rb.rho, q1.x), ez = fma(q1.w, rb.rho, q1.y);
+    const float tcx = fma(q0.x, rc.inv.x, fneg(rc.od.x));
+    const float tcy = fma(q0.y, rc.inv.y, fneg(rc.od.y));
+    const float tcz = fma(q0.z, rc.inv.z, fneg(rc.od.z));
+    const float tn = fmax(fmax(fma(fneg(ex), rc.ainv.x, tcx), fma(fneg(ey), rc.ainv.y, tcy)), fmax(fma(fneg(ez), rc.ainv.z, tcz), 0.0f));
+    const float tf = fmin(fmin(fma(ex, rc.ainv.x, tcx), fma(ey, rc.ainv.y, tcy)), fmin(fma(ez, rc.ainv.z, tcz), best));
+    *tn_out = tn;
     return !(tn > tf);
 }
 

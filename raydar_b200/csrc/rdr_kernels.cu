@@ -15,6 +15,22 @@
 
 namespace rdr {
 
+// Dynamic shared memory: [scene blob (when staged)][mbarrier, 16 B][per-lane scratch words].
+// Scratch = candidate masks of the scan (one word per 32-primitive chunk) or the BVH candidate queue
+// (BVH_QCAP words), strided by the block size so that lanes hit distinct banks.
+// A scene whose blob does not fit (FrameParams::staged == 0: large BVH scenes) is read in place from
+// global memory / L2 and only the scratch words live in shared memory.
+__device__ __forceinline__ const unsigned char *stage_scene(unsigned char *smem, const FrameParams &P)
+{
+    if (!P.staged) return P.blob;
+    stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
+    return smem;
+}
+__device__ __forceinline__ uint32_t *scratch_base(unsigned char *smem, const FrameParams &P)
+{
+    return P.staged ? mask_base(smem, P.lay) : reinterpret_cast<uint32_t *>(smem);
+}
+
 // ---- the sample loop (LaneState / lane_shade / trace_brute in rdr_trace.cuh) ------------------------------
 // Persistent lanes in warp lock-step.  The grid is sized to the machine (SMs x resident CTAs), not to the
 // image.  Each iteration:
@@ -26,13 +42,12 @@ namespace rdr {
 //      accumulator (one 16-byte store per pixel per launch, after one 16-byte load when it claimed it).
 // A pixel is always processed by exactly one lane with its samples in ascending order, so results do not
 // depend on the schedule (bit-identical to the per-pixel host loop).
-template <bool USE_CULL>
+template <int MODE>
 __global__ void __launch_bounds__(RDR_BLOCK, 3) render_kernel(const __grid_constant__ FrameParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
-    const SceneView S = scene_view(smem, P.lay);
-    uint32_t *masks = mask_base(smem, P.lay) + threadIdx.x;
+    const SceneView S = scene_view(stage_scene(smem, P), P.lay);
+    uint32_t *masks = scratch_base(smem, P) + threadIdx.x;
     const uint32_t n_pixels = P.cam.width * P.cam.height;
 
     LaneState st;
@@ -47,7 +62,7 @@ __global__ void __launch_bounds__(RDR_BLOCK, 3) render_kernel(const __grid_const
         }
         if (!__any_sync(0xffffffffu, st.alive)) break;
         if (st.alive) {
-            lane_accept_hit(st, trace_brute<USE_CULL>(S, P.cull, masks, blockDim.x, st.ro, st.rd));
+            lane_accept_hit(st, trace_any<MODE>(S, P.cull, masks, blockDim.x, st.ro, st.rd));
             lane_shade(P, S, st);
             if (!st.alive) P.accum[st.pixel] = st.acc;
         }
@@ -68,54 +83,51 @@ __global__ void __launch_bounds__(256) resolve_kernel(const f4 *__restrict__ acc
 }
 
 // ---- debug / parity kernels ---------------------------------------------------------------------------
-template <bool USE_CULL>
+template <int MODE>
 __global__ void __launch_bounds__(RDR_BLOCK, 2) first_hit_kernel(const __grid_constant__ FrameParams P,
                                                                 int32_t *__restrict__ ids, float *__restrict__ ts)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
-    const SceneView S = scene_view(smem, P.lay);
-    uint32_t *masks = mask_base(smem, P.lay) + threadIdx.x;
+    const SceneView S = scene_view(stage_scene(smem, P), P.lay);
+    uint32_t *masks = scratch_base(smem, P) + threadIdx.x;
     const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
     if (pixel >= P.cam.width * P.cam.height) return;
     const v3 o = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
     const v3 d = camera_ray_dir(P.cam, pixel % P.cam.width, pixel / P.cam.width);
-    const Hit h = trace_brute<USE_CULL>(S, P.cull, masks, blockDim.x, o, d);
+    const Hit h = trace_any<MODE>(S, P.cull, masks, blockDim.x, o, d);
     ids[pixel] = h.idx;
     ts[pixel] = h.idx >= 0 ? h.t : 0.0f;
 }
 
-template <bool USE_CULL>
+template <int MODE>
 __global__ void __launch_bounds__(RDR_BLOCK, 2) kat_trace_kernel(const __grid_constant__ FrameParams P, uint32_t n,
                                                                 const float *__restrict__ rays,
                                                                 int32_t *__restrict__ ids, float *__restrict__ ts)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
-    const SceneView S = scene_view(smem, P.lay);
-    uint32_t *masks = mask_base(smem, P.lay) + threadIdx.x;
+    const SceneView S = scene_view(stage_scene(smem, P), P.lay);
+    uint32_t *masks = scratch_base(smem, P) + threadIdx.x;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const v3 o = mk3(rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]);
     const v3 d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
-    const Hit h = trace_brute<USE_CULL>(S, P.cull, masks, blockDim.x, o, d);
+    const Hit h = trace_any<MODE>(S, P.cull, masks, blockDim.x, o, d);
     ids[i] = h.idx;
     ts[i] = h.idx >= 0 ? h.t : 0.0f;
 }
 
 // one path, one thread (block of 32 so the staging code is shared; lane 0 walks the path)
-template <bool USE_CULL>
+template <int MODE>
 __global__ void __launch_bounds__(RDR_BLOCK, 2) trace_path_kernel(const __grid_constant__ FrameParams P, uint32_t x, uint32_t y,
                                                                  uint32_t sample, RdrPathStep *__restrict__ steps,
                                                                  uint32_t capacity, uint32_t *__restrict__ n_steps,
                                                                  float *__restrict__ rgba)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
-    const SceneView S = scene_view(smem, P.lay);
-    uint32_t *masks = mask_base(smem, P.lay) + threadIdx.x;
+    const SceneView S = scene_view(stage_scene(smem, P), P.lay);
+    uint32_t *masks = scratch_base(smem, P) + threadIdx.x;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    *n_steps = trace_path_lane<USE_CULL>(P, S, masks, blockDim.x, x, y, sample, steps, capacity, rgba);
+    *n_steps = trace_path_lane<MODE>(P, S, masks, blockDim.x, x, y, sample, steps, capacity, rgba);
 }
 
 __global__ void kat_hit_sphere_kernel(uint32_t n, const float *__restrict__ rays, const float *__restrict__ prims,
@@ -162,12 +174,20 @@ __global__ void kat_rng_kernel(uint32_t seed_lo, uint32_t seed_hi, uint32_t pixe
 }
 
 // ---- launch wrappers (called from rdr_api.cpp) ---------------------------------------------------------
-static inline uint32_t max_chunks(const SceneLayout &L) { return (L.ns_pad > L.nc_pad ? L.ns_pad : L.nc_pad) / 32u; }
-
-size_t brute_smem_bytes(const SceneLayout &L, uint32_t block)
+static inline uint32_t scratch_words(const SceneLayout &L)
 {
-    return (size_t)L.blob_bytes + 16u + (size_t)(max_chunks(L) ? max_chunks(L) : 1u) * block * sizeof(uint32_t);
+    if (L.mode == 1u) return (uint32_t)BVH_QCAP;
+    const uint32_t chunks = (L.ns_pad > L.nc_pad ? L.ns_pad : L.nc_pad) / 32u;
+    return chunks ? chunks : 1u;
 }
+
+size_t scene_smem_bytes(const SceneLayout &L, bool staged, uint32_t block)
+{
+    return (staged ? (size_t)L.blob_bytes + 16u : 0u) + (size_t)scratch_words(L) * block * sizeof(uint32_t);
+}
+
+// kernel variant: 0 = scan + cull, 1 = scan exact-everything (debug), 2 = BVH
+static inline int mode_of(const FrameParams &P, bool use_cull) { return P.lay.mode == 1u ? 2 : (use_cull ? 0 : 1); }
 
 template <typename K>
 static cudaError_t set_smem(K kernel, size_t bytes)
@@ -175,42 +195,42 @@ static cudaError_t set_smem(K kernel, size_t bytes)
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+#define RDR_DISPATCH(mode, KERNEL, ...)                                   \
+    do {                                                                  \
+        if ((mode) == 2) { KERNEL(2, __VA_ARGS__); }                      \
+        else if ((mode) == 1) { KERNEL(1, __VA_ARGS__); }                 \
+        else { KERNEL(0, __VA_ARGS__); }                                  \
+    } while (0)
+
 cudaError_t launch_render(const FrameParams &P, bool use_cull, int resident_ctas, cudaStream_t stream)
 {
     const uint32_t n_pixels = P.cam.width * P.cam.height;
     if (n_pixels == 0u) return cudaSuccess;
-    const size_t smem = brute_smem_bytes(P.lay, RDR_BLOCK);
+    const size_t smem = scene_smem_bytes(P.lay, P.staged != 0u, RDR_BLOCK);
     // persistent grid: every resident CTA slot of the device, but no more CTAs than there are pixels to hand out
     uint32_t grid = (uint32_t)(resident_ctas > 0 ? resident_ctas : 1);
     const uint32_t needed = (n_pixels + RDR_BLOCK - 1u) / RDR_BLOCK;
     if (grid > needed) grid = needed;
     cudaError_t e = cudaMemsetAsync(P.pixel_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    if (use_cull) {
-        if ((e = set_smem(render_kernel<true>, smem)) != cudaSuccess) return e;
-        render_kernel<true><<<grid, RDR_BLOCK, smem, stream>>>(P);
-    } else {
-        if ((e = set_smem(render_kernel<false>, smem)) != cudaSuccess) return e;
-        render_kernel<false><<<grid, RDR_BLOCK, smem, stream>>>(P);
-    }
+#define RDR_K(M, ...) do { if ((e = set_smem(render_kernel<M>, smem)) != cudaSuccess) return e; render_kernel<M><<<grid, RDR_BLOCK, smem, stream>>>(P); } while (0)
+    RDR_DISPATCH(mode_of(P, use_cull), RDR_K, 0);
+#undef RDR_K
     return cudaGetLastError();
 }
 
 // resident CTAs of render_kernel on the current device for this scene's shared-memory footprint
-cudaError_t render_resident_ctas(const SceneLayout &L, bool use_cull, int *out)
+cudaError_t render_resident_ctas(const FrameParams &P, bool use_cull, int *out)
 {
-    const size_t smem = brute_smem_bytes(L, RDR_BLOCK);
+    const size_t smem = scene_smem_bytes(P.lay, P.staged != 0u, RDR_BLOCK);
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if (use_cull) {
-        if ((e = set_smem(render_kernel<true>, smem)) != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<true>, RDR_BLOCK, smem);
-    } else {
-        if ((e = set_smem(render_kernel<false>, smem)) != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<false>, RDR_BLOCK, smem);
-    }
+#define RDR_K(M, ...) do { if ((e = set_smem(render_kernel<M>, smem)) != cudaSuccess) return e; \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<M>, RDR_BLOCK, smem); } while (0)
+    RDR_DISPATCH(mode_of(P, use_cull), RDR_K, 0);
+#undef RDR_K
     if (e != cudaSuccess) return e;
     *out = sms * (per_sm > 0 ? per_sm : 1);
     return cudaSuccess;
@@ -227,16 +247,12 @@ cudaError_t launch_first_hit(const FrameParams &P, bool use_cull, int32_t *ids, 
 {
     const uint32_t n_pixels = P.cam.width * P.cam.height;
     if (n_pixels == 0u) return cudaSuccess;
-    const size_t smem = brute_smem_bytes(P.lay, RDR_BLOCK);
+    const size_t smem = scene_smem_bytes(P.lay, P.staged != 0u, RDR_BLOCK);
     const uint32_t grid = (n_pixels + RDR_BLOCK - 1u) / RDR_BLOCK;
     cudaError_t e;
-    if (use_cull) {
-        if ((e = set_smem(first_hit_kernel<true>, smem)) != cudaSuccess) return e;
-        first_hit_kernel<true><<<grid, RDR_BLOCK, smem, stream>>>(P, ids, ts);
-    } else {
-        if ((e = set_smem(first_hit_kernel<false>, smem)) != cudaSuccess) return e;
-        first_hit_kernel<false><<<grid, RDR_BLOCK, smem, stream>>>(P, ids, ts);
-    }
+#define RDR_K(M, ...) do { if ((e = set_smem(first_hit_kernel<M>, smem)) != cudaSuccess) return e; first_hit_kernel<M><<<grid, RDR_BLOCK, smem, stream>>>(P, ids, ts); } while (0)
+    RDR_DISPATCH(mode_of(P, use_cull), RDR_K, 0);
+#undef RDR_K
     return cudaGetLastError();
 }
 
@@ -244,31 +260,23 @@ cudaError_t launch_kat_trace(const FrameParams &P, bool use_cull, uint32_t n, co
                              cudaStream_t stream)
 {
     if (n == 0u) return cudaSuccess;
-    const size_t smem = brute_smem_bytes(P.lay, RDR_BLOCK);
+    const size_t smem = scene_smem_bytes(P.lay, P.staged != 0u, RDR_BLOCK);
     const uint32_t grid = (n + RDR_BLOCK - 1u) / RDR_BLOCK;
     cudaError_t e;
-    if (use_cull) {
-        if ((e = set_smem(kat_trace_kernel<true>, smem)) != cudaSuccess) return e;
-        kat_trace_kernel<true><<<grid, RDR_BLOCK, smem, stream>>>(P, n, rays, ids, ts);
-    } else {
-        if ((e = set_smem(kat_trace_kernel<false>, smem)) != cudaSuccess) return e;
-        kat_trace_kernel<false><<<grid, RDR_BLOCK, smem, stream>>>(P, n, rays, ids, ts);
-    }
+#define RDR_K(M, ...) do { if ((e = set_smem(kat_trace_kernel<M>, smem)) != cudaSuccess) return e; kat_trace_kernel<M><<<grid, RDR_BLOCK, smem, stream>>>(P, n, rays, ids, ts); } while (0)
+    RDR_DISPATCH(mode_of(P, use_cull), RDR_K, 0);
+#undef RDR_K
     return cudaGetLastError();
 }
 
 cudaError_t launch_trace_path(const FrameParams &P, bool use_cull, uint32_t x, uint32_t y, uint32_t sample,
                               RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float *rgba, cudaStream_t stream)
 {
-    const size_t smem = brute_smem_bytes(P.lay, 32);
+    const size_t smem = scene_smem_bytes(P.lay, P.staged != 0u, 32);
     cudaError_t e;
-    if (use_cull) {
-        if ((e = set_smem(trace_path_kernel<true>, smem)) != cudaSuccess) return e;
-        trace_path_kernel<true><<<1, 32, smem, stream>>>(P, x, y, sample, steps, capacity, n_steps, rgba);
-    } else {
-        if ((e = set_smem(trace_path_kernel<false>, smem)) != cudaSuccess) return e;
-        trace_path_kernel<false><<<1, 32, smem, stream>>>(P, x, y, sample, steps, capacity, n_steps, rgba);
-    }
+#define RDR_K(M, ...) do { if ((e = set_smem(trace_path_kernel<M>, smem)) != cudaSuccess) return e; trace_path_kernel<M><<<1, 32, smem, stream>>>(P, x, y, sample, steps, capacity, n_steps, rgba); } while (0)
+    RDR_DISPATCH(mode_of(P, use_cull), RDR_K, 0);
+#undef RDR_K
     return cudaGetLastError();
 }
 

@@ -14,9 +14,9 @@ struct FrameParams;
 struct SceneLayout;
 struct f4;
 
-size_t brute_smem_bytes(const SceneLayout &L, uint32_t block);
+size_t scene_smem_bytes(const SceneLayout &L, bool staged, uint32_t block);
 cudaError_t launch_render(const FrameParams &P, bool use_cull, int resident_ctas, cudaStream_t stream);
-cudaError_t render_resident_ctas(const SceneLayout &L, bool use_cull, int *out);
+cudaError_t render_resident_ctas(const FrameParams &P, bool use_cull, int *out);
 cudaError_t launch_resolve(const f4 *accum, uchar4 *out, uint32_t n_pixels, float divisor, cudaStream_t stream);
 cudaError_t launch_first_hit(const FrameParams &P, bool use_cull, int32_t *ids, float *ts, cudaStream_t stream);
 cudaError_t launch_kat_trace(const FrameParams &P, bool use_cull, uint32_t n, const float *rays, int32_t *ids, float *ts, cudaStream_t stream);

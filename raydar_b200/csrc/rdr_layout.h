@@ -24,7 +24,14 @@
 
 namespace rdr {
 
+// BVH mode (mode == 1) packs instead:
+//   nodes        f4[16*n_nodes]   8 entries x 2 quads per node (rdr_bvh.h)
+//   obj_geom     f4[n]
+//   material     f4[3*n]
+// and is either staged the same way (small scenes) or read in place from global memory / L2 (large scenes).
 struct SceneLayout {
+    uint32_t mode;                       // 0 = brute-force scan lists, 1 = BVH
+    uint32_t n_nodes, off_nodes;
     uint32_t n_objects, n_spheres, n_cubes;
     uint32_t ns_pad, nc_pad;
     uint32_t off_sphere_cull, off_cube_cull, off_sphere_geom, off_cube_geom;
@@ -38,6 +45,7 @@ struct FrameParams {
     CullConsts cull;
     SceneLayout lay;
     const unsigned char *blob;           // device copy of the packed scene
+    uint32_t staged;                     // 1: every CTA stages the blob into shared memory; 0: read in place (L2)
     f4 *accum;                           // W*H float RGBA accumulator (row-major, top row first)
     uint32_t *pixel_counter;             // next unclaimed pixel of this launch (zeroed before the launch)
     uint32_t seed_lo, seed_hi;

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "raydar_cuda.h"
+#include "rdr_bvh.h"
 #include "rdr_layout.h"
 
 namespace rdr {
@@ -16,7 +17,8 @@ namespace rdr {
 inline uint32_t round_up_u32(uint32_t v, uint32_t m) { return (v + m - 1u) / m * m; }
 
 // returns RDR_OK or an RdrStatus with `err` set
-inline int pack_scene_blob(const RdrSceneFlat *sc, std::vector<unsigned char> &blob, FrameParams &P, std::string &err)
+// use_bvh: pack the 8-wide hierarchy instead of the scan lists
+inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<unsigned char> &blob, FrameParams &P, std::string &err)
 {
     if (!sc) { err = "scene is NULL"; return RDR_ERR_INVALID; }
     if (sc->n_objects && (!sc->kind || !sc->geom || !sc->material)) { err = "scene arrays are NULL"; return RDR_ERR_INVALID; }
@@ -36,59 +38,96 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, std::vector<unsigned char> &b
     }
 
     // scene bounds for the cull margins (rdr_core.cuh): |c|_inf + size over objects, camera position
-    float obj_bound = 0.0f, q_max = 0.0f;
+    float obj_bound = 0.0f, q_max = 0.0f, r_min = INFINITY;
     for (uint32_t i = 0; i < n; ++i) {
         const float *g = sc->geom + 4 * (size_t)i;
         const float cm = std::max(std::fabs(g[0]), std::max(std::fabs(g[1]), std::fabs(g[2])));
         obj_bound = std::max(obj_bound, cm + std::fabs(g[3]));
-        if (sc->kind[i] == RDR_SPHERE)
+        if (sc->kind[i] == RDR_SPHERE) {
             q_max = std::max(q_max, 2.0f * (g[0] * g[0] + g[1] * g[1] + g[2] * g[2]) + g[3] * g[3]);
+            r_min = std::min(r_min, std::fabs(g[3]));
+        }
     }
+    if (!(r_min < INFINITY)) r_min = 0.0f;
     const float cam_bound = std::max(std::fabs(sc->cam_pos[0]), std::max(std::fabs(sc->cam_pos[1]), std::fabs(sc->cam_pos[2])));
     const float origin_bound = 1.001f * std::max(obj_bound, cam_bound) + 1e-3f;
     const float cube_pad = 3.814697265625e-06f * (origin_bound + obj_bound);   // 2^-18 * B
 
     SceneLayout L{};
     L.n_objects = n; L.n_spheres = (uint32_t)spheres.size(); L.n_cubes = (uint32_t)cubes.size();
-    L.ns_pad = round_up_u32(L.n_spheres, 32u); L.nc_pad = round_up_u32(L.n_cubes, 32u);
-    uint32_t off = 0;
-    L.off_sphere_cull = off; off += 16u * L.ns_pad;
-    L.off_cube_cull = off;   off += 16u * L.nc_pad;
-    L.off_sphere_geom = off; off += 16u * L.ns_pad;
-    L.off_cube_geom = off;   off += 16u * L.nc_pad;
-    L.off_obj_geom = off;    off += 16u * n;
-    L.off_material = off;    off += 48u * n;
-    L.off_sphere_idx = off;  off += 4u * L.ns_pad;
-    L.off_cube_idx = off;    off += 4u * L.nc_pad;
-    L.blob_bytes = std::max(16u, round_up_u32(off, 16u));
+    auto quad_at = [&](uint32_t base, uint32_t i) { return reinterpret_cast<float *>(blob.data() + base) + 4 * (size_t)i; };
+    auto fill_objects = [&]() {
+        for (uint32_t i = 0; i < n; ++i) {
+            const float *g = sc->geom + 4 * (size_t)i;
+            const float *m = sc->material + RDR_MAT_STRIDE * (size_t)i;
+            float *og = quad_at(L.off_obj_geom, i);
+            og[0] = g[0]; og[1] = g[1]; og[2] = g[2]; og[3] = g[3];
+            float *mm = reinterpret_cast<float *>(blob.data() + L.off_material) + 12 * (size_t)i;
+            mm[0] = m[0]; mm[1] = m[1]; mm[2] = m[2]; mm[3] = m[3];          // albedo, roughness
+            mm[4] = m[5]; mm[5] = m[6]; mm[6] = m[7]; mm[7] = m[8];          // emission colour, strength
+            mm[8] = m[4]; mm[9] = m[9]; mm[10] = m[10];                      // metallic, transmission, ior
+            const uint32_t kind_bits = sc->kind[i];
+            memcpy(&mm[11], &kind_bits, 4);
+        }
+    };
 
-    blob.assign(L.blob_bytes, 0);
-    auto quad = [&](uint32_t base, uint32_t i) { return reinterpret_cast<float *>(blob.data() + base) + 4 * (size_t)i; };
-    for (uint32_t j = 0; j < L.n_spheres; ++j) {
-        const float *g = sc->geom + 4 * (size_t)spheres[j];
-        float *c = quad(L.off_sphere_cull, j), *e = quad(L.off_sphere_geom, j);
-        c[0] = g[0]; c[1] = g[1]; c[2] = g[2]; c[3] = g[3] * g[3];
-        e[0] = g[0]; e[1] = g[1]; e[2] = g[2]; e[3] = g[3];
-        reinterpret_cast<uint32_t *>(blob.data() + L.off_sphere_idx)[j] = spheres[j];
+    bool bvh_done = false;
+    if (use_bvh) {
+        if (n > BVH_INDEX_MASK) { err = "too many objects"; return RDR_ERR_INVALID; }
+        std::vector<BvhBuildPrim> prims(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            const float *g = sc->geom + 4 * (size_t)i;
+            BvhBuildPrim &p = prims[i];
+            p.c[0] = g[0]; p.c[1] = g[1]; p.c[2] = g[2]; p.index = i; p.cube = sc->kind[i] == RDR_CUBE;
+            p.e = p.cube ? std::fabs(g[3]) * 0.5f + cube_pad : std::fabs(g[3]) + 2.0f * cube_pad;
+        }
+        BvhBuilder builder;
+        if (builder.build(std::move(prims))) {
+            L.mode = 1u;
+            L.n_nodes = builder.n_nodes();
+            uint64_t off = 0;
+            L.off_nodes = (uint32_t)off; off += 256ull * L.n_nodes;
+            L.off_obj_geom = (uint32_t)off; off += 16ull * n;
+            L.off_material = (uint32_t)off; off += 48ull * n;
+            if (off > 0xfffffff0ull) { err = "scene too large"; return RDR_ERR_INVALID; }
+            L.blob_bytes = std::max(16u, round_up_u32((uint32_t)off, 16u));
+            blob.assign(L.blob_bytes, 0);
+            memcpy(blob.data() + L.off_nodes, builder.nodes.data(), 256ull * L.n_nodes);
+            fill_objects();
+            bvh_done = true;
+        }
+        // a tree deeper than the traversal stack allows (pathological input) falls back to the scan lists
     }
-    for (uint32_t j = 0; j < L.n_cubes; ++j) {
-        const float *g = sc->geom + 4 * (size_t)cubes[j];
-        float *c = quad(L.off_cube_cull, j), *e = quad(L.off_cube_geom, j);
-        c[0] = g[0]; c[1] = g[1]; c[2] = g[2]; c[3] = std::fabs(g[3]) * 0.5f + cube_pad;
-        e[0] = g[0]; e[1] = g[1]; e[2] = g[2]; e[3] = g[3];
-        reinterpret_cast<uint32_t *>(blob.data() + L.off_cube_idx)[j] = cubes[j];
-    }
-    for (uint32_t i = 0; i < n; ++i) {
-        const float *g = sc->geom + 4 * (size_t)i;
-        const float *m = sc->material + RDR_MAT_STRIDE * (size_t)i;
-        float *og = quad(L.off_obj_geom, i);
-        og[0] = g[0]; og[1] = g[1]; og[2] = g[2]; og[3] = g[3];
-        float *mm = reinterpret_cast<float *>(blob.data() + L.off_material) + 12 * (size_t)i;
-        mm[0] = m[0]; mm[1] = m[1]; mm[2] = m[2]; mm[3] = m[3];          // albedo, roughness
-        mm[4] = m[5]; mm[5] = m[6]; mm[6] = m[7]; mm[7] = m[8];          // emission colour, strength
-        mm[8] = m[4]; mm[9] = m[9]; mm[10] = m[10];                      // metallic, transmission, ior
-        const uint32_t kind_bits = sc->kind[i];
-        memcpy(&mm[11], &kind_bits, 4);
+    if (!bvh_done) {
+        L.mode = 0u;
+        L.ns_pad = round_up_u32(L.n_spheres, 32u); L.nc_pad = round_up_u32(L.n_cubes, 32u);
+        uint32_t off = 0;
+        L.off_sphere_cull = off; off += 16u * L.ns_pad;
+        L.off_cube_cull = off;   off += 16u * L.nc_pad;
+        L.off_sphere_geom = off; off += 16u * L.ns_pad;
+        L.off_cube_geom = off;   off += 16u * L.nc_pad;
+        L.off_obj_geom = off;    off += 16u * n;
+        L.off_material = off;    off += 48u * n;
+        L.off_sphere_idx = off;  off += 4u * L.ns_pad;
+        L.off_cube_idx = off;    off += 4u * L.nc_pad;
+        L.blob_bytes = std::max(16u, round_up_u32(off, 16u));
+
+        blob.assign(L.blob_bytes, 0);
+        for (uint32_t j = 0; j < L.n_spheres; ++j) {
+            const float *g = sc->geom + 4 * (size_t)spheres[j];
+            float *c = quad_at(L.off_sphere_cull, j), *e = quad_at(L.off_sphere_geom, j);
+            c[0] = g[0]; c[1] = g[1]; c[2] = g[2]; c[3] = g[3] * g[3];
+            e[0] = g[0]; e[1] = g[1]; e[2] = g[2]; e[3] = g[3];
+            reinterpret_cast<uint32_t *>(blob.data() + L.off_sphere_idx)[j] = spheres[j];
+        }
+        for (uint32_t j = 0; j < L.n_cubes; ++j) {
+            const float *g = sc->geom + 4 * (size_t)cubes[j];
+            float *c = quad_at(L.off_cube_cull, j), *e = quad_at(L.off_cube_geom, j);
+            c[0] = g[0]; c[1] = g[1]; c[2] = g[2]; c[3] = std::fabs(g[3]) * 0.5f + cube_pad;
+            e[0] = g[0]; e[1] = g[1]; e[2] = g[2]; e[3] = g[3];
+            reinterpret_cast<uint32_t *>(blob.data() + L.off_cube_idx)[j] = cubes[j];
+        }
+        fill_objects();
     }
 
     memcpy(P.cam.inv_proj, sc->inv_proj, sizeof P.cam.inv_proj);
@@ -100,6 +139,7 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, std::vector<unsigned char> &b
     memcpy(P.world.b, sc->world_b, sizeof P.world.b);
     P.cull.sphere_q_max = q_max;
     P.cull.origin_bound = origin_bound;
+    P.cull.sphere_r_min = r_min;
     P.lay = L;
     return RDR_OK;
 }

@@ -13,6 +13,8 @@ struct SceneView {
     const f4 *sphere_cull, *cube_cull, *sphere_geom, *cube_geom, *obj_geom, *material;
     const uint32_t *sphere_idx, *cube_idx;
     uint32_t n_spheres, n_cubes, ns_chunks, nc_chunks;
+    const f4 *nodes;        // BVH mode: 16 quads per node
+    uint32_t n_objects;
 };
 
 RDR_HD SceneView scene_view(const unsigned char *base, const SceneLayout &L)
@@ -28,6 +30,8 @@ RDR_HD SceneView scene_view(const unsigned char *base, const SceneLayout &L)
     s.cube_idx = reinterpret_cast<const uint32_t *>(base + L.off_cube_idx);
     s.n_spheres = L.n_spheres; s.n_cubes = L.n_cubes;
     s.ns_chunks = L.ns_pad >> 5; s.nc_chunks = L.nc_pad >> 5;
+    s.nodes = reinterpret_cast<const f4 *>(base + L.off_nodes);
+    s.n_objects = L.n_objects;
     return s;
 }
 
@@ -43,7 +47,7 @@ RDR_HD Material load_material(const SceneView &S, int idx, bool *is_sphere)
 }
 
 // optional instrumentation (host-simulation only; compiled out on the device)
-struct TraceStats { uint64_t traces, sphere_exact, cube_exact, degenerate; };
+struct TraceStats { uint64_t traces, sphere_exact, cube_exact, degenerate, nodes_visited, entries_hit; };
 #if defined(__CUDA_ARCH__)
 #define RDR_STAT(stats, field)
 #else
@@ -145,6 +149,95 @@ RDR_HD Hit trace_brute(const SceneView &S, const CullConsts &cc, uint32_t *masks
         }
     }
     return best;
+}
+
+// ---- BVH nearest hit (same winner as the scan; see rdr_bvh.h for the conservative boxes) ----------------
+// Repeats two lock-step-friendly phases until the lane's stack and candidate queue are empty:
+//   T  pop nodes, test their 8 entries with the FMA slab test (pruned by the best exact t so far); child
+//      nodes go to the stack (with their entry distance, so that stale ones are skipped after `best`
+//      improves), primitives go to the lane's candidate queue;
+//   E  exact, reference-ordered tests on the queued primitives -- spheres first, then cubes, so that lanes of
+//      a warp run the same code -- updating the (t, original index) winner.
+// queue: QCAP words per lane (queue[i * stride]); stack: 64 (node, tn) pairs in local memory.
+constexpr int BVH_QCAP = 16;
+constexpr int BVH_STACK = 64;
+
+RDR_HD void bvh_exact_prim(const SceneView &S, uint32_t payload, v3 o, v3 d, Hit &best, TraceStats *stats)
+{
+    const int idx = (int)(payload & 0x3fffffffu);
+    const f4 g = S.obj_geom[idx];
+    float t;
+    bool hit;
+    if (payload & 0x40000000u) { RDR_STAT(stats, cube_exact); hit = hit_cube_exact(o, d, mk3(g.x, g.y, g.z), g.w, &t); }
+    else { RDR_STAT(stats, sphere_exact); hit = hit_sphere_exact(o, d, mk3(g.x, g.y, g.z), g.w, &t); }
+    if (hit && hit_better(t, idx, best.t, best.idx)) { best.idx = idx; best.t = t; }
+}
+
+RDR_HD Hit trace_bvh(const SceneView &S, const CullConsts &cc, uint32_t *queue, uint32_t stride, v3 o, v3 d,
+                     TraceStats *stats = nullptr)
+{
+    Hit best; best.idx = -1; best.t = finf();
+    RDR_STAT(stats, traces);
+    if (S.n_objects == 0u) return best;
+    const RayBvh rb = make_ray_bvh(o, d, cc);
+    if (rb.rc.degenerate) {                       // origin outside the scene bound / non-finite ray: exact test on everything
+        RDR_STAT(stats, degenerate);
+        for (uint32_t i = 0; i < S.n_objects; ++i) {
+            const uint32_t kind_bits = f2u(S.material[3 * i + 2].w);
+            bvh_exact_prim(S, i | (kind_bits ? 0x40000000u : 0u), o, d, best, stats);
+        }
+        return best;
+    }
+    uint32_t stk_node[BVH_STACK];
+    float stk_tn[BVH_STACK];
+    int sp = 1;
+    stk_node[0] = 0u; stk_tn[0] = 0.0f;
+    uint32_t nq = 0u;
+    float prune = finf();
+    for (;;) {
+        // ---- phase T ----
+        while (sp > 0 && nq <= (uint32_t)(BVH_QCAP - 8)) {
+            --sp;
+            const uint32_t node = stk_node[sp];
+            if (stk_tn[sp] > prune) continue;
+            RDR_STAT(stats, nodes_visited);
+            const f4 *e = S.nodes + (size_t)node * 16u;
+            RDR_UNROLL
+            for (int k = 0; k < 8; ++k) {
+                const f4 q0 = e[2 * k], q1 = e[2 * k + 1];
+                float tn;
+                if (bvh_entry_may_hit(rb, q0, q1, prune, &tn)) {
+                    RDR_STAT(stats, entries_hit);
+                    const uint32_t payload = f2u(q1.z);
+                    if (payload & 0x80000000u) { queue[nq * stride] = payload; ++nq; }
+                    else { stk_node[sp] = payload; stk_tn[sp] = tn; ++sp; }
+                }
+            }
+        }
+        // ---- phase E ----
+        for (uint32_t q = 0; q < nq; ++q) {
+            const uint32_t payload = queue[q * stride];
+            if (!(payload & 0x40000000u)) bvh_exact_prim(S, payload, o, d, best, stats);
+        }
+        for (uint32_t q = 0; q < nq; ++q) {
+            const uint32_t payload = queue[q * stride];
+            if (payload & 0x40000000u) bvh_exact_prim(S, payload, o, d, best, stats);
+        }
+        nq = 0u;
+        if (best.idx >= 0 && !isnan_(best.t)) prune = best.t;
+        if (sp == 0) break;
+    }
+    return best;
+}
+
+// nearest-hit dispatch of the kernels: MODE 0 = scan with cull, 1 = scan exact-everything, 2 = BVH
+template <int MODE>
+RDR_HD Hit trace_any(const SceneView &S, const CullConsts &cc, uint32_t *scratch, uint32_t stride, v3 o, v3 d,
+                     TraceStats *stats = nullptr)
+{
+    if (MODE == 2) return trace_bvh(S, cc, scratch, stride, o, d, stats);
+    if (MODE == 1) return trace_brute<false>(S, cc, scratch, stride, o, d, stats);
+    return trace_brute<true>(S, cc, scratch, stride, o, d, stats);
 }
 
 // 0, but opaque to the compiler's uniformity analysis (see LaneState)
@@ -256,7 +349,7 @@ RDR_HD void lane_shade(const FrameParams &P, const SceneView &S, LaneState &st)
 }
 
 // scalar driver of the phases for one pixel (host simulation; the kernel drives them in warp lock-step)
-template <bool USE_CULL>
+template <int MODE>
 RDR_HD f4 render_pixel(const FrameParams &P, const SceneView &S, uint32_t *masks, uint32_t stride, uint32_t pixel, f4 acc,
                        TraceStats *stats = nullptr)
 {
@@ -264,14 +357,14 @@ RDR_HD f4 render_pixel(const FrameParams &P, const SceneView &S, uint32_t *masks
     lane_init(st, masks);
     lane_start_pixel(P, pixel, acc, st);
     while (st.alive) {
-        lane_accept_hit(st, trace_brute<USE_CULL>(S, P.cull, masks, stride, st.ro, st.rd, stats));
+        lane_accept_hit(st, trace_any<MODE>(S, P.cull, masks, stride, st.ro, st.rd, stats));
         lane_shade(P, S, st);
     }
     return st.acc;
 }
 
 // one path with every bounce recorded (debug / parity); returns the number of steps taken
-template <bool USE_CULL>
+template <int MODE>
 RDR_HD uint32_t trace_path_lane(const FrameParams &P, const SceneView &S, uint32_t *masks, uint32_t stride,
                                 uint32_t x, uint32_t y, uint32_t sample, RdrPathStep *steps, uint32_t capacity, float rgba[4])
 {
@@ -281,7 +374,7 @@ RDR_HD uint32_t trace_path_lane(const FrameParams &P, const SceneView &S, uint32
     v3 light = mk3(0.0f, 0.0f, 0.0f), atten = mk3(1.0f, 1.0f, 1.0f);
     uint32_t written = 0u;
     for (uint32_t bounce = 0; bounce < P.max_bounces; ++bounce) {
-        const Hit hit = trace_brute<USE_CULL>(S, P.cull, masks, stride, ro, rd);
+        const Hit hit = trace_any<MODE>(S, P.cull, masks, stride, ro, rd);
         RdrPathStep st;
         memset(&st, 0, sizeof st);
         if (hit.idx >= 0) {

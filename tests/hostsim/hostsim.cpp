@@ -25,11 +25,11 @@ struct Packed {
     SceneView S{};
     std::vector<uint32_t> masks;
     int status = RDR_OK;
-    explicit Packed(const RdrSceneFlat *sc)
+    explicit Packed(const RdrSceneFlat *sc, bool use_bvh = false)
     {
         std::vector<unsigned char> tmp;
         std::string err;
-        status = pack_scene_blob(sc, tmp, P, err);
+        status = pack_scene_blob(sc, use_bvh, tmp, P, err);
         if (status != RDR_OK) return;
         storage.resize(tmp.size() + 16);
         blob = storage.data();
@@ -37,14 +37,21 @@ struct Packed {
         memcpy(blob, tmp.data(), tmp.size());
         P.blob = blob;
         S = scene_view(blob, P.lay);
-        masks.resize(std::max(P.lay.ns_pad, P.lay.nc_pad) / 32 + 1);
+        masks.resize(std::max<uint32_t>(std::max(P.lay.ns_pad, P.lay.nc_pad) / 32 + 1, BVH_QCAP));
     }
 };
+
+Hit trace_mode(int use_cull, const Packed &pk, uint32_t *scratch, v3 o, v3 d, TraceStats *st)
+{
+    if (pk.P.lay.mode == 1u) return trace_any<2>(pk.S, pk.P.cull, scratch, 1, o, d, st);
+    return use_cull ? trace_any<0>(pk.S, pk.P.cull, scratch, 1, o, d, st) : trace_any<1>(pk.S, pk.P.cull, scratch, 1, o, d, st);
+}
 
 void merge(TraceStats *dst, const TraceStats &src)
 {
     if (!dst) return;
     dst->traces += src.traces; dst->sphere_exact += src.sphere_exact; dst->cube_exact += src.cube_exact; dst->degenerate += src.degenerate;
+    dst->nodes_visited += src.nodes_visited; dst->entries_hit += src.entries_hit;
 }
 
 }  // namespace
@@ -53,7 +60,7 @@ extern "C" {
 
 int hs_first_hit(const RdrSceneFlat *sc, int use_cull, int32_t *ids, float *ts, TraceStats *stats)
 {
-    Packed pk(sc);
+    Packed pk(sc, use_cull == 2);
     if (pk.status != RDR_OK) return pk.status;
     const int64_t n = (int64_t)sc->width * sc->height;
     TraceStats total{};
@@ -65,8 +72,7 @@ int hs_first_hit(const RdrSceneFlat *sc, int use_cull, int32_t *ids, float *ts, 
         for (int64_t p = 0; p < n; ++p) {
             const v3 o = mk3(pk.P.cam.pos[0], pk.P.cam.pos[1], pk.P.cam.pos[2]);
             const v3 d = camera_ray_dir(pk.P.cam, (uint32_t)(p % sc->width), (uint32_t)(p / sc->width));
-            const Hit h = use_cull ? trace_brute<true>(pk.S, pk.P.cull, masks.data(), 1, o, d, &local)
-                                   : trace_brute<false>(pk.S, pk.P.cull, masks.data(), 1, o, d, &local);
+            const Hit h = trace_mode(use_cull, pk, masks.data(), o, d, &local);
             ids[p] = h.idx;
             ts[p] = h.idx >= 0 ? h.t : 0.0f;
         }
@@ -79,7 +85,7 @@ int hs_first_hit(const RdrSceneFlat *sc, int use_cull, int32_t *ids, float *ts, 
 
 int hs_trace(const RdrSceneFlat *sc, int use_cull, uint32_t n, const float *rays, int32_t *ids, float *ts, TraceStats *stats)
 {
-    Packed pk(sc);
+    Packed pk(sc, use_cull == 2);
     if (pk.status != RDR_OK) return pk.status;
     TraceStats total{};
 #pragma omp parallel
@@ -90,8 +96,7 @@ int hs_trace(const RdrSceneFlat *sc, int use_cull, uint32_t n, const float *rays
         for (int64_t i = 0; i < (int64_t)n; ++i) {
             const v3 o = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
             const v3 d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
-            const Hit h = use_cull ? trace_brute<true>(pk.S, pk.P.cull, masks.data(), 1, o, d, &local)
-                                   : trace_brute<false>(pk.S, pk.P.cull, masks.data(), 1, o, d, &local);
+            const Hit h = trace_mode(use_cull, pk, masks.data(), o, d, &local);
             ids[i] = h.idx;
             ts[i] = h.idx >= 0 ? h.t : 0.0f;
         }
@@ -105,7 +110,7 @@ int hs_trace(const RdrSceneFlat *sc, int use_cull, uint32_t n, const float *rays
 int hs_render(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t sample_begin, uint32_t n_samples,
               uint32_t max_bounces, float *accum, TraceStats *stats)
 {
-    Packed pk(sc);
+    Packed pk(sc, use_cull == 2);
     if (pk.status != RDR_OK) return pk.status;
     pk.P.seed_lo = (uint32_t)seed; pk.P.seed_hi = (uint32_t)(seed >> 32);
     pk.P.max_bounces = max_bounces; pk.P.sample_begin = sample_begin; pk.P.sample_count = n_samples;
@@ -118,8 +123,9 @@ int hs_render(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t samp
 #pragma omp for schedule(dynamic, 256)
         for (int64_t p = 0; p < n; ++p) {
             f4 acc; acc.x = accum[4 * p]; acc.y = accum[4 * p + 1]; acc.z = accum[4 * p + 2]; acc.w = accum[4 * p + 3];
-            acc = use_cull ? render_pixel<true>(pk.P, pk.S, masks.data(), 1, (uint32_t)p, acc, &local)
-                           : render_pixel<false>(pk.P, pk.S, masks.data(), 1, (uint32_t)p, acc, &local);
+            acc = pk.P.lay.mode == 1u ? render_pixel<2>(pk.P, pk.S, masks.data(), 1, (uint32_t)p, acc, &local)
+                  : use_cull       ? render_pixel<0>(pk.P, pk.S, masks.data(), 1, (uint32_t)p, acc, &local)
+                                   : render_pixel<1>(pk.P, pk.S, masks.data(), 1, (uint32_t)p, acc, &local);
             accum[4 * p] = acc.x; accum[4 * p + 1] = acc.y; accum[4 * p + 2] = acc.z; accum[4 * p + 3] = acc.w;
         }
 #pragma omp critical
@@ -132,12 +138,13 @@ int hs_render(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t samp
 int hs_trace_path(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t x, uint32_t y, uint32_t sample,
                   uint32_t max_bounces, RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float rgba[4])
 {
-    Packed pk(sc);
+    Packed pk(sc, use_cull == 2);
     if (pk.status != RDR_OK) return pk.status;
     pk.P.seed_lo = (uint32_t)seed; pk.P.seed_hi = (uint32_t)(seed >> 32);
     pk.P.max_bounces = max_bounces;
-    *n_steps = use_cull ? trace_path_lane<true>(pk.P, pk.S, pk.masks.data(), 1, x, y, sample, steps, capacity, rgba)
-                        : trace_path_lane<false>(pk.P, pk.S, pk.masks.data(), 1, x, y, sample, steps, capacity, rgba);
+    *n_steps = pk.P.lay.mode == 1u ? trace_path_lane<2>(pk.P, pk.S, pk.masks.data(), 1, x, y, sample, steps, capacity, rgba)
+               : use_cull         ? trace_path_lane<0>(pk.P, pk.S, pk.masks.data(), 1, x, y, sample, steps, capacity, rgba)
+                                  : trace_path_lane<1>(pk.P, pk.S, pk.masks.data(), 1, x, y, sample, steps, capacity, rgba);
     return RDR_OK;
 }
 
@@ -149,7 +156,7 @@ void hs_resolve(const float *accum, uint64_t n_pixels, uint32_t divisor, uint8_t
 // raw conservative tests, for the adversarial margin checks: may[i] = 1 if the cull keeps primitive i for ray i
 void hs_sphere_cull_batch(uint32_t n, const float *rays, const float *spheres, float q_max, float origin_bound, int32_t *may, int32_t *degenerate)
 {
-    CullConsts cc{q_max, origin_bound};
+    CullConsts cc{q_max, origin_bound, 0.0f};
     for (uint32_t i = 0; i < n; ++i) {
         const v3 o = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
         const RayCull rc = make_ray_cull(o, d, cc);
@@ -163,7 +170,7 @@ void hs_sphere_cull_batch(uint32_t n, const float *rays, const float *spheres, f
 void hs_cube_cull_batch(uint32_t n, const float *rays, const float *cubes, float pad, float origin_bound, const float *best,
                         int32_t *may, int32_t *degenerate)
 {
-    CullConsts cc{0.0f, origin_bound};
+    CullConsts cc{0.0f, origin_bound, 0.0f};
     for (uint32_t i = 0; i < n; ++i) {
         const v3 o = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
         const RayCull rc = make_ray_cull(o, d, cc);
@@ -198,10 +205,19 @@ int hs_scene_consts(const RdrSceneFlat *sc, float *q_max, float *origin_bound, f
     if (pk.status != RDR_OK) return pk.status;
     *q_max = pk.P.cull.sphere_q_max; *origin_bound = pk.P.cull.origin_bound;
     *cube_pad = 0.0f;
-    if (pk.P.lay.n_cubes) {
+    if (pk.P.lay.n_cubes && pk.P.lay.mode == 0u) {
         const f4 c = pk.S.cube_cull[0], g = pk.S.cube_geom[0];
         *cube_pad = c.w - (g.w < 0 ? -g.w : g.w) * 0.5f;
     }
+    return RDR_OK;
+}
+
+// hierarchy shape of a scene (BVH mode): nodes, depth is checked by the builder
+int hs_bvh_info(const RdrSceneFlat *sc, uint32_t *n_nodes, uint32_t *mode, uint32_t *blob_bytes)
+{
+    Packed pk(sc, true);
+    if (pk.status != RDR_OK) return pk.status;
+    *n_nodes = pk.P.lay.n_nodes; *mode = pk.P.lay.mode; *blob_bytes = pk.P.lay.blob_bytes;
     return RDR_OK;
 }
 

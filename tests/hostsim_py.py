@@ -18,7 +18,8 @@ _LIB = os.path.join(_HERE, "hostsim", "libhostsim.so")
 
 
 class TraceStats(C.Structure):
-    _fields_ = [("traces", C.c_uint64), ("sphere_exact", C.c_uint64), ("cube_exact", C.c_uint64), ("degenerate", C.c_uint64)]
+    _fields_ = [("traces", C.c_uint64), ("sphere_exact", C.c_uint64), ("cube_exact", C.c_uint64), ("degenerate", C.c_uint64),
+                ("nodes_visited", C.c_uint64), ("entries_hit", C.c_uint64)]
 
 
 def build():
@@ -53,6 +54,7 @@ def lib():
         L.hs_exact_batch.argtypes = [C.c_int, C.c_uint32, fp, fp, fp, i32p]
         L.hs_rng_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
         L.hs_scene_consts.argtypes = [sfp, fp, fp, fp]
+        L.hs_bvh_info.argtypes = [sfp, u32p, u32p, u32p]
         _lib = L
     return _lib
 
@@ -131,6 +133,16 @@ def rng_block(seed, pixel, sample, bounce, block):
     out = (C.c_uint32 * 4)()
     lib().hs_rng_block(seed, pixel, sample, bounce, block, out)
     return list(out)
+
+
+BVH = 2      # pass as use_cull to select the hierarchy (1/True = scan + cull, 0/False = scan, exact test on everything)
+
+
+def bvh_info(scene):
+    f = rb._as_flat(scene)
+    n = C.c_uint32(); mode = C.c_uint32(); nbytes = C.c_uint32()
+    _ok(lib().hs_bvh_info(C.byref(f), C.byref(n), C.byref(mode), C.byref(nbytes)))
+    return n.value, mode.value, nbytes.value
 
 
 def scene_consts(scene):

@@ -97,3 +97,65 @@ def first_hit(scene):
         best = np.where(better, i, best)
         best_t = np.where(better, t, best_t)
     return best.reshape(scene.height, scene.width), np.where(best >= 0, best_t, 0).astype(f32).reshape(scene.height, scene.width)
+
+
+# ---- Camera::update_matrices (scene/camera.rs:210-231) restated from cgmath 0.18 in numpy f32 ------------------
+# (look_at_lh, perspective, cofactor invert).  Reproduces the matrices stored in the .rscn fixtures bit for bit
+# (tests/test_scene_io.py checks the C++ twin against the same fixtures).
+def _dot3(a, b):
+    return f32(f32(f32(a[0] * b[0]) + f32(a[1] * b[1])) + f32(a[2] * b[2]))
+
+
+def _norm3(a):
+    inv = f32(f32(1) / np.sqrt(_dot3(a, a)))
+    return np.array([f32(x * inv) for x in a], f32)
+
+
+def _cross(a, b):
+    return np.array([f32(f32(a[1] * b[2]) - f32(a[2] * b[1])), f32(f32(a[2] * b[0]) - f32(a[0] * b[2])),
+                     f32(f32(a[0] * b[1]) - f32(a[1] * b[0]))], f32)
+
+
+def look_at_lh(eye, center, up):
+    eye = np.asarray(eye, f32); center = np.asarray(center, f32); up = np.asarray(up, f32)
+    d = -np.array([f32(center[i] - eye[i]) for i in range(3)], f32)
+    fw = _norm3(d); s = _norm3(_cross(fw, up)); u = _cross(s, fw)
+    m = np.zeros(16, f32)
+    m[0:4] = [s[0], u[0], -fw[0], 0]; m[4:8] = [s[1], u[1], -fw[1], 0]; m[8:12] = [s[2], u[2], -fw[2], 0]
+    m[12:16] = [-_dot3(eye, s), -_dot3(eye, u), _dot3(eye, fw), 1]
+    return m
+
+
+def perspective(fov_deg, aspect, near, far):
+    import math
+    rad = f32(f32(fov_deg) * f32(math.pi / 180.0))
+    fv = f32(f32(1) / f32(math.tan(float(f32(rad / f32(2))))))
+    near = f32(near); far = f32(far); aspect = f32(aspect)
+    m = np.zeros(16, f32)
+    m[0] = f32(fv / aspect); m[5] = fv; m[10] = f32(f32(far + near) / f32(near - far)); m[11] = -1
+    m[14] = f32(f32(f32(f32(2) * far) * near) / f32(near - far))
+    return m
+
+
+def _det3(m):
+    return f32(f32(f32(m[0][0] * f32(f32(m[1][1] * m[2][2]) - f32(m[2][1] * m[1][2]))) -
+                   f32(m[1][0] * f32(f32(m[0][1] * m[2][2]) - f32(m[2][1] * m[0][2])))) +
+               f32(m[2][0] * f32(f32(m[0][1] * m[1][2]) - f32(m[1][1] * m[0][2]))))
+
+
+def invert4(flat):
+    M = [[f32(flat[c * 4 + r]) for r in range(4)] for c in range(4)]
+    d = []
+    for skip in range(4):
+        cols = [c for c in range(4) if c != skip]
+        d.append(_det3([[M[c][k + 1] for c in cols] for k in range(3)]))
+    det = f32(f32(f32(f32(M[0][0] * d[0]) - f32(M[1][0] * d[1])) + f32(M[2][0] * d[2])) - f32(M[3][0] * d[3]))
+    inv = f32(f32(1) / det)
+    t = [[M[r][c] for r in range(4)] for c in range(4)]
+    out = []
+    for i in range(4):
+        for j in range(4):
+            mat = [[c[k] for k in range(4) if k != j] for ci, c in enumerate(t) if ci != i]
+            sign = f32(-1) if (i + j) & 1 else f32(1)
+            out.append(f32(f32(_det3(mat) * sign) * inv))
+    return np.array(out, f32)

@@ -1,0 +1,93 @@
+"""The 8-wide hierarchy (raydar_b200/csrc/rdr_bvh.h, trace_bvh in rdr_trace.cuh) must return exactly the winner of
+the reference's linear scan (cpu.rs:344-352), including the first-minimum tie-break, on scenes far larger than the
+scan can hold.  CPU checks through tests/hostsim; the GPU twin is tests/test_gpu_parity.py::test_bvh_*."""
+import numpy as np
+import pytest
+
+import synth_scenes as ss
+
+
+def u32(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_hierarchy_shape(hs):
+    scene = ss.config4(5000, 64, 36)
+    n_nodes, mode, nbytes = hs.bvh_info(scene)
+    assert mode == 1
+    assert 5001 / 8 <= n_nodes <= 5001                      # 8-wide: between N/8 and N nodes
+    assert nbytes == 256 * n_nodes + 64 * 5001 + (-(256 * n_nodes + 64 * 5001)) % 16
+
+
+@pytest.mark.parametrize("n", [300, 20_000])
+def test_config4_first_hit_matches_linear_scan(hs, orc, n):
+    """BASELINE config 4 (random Spheres/Cubes over a 200 x 200 field + ground cube), reduced object count and
+    resolution so that the O(N) oracle finishes in seconds."""
+    scene = ss.config4(n, 256, 144)
+    ids_o, t_o = orc.first_hit(scene)
+    ids, ts, st = hs.first_hit(scene, hs.BVH)
+    assert np.array_equal(ids, ids_o)
+    assert np.array_equal(u32(ts), u32(t_o))
+    assert len(np.unique(ids_o)) > min(n, 2000) // 4
+    assert st.degenerate == 0
+    assert (st.sphere_exact + st.cube_exact) / st.traces < 0.01 * n + 12      # a tiny fraction of the N exact tests
+
+
+def test_config4_secondary_rays(hs, orc):
+    scene = ss.config4(3000, 96, 54)
+    want = orc.render(scene, 11, 0, 3, 12, n_threads=orc.max_threads())
+    got, st = hs.render(scene, 11, 0, 3, 12, use_cull=hs.BVH)
+    assert np.array_equal(u32(got), u32(want))
+
+
+def test_config5_glass_metal_lattice(hs, orc):
+    """BASELINE config 5: 8x8x8 glass/metal lattice in a closed box, 32 bounces."""
+    scene = ss.config5(160, 90)
+    assert scene.n_objects == 513
+    ids_o, t_o = orc.first_hit(scene)
+    for mode in (True, hs.BVH):
+        ids, ts, _ = hs.first_hit(scene, mode)
+        assert np.array_equal(ids, ids_o) and np.array_equal(u32(ts), u32(t_o))
+    small = scene.with_resolution(64, 36)
+    want, stats = orc.render(small, 5, 0, 2, 32, n_threads=orc.max_threads(), want_stats=True)
+    assert stats.trace_calls / stats.samples > 25            # closed box: paths rarely end before the bounce limit
+    for mode in (True, hs.BVH):
+        got, _ = hs.render(small, 5, 0, 2, 32, use_cull=mode)
+        assert np.array_equal(u32(got), u32(want))
+
+
+def test_coincident_and_nested_primitives(hs, orc, default_scene):
+    """Ties (equal t from different objects) and boxes that contain other boxes: the lowest original index wins."""
+    import copy
+    rng = np.random.default_rng(3)
+    kind, geom = [], []
+    for i in range(400):
+        c = rng.integers(-4, 5, 3).astype(np.float32)
+        k = int(rng.integers(0, 2))
+        kind.append(k); geom.append([c[0], c[1], c[2] + 10, [0.5, 1.0][k] * float(rng.choice([1.0, 1.0, 2.0, 8.0]))])
+    s = copy.copy(default_scene)
+    s.kind = np.asarray(kind, np.uint32); s.geom = np.asarray(geom, np.float32)
+    s.material = np.tile(default_scene.material[1], (400, 1))
+    n = 30_000
+    d = np.concatenate([rng.integers(-6, 7, (n, 2)) / np.float32(8.0), np.ones((n, 1))], 1).astype(np.float32)
+    rays = np.concatenate([np.zeros((n, 3), np.float32), d], 1)
+    a_ids, a_t, _ = hs.trace(s, rays, False)
+    b_ids, b_t, _ = hs.trace(s, rays, hs.BVH)
+    assert np.array_equal(a_ids, b_ids) and np.array_equal(u32(a_t), u32(b_t))
+    for i in range(0, n, 101):
+        idx, t = orc.trace(s, rays[i, :3], rays[i, 3:])
+        assert idx == b_ids[i]
+
+
+def test_rscn_round_trip(rb, orc, tmp_path):
+    """The synthetic scenes can be saved as .rscn and read back by both loaders with identical arrays."""
+    scene = ss.config5(320, 180)
+    path = str(tmp_path / "config5.rscn")
+    ss.write_rscn(scene, path)
+    py = orc.load_rscn(path)
+    assert np.array_equal(u32(py.geom), u32(scene.geom)) and np.array_equal(u32(py.inv_view), u32(scene.inv_view))
+    f = rb.Scene.load(path).flat()
+    assert f.n_objects == 513 and np.array_equal(u32(np.array(f.inv_proj[:])), u32(scene.inv_proj))
+    # and the C++ update_matrices agrees with the numpy restatement used by the generator
+    sc = rb.Scene.load(path).set_resolution(320, 180)
+    assert np.array_equal(u32(sc.matrices()[2]), u32(scene.inv_view)) and np.array_equal(u32(sc.matrices()[3]), u32(scene.inv_proj))

@@ -51,20 +51,22 @@ def test_intersection_kat(renderer, orc, sphere):
 
 
 @pytest.mark.parametrize("name,res", [("default", None), ("benchmark", (1920, 1080)), ("benchmark", None)])
-@pytest.mark.parametrize("cull", [True, False])
-def test_first_hit_ids_bit_exact(renderer, orc, default_scene, benchmark_scene, name, res, cull):
+@pytest.mark.parametrize("cull", [True, False, "bvh"])
+def test_first_hit_ids_bit_exact(rb, renderer, orc, default_scene, benchmark_scene, name, res, cull):
     scene = default_scene if name == "default" else benchmark_scene
     if res:
         scene = scene.with_resolution(*res)
-    if not cull and scene.width > 1920:
+    if cull is False and scene.width > 1920:
         pytest.skip("exact-everything reference run only up to 1080p")
     ids_o, t_o = orc.first_hit(scene)
-    renderer.debug_set_cull(cull)
+    renderer.debug_set_cull(cull is not False)
+    renderer.set_accel(rb.ACCEL_BVH if cull == "bvh" else rb.ACCEL_BRUTE)
     try:
         renderer.new_frame(scene)
         ids_g, t_g = renderer.first_hit()
     finally:
         renderer.debug_set_cull(True)
+        renderer.set_accel(rb.ACCEL_AUTO)
     assert np.array_equal(ids_o, ids_g)
     assert np.array_equal(u32(t_o), u32(t_g))
 
@@ -93,12 +95,14 @@ def test_trace_arbitrary_rays(renderer, orc, benchmark_scene):
             assert u32(np.float32(t)) == u32(t_g[i])
 
 
+@pytest.mark.parametrize("accel", ["brute", "bvh"])
 @pytest.mark.parametrize("name", ["default", "benchmark"])
-def test_single_path_debug_mode(rb, orc, default_scene, benchmark_scene, name):
+def test_single_path_debug_mode(rb, orc, default_scene, benchmark_scene, name, accel):
     scene = (default_scene if name == "default" else benchmark_scene.with_resolution(480, 270))
     seed = 0xC0FFEE
     r = rb.Renderer(rb.RendererConfig(max_sample_count=4, max_bounces=12))
     r.set_seed(seed)
+    r.set_accel(rb.ACCEL_BVH if accel == "bvh" else rb.ACCEL_BRUTE)
     r.new_frame(scene)
     rng = np.random.default_rng(5)
     fields = ["position", "normal", "origin", "direction", "attenuation", "light"]
@@ -120,13 +124,15 @@ def test_single_path_debug_mode(rb, orc, default_scene, benchmark_scene, name):
     r.close()
 
 
+@pytest.mark.parametrize("accel", ["brute", "bvh"])
 @pytest.mark.parametrize("name,res,spp", [("default", (427, 240), 16), ("benchmark", (320, 180), 8)])
-def test_accumulator_bit_exact(rb, orc, default_scene, benchmark_scene, name, res, spp):
+def test_accumulator_bit_exact(rb, orc, default_scene, benchmark_scene, name, res, spp, accel):
     scene = (default_scene if name == "default" else benchmark_scene).with_resolution(*res)
     seed = 99
     acc_o = orc.render(scene, seed, 0, spp, 12, n_threads=orc.max_threads())
     r = rb.Renderer(rb.RendererConfig(max_sample_count=spp, max_bounces=12))
     r.set_seed(seed)
+    r.set_accel(rb.ACCEL_BVH if accel == "bvh" else rb.ACCEL_BRUTE)
     img = r.render_frame(scene)
     acc_g = r.read_accum()
     assert np.array_equal(u32(acc_o), u32(acc_g))
@@ -178,6 +184,43 @@ def test_converged_psnr_independent_streams(rb, orc, default_scene):
     psnr = 10 * np.log10(1.0 / mse)
     assert psnr >= 40.0, psnr
     r.close()
+
+
+def test_bvh_config4_100k_objects(rb, orc):
+    """BASELINE config 4: 100k random Spheres/Cubes + ground cube (hierarchy in global memory / L2, not staged).
+    First-hit ids and t against the O(N) linear scan of the oracle at a resolution it finishes in seconds, then the
+    accumulator of a small multi-bounce render."""
+    import synth_scenes as ss
+    scene = ss.config4(100_000, 160, 90)
+    ids_o, t_o = orc.first_hit(scene)
+    r = rb.Renderer(rb.RendererConfig(2, 12)); r.set_seed(3)          # ACCEL_AUTO -> BVH (n > threshold)
+    r.new_frame(scene)
+    ids_g, t_g = r.first_hit()
+    assert np.array_equal(ids_o, ids_g)
+    assert np.array_equal(u32(t_o), u32(t_g))
+    assert len(np.unique(ids_o)) > 3000
+    small = scene.with_resolution(48, 27)
+    want = orc.render(small, 3, 0, 2, 12, n_threads=orc.max_threads())
+    r.render_frame(small)
+    assert np.array_equal(u32(want), u32(r.read_accum()))
+    # the brute-force scan cannot hold this scene in shared memory: explicit request is an error, not a fallback
+    r.set_accel(rb.ACCEL_BRUTE)
+    with pytest.raises(rb.RaydarError) as e:
+        r.new_frame(scene)
+    assert e.value.status == rb.ERR_UNSUPPORTED
+    r.close()
+
+
+def test_bvh_config5_glass_metal_32_bounces(rb, orc):
+    """BASELINE config 5: glass/metal lattice in a closed box, 32 bounces; scan and hierarchy against the oracle."""
+    import synth_scenes as ss
+    scene = ss.config5(192, 108)
+    want = orc.render(scene, 9, 0, 2, 32, n_threads=orc.max_threads())
+    for accel in (rb.ACCEL_BRUTE, rb.ACCEL_BVH):
+        r = rb.Renderer(rb.RendererConfig(2, 32)); r.set_seed(9); r.set_accel(accel)
+        r.render_frame(scene)
+        assert np.array_equal(u32(want), u32(r.read_accum())), accel
+        r.close()
 
 
 def test_edge_cases(rb, orc, default_scene):
