@@ -45,9 +45,13 @@ enum { RDR_LOBE_MISS = 0, RDR_LOBE_DIFFUSE = 1, RDR_LOBE_SPECULAR = 2, RDR_LOBE_
 enum { RDR_MAT_STRIDE = 11 };  /* albedo3, roughness, metallic, emission_color3, emission_strength,
                                   transmission, ior -- field order of scene/material.rs:4-13 */
 
-/* nearest-hit search strategy; AUTO = brute force over the shared-memory SoA buffer for small
- * scenes, BVH otherwise.  Both return the reference's trace_ray winner (cpu.rs:344-352). */
-enum { RDR_ACCEL_AUTO = 0, RDR_ACCEL_BRUTE = 1, RDR_ACCEL_BVH = 2 };
+/* nearest-hit search strategy.  All return the reference's trace_ray winner (cpu.rs:344-352):
+ *   BRUTE    flat scan over the shared-memory SoA primitive buffer (every primitive, every ray)
+ *   CLUSTER  two-level scan of the same buffer: a uniform scan over <= 128 cluster boxes, then the members
+ *            of the clusters a ray touches
+ *   BVH      8-wide hierarchy (shared memory when it fits, otherwise global memory / L2)
+ *   AUTO     CLUSTER up to 1024 objects, BVH above */
+enum { RDR_ACCEL_AUTO = 0, RDR_ACCEL_BRUTE = 1, RDR_ACCEL_BVH = 2, RDR_ACCEL_CLUSTER = 3 };
 
 typedef struct RdrRenderer RdrRenderer;    /* replaces CpuRenderer state, cpu.rs:111-116 */
 typedef struct RdrScene RdrScene;          /* host-side loaded scene, scene/mod.rs:13-18 */

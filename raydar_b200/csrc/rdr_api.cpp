@@ -91,10 +91,17 @@ int fail(RdrRenderer *r, int status, const char *fmt, ...)
 int pack_scene(RdrRenderer *r, const RdrSceneFlat *sc, std::vector<unsigned char> &blob, FrameParams &P)
 {
     std::string err;
-    // RDR_ACCEL_AUTO: the scan for tiny scenes (one or two list chunks), the hierarchy otherwise
+    // RDR_ACCEL_AUTO: the two-level scan while the cluster masks fit (<= 128 clusters), the hierarchy above
     const bool use_bvh = r->accel == RDR_ACCEL_BVH || (r->accel == RDR_ACCEL_AUTO && sc && sc->n_objects > RDR_AUTO_BVH_THRESHOLD);
     const int st = rdr::pack_scene_blob(sc, use_bvh, blob, P, err);
     return st == RDR_OK ? RDR_OK : fail(r, st, "%s", err.c_str());
+}
+
+// kernel variant for a scan-packed blob: 0 flat scan + cull, 1 flat scan exact-everything (debug), 2 cluster scan
+int scan_variant(const RdrRenderer *r)
+{
+    if (!r->use_cull) return 1;
+    return r->accel == RDR_ACCEL_BRUTE ? 0 : 2;
 }
 
 int ensure_device(RdrRenderer *r) { RDR_CUDA(r, cudaSetDevice(r->device)); return RDR_OK; }
@@ -119,8 +126,8 @@ int render_launch(RdrRenderer *r, uint32_t n)
     P.sample_count = n;
     P.max_bounces = r->config.max_bounces;
     RDR_CUDA(r, cudaEventRecord(r->ev_start, r->stream));
-    if (r->resident_ctas <= 0) RDR_CUDA(r, rdr::render_resident_ctas(P, r->use_cull, &r->resident_ctas));
-    RDR_CUDA(r, rdr::launch_render(P, r->use_cull, r->resident_ctas, r->stream));
+    if (r->resident_ctas <= 0) RDR_CUDA(r, rdr::render_resident_ctas(P, scan_variant(r), &r->resident_ctas));
+    RDR_CUDA(r, rdr::launch_render(P, scan_variant(r), r->resident_ctas, r->stream));
     RDR_CUDA(r, cudaEventRecord(r->ev_stop, r->stream));
     r->launches += 1;
     return RDR_OK;
@@ -429,7 +436,7 @@ int rdr_set_sample_offset(RdrRenderer *r, uint32_t first_sample)
 int rdr_set_accel(RdrRenderer *r, int accel)
 {
     if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
-    if (accel < RDR_ACCEL_AUTO || accel > RDR_ACCEL_BVH) return fail(r, RDR_ERR_INVALID, "unknown accel %d", accel);
+    if (accel < RDR_ACCEL_AUTO || accel > RDR_ACCEL_CLUSTER) return fail(r, RDR_ERR_INVALID, "unknown accel %d", accel);
     r->accel = accel;
     return RDR_OK;
 }
@@ -452,7 +459,7 @@ int rdr_first_hit(RdrRenderer *r, int32_t *ids, float *t)
     const size_t n = (size_t)r->params.cam.width * r->params.cam.height;
     DevBuf<int32_t> d_ids; DevBuf<float> d_t;
     RDR_CUDA(r, d_ids.alloc(n)); RDR_CUDA(r, d_t.alloc(n));
-    RDR_CUDA(r, rdr::launch_first_hit(r->params, r->use_cull, d_ids.p, d_t.p, r->stream));
+    RDR_CUDA(r, rdr::launch_first_hit(r->params, scan_variant(r), d_ids.p, d_t.p, r->stream));
     r->launches += 1;
     if (ids) RDR_CUDA(r, cudaMemcpyAsync(ids, d_ids.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, r->stream));
     if (t) RDR_CUDA(r, cudaMemcpyAsync(t, d_t.p, n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
@@ -471,7 +478,7 @@ int rdr_trace_path(RdrRenderer *r, uint32_t x, uint32_t y, uint32_t sample, RdrP
     RDR_CUDA(r, d_steps.alloc(capacity)); RDR_CUDA(r, d_n.alloc(1)); RDR_CUDA(r, d_rgba.alloc(4));
     FrameParams P = r->params;
     P.max_bounces = r->config.max_bounces;
-    RDR_CUDA(r, rdr::launch_trace_path(P, r->use_cull, x, y, sample, d_steps.p, capacity, d_n.p, d_rgba.p, r->stream));
+    RDR_CUDA(r, rdr::launch_trace_path(P, scan_variant(r), x, y, sample, d_steps.p, capacity, d_n.p, d_rgba.p, r->stream));
     r->launches += 1;
     uint32_t n = 0;
     RDR_CUDA(r, cudaMemcpyAsync(&n, d_n.p, sizeof n, cudaMemcpyDeviceToHost, r->stream));
@@ -518,7 +525,7 @@ int rdr_kat_trace(RdrRenderer *r, uint32_t n, const float *rays, int32_t *ids, f
     DevBuf<float> d_rays, d_t; DevBuf<int32_t> d_ids;
     RDR_CUDA(r, d_rays.alloc(6 * (size_t)n)); RDR_CUDA(r, d_t.alloc(n)); RDR_CUDA(r, d_ids.alloc(n));
     RDR_CUDA(r, cudaMemcpyAsync(d_rays.p, rays, 6 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, r->stream));
-    RDR_CUDA(r, rdr::launch_kat_trace(r->params, r->use_cull, n, d_rays.p, d_ids.p, d_t.p, r->stream));
+    RDR_CUDA(r, rdr::launch_kat_trace(r->params, scan_variant(r), n, d_rays.p, d_ids.p, d_t.p, r->stream));
     r->launches += 1;
     RDR_CUDA(r, cudaMemcpyAsync(ids, d_ids.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, r->stream));
     RDR_CUDA(r, cudaMemcpyAsync(t, d_t.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));

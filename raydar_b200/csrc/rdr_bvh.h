@@ -159,4 +159,60 @@ private:
     }
 };
 
+// ---- two-level clustering for the cluster scan -----------------------------------------------------------------
+// Groups the primitives into spatially coherent clusters of <= 8 (k-way median splits, k = ceil(n / 8), so the
+// clusters come out nearly full); primitives that are large compared with the scene (a floor cube) stay alone.
+struct ClusterSet {
+    std::vector<std::vector<uint32_t>> clusters;      // positions into the input array
+};
+
+inline ClusterSet build_clusters(const std::vector<BvhBuildPrim> &prims)
+{
+    ClusterSet out;
+    const uint32_t n = (uint32_t)prims.size();
+    if (n == 0) return out;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    std::vector<float> extents(n);
+    for (uint32_t i = 0; i < n; ++i) extents[i] = prims[i].e;
+    std::vector<float> sorted = extents;
+    std::nth_element(sorted.begin(), sorted.begin() + n / 2, sorted.end());
+    const float median_e = sorted[n / 2];
+    std::vector<uint32_t> rest;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (prims[i].e > 8.0f * median_e && n > 8) out.clusters.push_back({i});     // large primitive: its own entry
+        else rest.push_back(i);
+    }
+    (void)lo; (void)hi;
+    if (rest.empty()) return out;
+    // recursive proportional k-way split along the largest centroid axis
+    struct Job { uint32_t b, e; int k; };
+    std::vector<Job> todo{{0u, (uint32_t)rest.size(), (int)((rest.size() + 7) / 8)}};
+    while (!todo.empty()) {
+        const Job j = todo.back(); todo.pop_back();
+        if (j.k <= 1 || j.e - j.b <= 1) {
+            // a group the proportional split left above 8 (cannot happen: k = ceil(n/8)) is still cut here
+            for (uint32_t b = j.b; b < j.e; b += 8)
+                out.clusters.emplace_back(rest.begin() + b, rest.begin() + std::min(j.e, b + 8));
+            continue;
+        }
+        float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t i = j.b; i < j.e; ++i)
+            for (int a = 0; a < 3; ++a) { clo[a] = std::min(clo[a], prims[rest[i]].c[a]); chi[a] = std::max(chi[a], prims[rest[i]].c[a]); }
+        int axis = 0;
+        if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+        if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+        const int kl = j.k / 2, kr = j.k - kl;
+        // left part gets kl clusters' worth of primitives, at most 8 per cluster
+        uint32_t mid = j.b + (uint32_t)(((uint64_t)(j.e - j.b) * kl + j.k - 1) / j.k);
+        mid = std::min(mid, j.b + 8u * (uint32_t)kl);
+        mid = std::max(mid, j.e > 8u * (uint32_t)kr ? j.e - 8u * (uint32_t)kr : j.b);
+        mid = std::max(j.b + 1, std::min(j.e - 1, mid));
+        std::nth_element(rest.begin() + j.b, rest.begin() + mid, rest.begin() + j.e,
+                         [&](uint32_t x, uint32_t y) { return prims[x].c[axis] < prims[y].c[axis]; });
+        todo.push_back({j.b, mid, kl});
+        todo.push_back({mid, j.e, kr});
+    }
+    return out;
+}
+
 }  // namespace rdr

@@ -178,7 +178,7 @@ static inline uint32_t scratch_words(const SceneLayout &L)
 {
     if (L.mode == 1u) return (uint32_t)BVH_QCAP;
     const uint32_t chunks = (L.ns_pad > L.nc_pad ? L.ns_pad : L.nc_pad) / 32u;
-    return chunks ? chunks : 1u;
+    return chunks > CL_SCRATCH ? chunks : CL_SCRATCH;       // flat-scan masks or cluster masks + queue
 }
 
 size_t scene_smem_bytes(const SceneLayout &L, bool staged, uint32_t block)
@@ -186,8 +186,9 @@ size_t scene_smem_bytes(const SceneLayout &L, bool staged, uint32_t block)
     return (staged ? (size_t)L.blob_bytes + 16u : 0u) + (size_t)scratch_words(L) * block * sizeof(uint32_t);
 }
 
-// kernel variant: 0 = scan + cull, 1 = scan exact-everything (debug), 2 = BVH
-static inline int mode_of(const FrameParams &P, bool use_cull) { return P.lay.mode == 1u ? 2 : (use_cull ? 0 : 1); }
+// kernel variant (the MODE template argument): 0 = flat scan + cull, 1 = flat scan exact-everything (debug),
+// 2 = BVH, 3 = two-level cluster scan.  A BVH-packed blob can only be traversed as a BVH.
+static inline int mode_of(const FrameParams &P, int variant) { return P.lay.mode == 1u ? 2 : (variant == 2 ? 3 : variant); }
 
 template <typename K>
 static cudaError_t set_smem(K kernel, size_t bytes)
@@ -197,12 +198,13 @@ static cudaError_t set_smem(K kernel, size_t bytes)
 
 #define RDR_DISPATCH(mode, KERNEL, ...)                                   \
     do {                                                                  \
-        if ((mode) == 2) { KERNEL(2, __VA_ARGS__); }                      \
+        if ((mode) == 3) { KERNEL(3, __VA_ARGS__); }                      \
+        else if ((mode) == 2) { KERNEL(2, __VA_ARGS__); }                 \
         else if ((mode) == 1) { KERNEL(1, __VA_ARGS__); }                 \
         else { KERNEL(0, __VA_ARGS__); }                                  \
     } while (0)
 
-cudaError_t launch_render(const FrameParams &P, bool use_cull, int resident_ctas, cudaStream_t stream)
+cudaError_t launch_render(const FrameParams &P, int variant, int resident_ctas, cudaStream_t stream)
 {
     const uint32_t n_pixels = P.cam.width * P.cam.height;
     if (n_pixels == 0u) return cudaSuccess;
@@ -214,13 +216,13 @@ cudaError_t launch_render(const FrameParams &P, bool use_cull, int resident_ctas
     cudaError_t e = cudaMemsetAsync(P.pixel_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
 #define RDR_K(M, ...) do { if ((e = set_smem(render_kernel<M>, smem)) != cudaSuccess) return e; render_kernel<M><<<grid, RDR_BLOCK, smem, stream>>>(P); } while (0)
-    RDR_DISPATCH(mode_of(P, use_cull), RDR_K, 0);
+    RDR_DISPATCH(mode_of(P, variant), RDR_K, 0);
 #undef RDR_K
     return cudaGetLastError();
 }
 
 // resident CTAs of render_kernel on the current device for this scene's shared-memory footprint
-cudaError_t render_resident_ctas(const FrameParams &P, bool use_cull, int *out)
+cudaError_t render_resident_ctas(const FrameParams &P, int variant, int *out)
 {
     const size_t smem = scene_smem_bytes(P.lay, P.staged != 0u, RDR_BLOCK);
     int dev = 0, sms = 0, per_sm = 0;
@@ -229,7 +231,7 @@ cudaError_t render_resident_ctas(const FrameParams &P, bool use_cull, int *out)
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
 #define RDR_K(M, ...) do { if ((e = set_smem(render_kernel<M>, smem)) != cudaSuccess) return e; \
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<M>, RDR_BLOCK, smem); } while (0)
-    RDR_DISPATCH(mode_of(P, use_cull), RDR_K, 0);
+    RDR_DISPATCH(mode_of(P, variant), RDR_K, 0);
 #undef RDR_K
     if (e != cudaSuccess) return e;
     *out = sms * (per_sm > 0 ? per_sm : 1);
@@ -243,7 +245,7 @@ cudaError_t launch_resolve(const f4 *accum, uchar4 *out, uint32_t n_pixels, floa
     return cudaGetLastError();
 }
 
-cudaError_t launch_first_hit(const FrameParams &P, bool use_cull, int32_t *ids, float *ts, cudaStream_t stream)
+cudaError_t launch_first_hit(const FrameParams &P, int variant, int32_t *ids, float *ts, cudaStream_t stream)
 {
     const uint32_t n_pixels = P.cam.width * P.cam.height;
     if (n_pixels == 0u) return cudaSuccess;
@@ -251,12 +253,12 @@ cudaError_t launch_first_hit(const FrameParams &P, bool use_cull, int32_t *ids, 
     const uint32_t grid = (n_pixels + RDR_BLOCK - 1u) / RDR_BLOCK;
     cudaError_t e;
 #define RDR_K(M, ...) do { if ((e = set_smem(first_hit_kernel<M>, smem)) != cudaSuccess) return e; first_hit_kernel<M><<<grid, RDR_BLOCK, smem, stream>>>(P, ids, ts); } while (0)
-    RDR_DISPATCH(mode_of(P, use_cull), RDR_K, 0);
+    RDR_DISPATCH(mode_of(P, variant), RDR_K, 0);
 #undef RDR_K
     return cudaGetLastError();
 }
 
-cudaError_t launch_kat_trace(const FrameParams &P, bool use_cull, uint32_t n, const float *rays, int32_t *ids, float *ts,
+cudaError_t launch_kat_trace(const FrameParams &P, int variant, uint32_t n, const float *rays, int32_t *ids, float *ts,
                              cudaStream_t stream)
 {
     if (n == 0u) return cudaSuccess;
@@ -264,18 +266,18 @@ cudaError_t launch_kat_trace(const FrameParams &P, bool use_cull, uint32_t n, co
     const uint32_t grid = (n + RDR_BLOCK - 1u) / RDR_BLOCK;
     cudaError_t e;
 #define RDR_K(M, ...) do { if ((e = set_smem(kat_trace_kernel<M>, smem)) != cudaSuccess) return e; kat_trace_kernel<M><<<grid, RDR_BLOCK, smem, stream>>>(P, n, rays, ids, ts); } while (0)
-    RDR_DISPATCH(mode_of(P, use_cull), RDR_K, 0);
+    RDR_DISPATCH(mode_of(P, variant), RDR_K, 0);
 #undef RDR_K
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace_path(const FrameParams &P, bool use_cull, uint32_t x, uint32_t y, uint32_t sample,
+cudaError_t launch_trace_path(const FrameParams &P, int variant, uint32_t x, uint32_t y, uint32_t sample,
                               RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float *rgba, cudaStream_t stream)
 {
     const size_t smem = scene_smem_bytes(P.lay, P.staged != 0u, 32);
     cudaError_t e;
 #define RDR_K(M, ...) do { if ((e = set_smem(trace_path_kernel<M>, smem)) != cudaSuccess) return e; trace_path_kernel<M><<<1, 32, smem, stream>>>(P, x, y, sample, steps, capacity, n_steps, rgba); } while (0)
-    RDR_DISPATCH(mode_of(P, use_cull), RDR_K, 0);
+    RDR_DISPATCH(mode_of(P, variant), RDR_K, 0);
 #undef RDR_K
     return cudaGetLastError();
 }

@@ -15,12 +15,12 @@ struct SceneLayout;
 struct f4;
 
 size_t scene_smem_bytes(const SceneLayout &L, bool staged, uint32_t block);
-cudaError_t launch_render(const FrameParams &P, bool use_cull, int resident_ctas, cudaStream_t stream);
-cudaError_t render_resident_ctas(const FrameParams &P, bool use_cull, int *out);
+cudaError_t launch_render(const FrameParams &P, int variant, int resident_ctas, cudaStream_t stream);
+cudaError_t render_resident_ctas(const FrameParams &P, int variant, int *out);
 cudaError_t launch_resolve(const f4 *accum, uchar4 *out, uint32_t n_pixels, float divisor, cudaStream_t stream);
-cudaError_t launch_first_hit(const FrameParams &P, bool use_cull, int32_t *ids, float *ts, cudaStream_t stream);
-cudaError_t launch_kat_trace(const FrameParams &P, bool use_cull, uint32_t n, const float *rays, int32_t *ids, float *ts, cudaStream_t stream);
-cudaError_t launch_trace_path(const FrameParams &P, bool use_cull, uint32_t x, uint32_t y, uint32_t sample,
+cudaError_t launch_first_hit(const FrameParams &P, int variant, int32_t *ids, float *ts, cudaStream_t stream);
+cudaError_t launch_kat_trace(const FrameParams &P, int variant, uint32_t n, const float *rays, int32_t *ids, float *ts, cudaStream_t stream);
+cudaError_t launch_trace_path(const FrameParams &P, int variant, uint32_t x, uint32_t y, uint32_t sample,
                               RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float *rgba, cudaStream_t stream);
 cudaError_t launch_kat_hit(bool sphere, uint32_t n, const float *rays, const float *prims, float *t, int32_t *hit, cudaStream_t stream);
 cudaError_t launch_kat_camera_rays(const FrameParams &P, uint32_t n, const uint32_t *xy, float *rays, cudaStream_t stream);

@@ -110,6 +110,23 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
         L.off_material = off;    off += 48u * n;
         L.off_sphere_idx = off;  off += 4u * L.ns_pad;
         L.off_cube_idx = off;    off += 4u * L.nc_pad;
+        off = round_up_u32(off, 16u);
+        // two-level cluster scan (rdr_layout.h)
+        std::vector<BvhBuildPrim> cprims(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            const float *g = sc->geom + 4 * (size_t)i;
+            BvhBuildPrim &p = cprims[i];
+            p.c[0] = g[0]; p.c[1] = g[1]; p.c[2] = g[2]; p.index = i; p.cube = sc->kind[i] == RDR_CUBE;
+            p.e = p.cube ? std::fabs(g[3]) * 0.5f + cube_pad : std::fabs(g[3]) + 2.0f * cube_pad;
+        }
+        const ClusterSet cs = build_clusters(cprims);
+        L.n_top = (uint32_t)cs.clusters.size(); L.nt_pad = round_up_u32(L.n_top, 32u);
+        if (L.nt_pad > 128u) { err = "too many objects for the shared-memory scan (limit 128 clusters): use RDR_ACCEL_BVH or AUTO"; return RDR_ERR_UNSUPPORTED; }
+        L.n_members = 8u * L.n_top;
+        L.off_top = off;         off += 32u * L.nt_pad;
+        L.off_member_box = off;  off += 16u * L.n_members;
+        L.off_member_geom = off; off += 16u * L.n_members;
+        L.off_member_idx = off;  off += 4u * L.n_members;
         L.blob_bytes = std::max(16u, round_up_u32(off, 16u));
 
         blob.assign(L.blob_bytes, 0);
@@ -126,6 +143,37 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
             c[0] = g[0]; c[1] = g[1]; c[2] = g[2]; c[3] = std::fabs(g[3]) * 0.5f + cube_pad;
             e[0] = g[0]; e[1] = g[1]; e[2] = g[2]; e[3] = g[3];
             reinterpret_cast<uint32_t *>(blob.data() + L.off_cube_idx)[j] = cubes[j];
+        }
+        for (uint32_t k = 0; k < L.nt_pad; ++k) {                      // unused top entries: e = -1 (always rejected)
+            float *t = reinterpret_cast<float *>(blob.data() + L.off_top) + 8 * (size_t)k;
+            t[3] = t[4] = t[5] = -1.0f;
+        }
+        for (uint32_t k = 0; k < L.n_top; ++k) {
+            const std::vector<uint32_t> &members = cs.clusters[k];
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            bool any_sphere = false;
+            for (uint32_t j = 0; j < members.size(); ++j) {
+                const BvhBuildPrim &p = cprims[members[j]];
+                const float *g = sc->geom + 4 * (size_t)p.index;
+                const uint32_t slot = 8u * k + j;
+                float *mb = quad_at(L.off_member_box, slot), *mg = quad_at(L.off_member_geom, slot);
+                mb[0] = p.c[0]; mb[1] = p.c[1]; mb[2] = p.c[2]; mb[3] = p.cube ? p.e : -p.e;
+                mg[0] = g[0]; mg[1] = g[1]; mg[2] = g[2]; mg[3] = g[3];
+                reinterpret_cast<uint32_t *>(blob.data() + L.off_member_idx)[slot] = p.index | (p.cube ? BVH_CUBE_BIT : 0u);
+                for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p.c[a] - p.e); hi[a] = std::max(hi[a], p.c[a] + p.e); }
+                any_sphere |= !p.cube;
+            }
+            float *t = reinterpret_cast<float *>(blob.data() + L.off_top) + 8 * (size_t)k;
+            float e3[3];
+            for (int a = 0; a < 3; ++a) {
+                t[a] = 0.5f * (lo[a] + hi[a]);
+                const float h = std::max(hi[a] - t[a], t[a] - lo[a]);
+                e3[a] = std::nextafter(h * (1.0f + 1e-6f), INFINITY);
+            }
+            t[3] = e3[0]; t[4] = e3[1]; t[5] = e3[2];
+            const uint32_t payload = ((8u * k) << 4) | (uint32_t)members.size();
+            memcpy(&t[6], &payload, 4);
+            t[7] = any_sphere ? 1.0f : 0.0f;
         }
         fill_objects();
     }

@@ -15,6 +15,9 @@ struct SceneView {
     uint32_t n_spheres, n_cubes, ns_chunks, nc_chunks;
     const f4 *nodes;        // BVH mode: 16 quads per node
     uint32_t n_objects;
+    const f4 *top, *member_box, *member_geom;       // cluster scan
+    const uint32_t *member_idx;
+    uint32_t n_top, nt_chunks;
 };
 
 RDR_HD SceneView scene_view(const unsigned char *base, const SceneLayout &L)
@@ -32,6 +35,11 @@ RDR_HD SceneView scene_view(const unsigned char *base, const SceneLayout &L)
     s.ns_chunks = L.ns_pad >> 5; s.nc_chunks = L.nc_pad >> 5;
     s.nodes = reinterpret_cast<const f4 *>(base + L.off_nodes);
     s.n_objects = L.n_objects;
+    s.top = reinterpret_cast<const f4 *>(base + L.off_top);
+    s.member_box = reinterpret_cast<const f4 *>(base + L.off_member_box);
+    s.member_geom = reinterpret_cast<const f4 *>(base + L.off_member_geom);
+    s.member_idx = reinterpret_cast<const uint32_t *>(base + L.off_member_idx);
+    s.n_top = L.n_top; s.nt_chunks = L.nt_pad >> 5;
     return s;
 }
 
@@ -230,11 +238,142 @@ RDR_HD Hit trace_bvh(const SceneView &S, const CullConsts &cc, uint32_t *queue, 
     return best;
 }
 
-// nearest-hit dispatch of the kernels: MODE 0 = scan with cull, 1 = scan exact-everything, 2 = BVH
+// ---- two-level ("cluster") scan -------------------------------------------------------------------------------
+// The flat scan tests every primitive for every ray.  Here the primitives are grouped on the host into spatially
+// coherent clusters of <= 8 (rdr_bvh.h build_clusters; a large primitive such as the floor stays alone):
+//   A0  uniform scan over the cluster boxes -- every lane tests the same box, broadcast LDS.128, no divergence --
+//       leaving a per-lane bit mask of the clusters the ray may touch (typically 2-4 of ~24 on benchmark.rscn);
+//   A1  each lane walks ITS clusters and slab-tests their members (per-lane shared-memory reads, one quad per
+//       member); survivors go to the lane's candidate queue;
+//   B   exact, reference-ordered tests on the queue, spheres first (behind the cheap sphere pre-test), then cubes.
+// The boxes are conservative w.r.t. the as-written tests exactly as in the BVH (per-ray rho on sphere boxes), and
+// the winner is the (t, original index) minimum, so the result equals the flat scan's.
+// scratch: per-lane words, [0 .. nt_chunks) cluster masks, [CL_QBASE .. CL_QBASE + BVH_QCAP) the queue.
+constexpr uint32_t CL_QBASE = 4u;            // up to 128 clusters (1024 primitives)
+constexpr uint32_t CL_SCRATCH = CL_QBASE + (uint32_t)BVH_QCAP;
+
+// member quad: (cx, cy, cz, +-(e)), negative e marks a sphere (its box grows by the per-ray rho)
+RDR_HD bool member_may_hit(const RayBvh &rb, f4 m, float best)
+{
+    const RayCull &rc = rb.rc;
+    const uint32_t sphere_mask = (uint32_t)((int32_t)f2u(m.w) >> 31);
+    const float e = fadd(fabs_(m.w), u2f(f2u(rb.rho) & sphere_mask));
+    const float tcx = fma(m.x, rc.inv.x, fneg(rc.od.x));
+    const float tcy = fma(m.y, rc.inv.y, fneg(rc.od.y));
+    const float tcz = fma(m.z, rc.inv.z, fneg(rc.od.z));
+    const float tn = fmax(fmax(fma(fneg(e), rc.ainv.x, tcx), fma(fneg(e), rc.ainv.y, tcy)), fmax(fma(fneg(e), rc.ainv.z, tcz), 0.0f));
+    const float tf = fmin(fmin(fma(e, rc.ainv.x, tcx), fma(e, rc.ainv.y, tcy)), fmin(fma(e, rc.ainv.z, tcz), best));
+    return !(tn > tf);
+}
+
+RDR_HD void cluster_exact(const SceneView &S, const RayBvh &rb, uint32_t *scratch, uint32_t stride, uint32_t nq, v3 o, v3 d,
+                          Hit &best, TraceStats *stats)
+{
+    for (uint32_t q = 0; q < nq; ++q) {                     // spheres
+        const uint32_t slot = scratch[(CL_QBASE + q) * stride];
+        const uint32_t tag = S.member_idx[slot];
+        if (tag & 0x40000000u) continue;
+        const f4 g = S.member_geom[slot];
+        if (!sphere_may_hit(o, d, rb.rc, g.x, g.y, g.z, fmul(g.w, g.w))) continue;
+        RDR_STAT(stats, sphere_exact);
+        float t;
+        if (hit_sphere_exact(o, d, mk3(g.x, g.y, g.z), g.w, &t)) {
+            const int idx = (int)(tag & 0x3fffffffu);
+            if (hit_better(t, idx, best.t, best.idx)) { best.idx = idx; best.t = t; }
+        }
+    }
+    for (uint32_t q = 0; q < nq; ++q) {                     // cubes
+        const uint32_t slot = scratch[(CL_QBASE + q) * stride];
+        const uint32_t tag = S.member_idx[slot];
+        if (!(tag & 0x40000000u)) continue;
+        const f4 g = S.member_geom[slot];
+        RDR_STAT(stats, cube_exact);
+        float t;
+        if (hit_cube_exact(o, d, mk3(g.x, g.y, g.z), g.w, &t)) {
+            const int idx = (int)(tag & 0x3fffffffu);
+            if (hit_better(t, idx, best.t, best.idx)) { best.idx = idx; best.t = t; }
+        }
+    }
+}
+
+RDR_HD Hit trace_cluster(const SceneView &S, const CullConsts &cc, uint32_t *scratch, uint32_t stride, v3 o, v3 d,
+                         TraceStats *stats = nullptr)
+{
+    Hit best; best.idx = -1; best.t = finf();
+    RDR_STAT(stats, traces);
+    if (S.n_top == 0u) return best;
+    const RayBvh rb = make_ray_bvh(o, d, cc);
+    if (rb.rc.degenerate) {                       // origin outside the scene bound / non-finite ray: exact test on everything
+        RDR_STAT(stats, degenerate);
+        for (uint32_t k = 0; k < S.n_top; ++k) {
+            const uint32_t payload = f2u(S.top[2 * k + 1].z);
+            for (uint32_t j = 0; j < (payload & 15u); ++j) {
+                const uint32_t slot = (payload >> 4) + j;
+                const uint32_t tag = S.member_idx[slot];
+                const f4 g = S.member_geom[slot];
+                float t;
+                const bool hit = (tag & 0x40000000u) ? hit_cube_exact(o, d, mk3(g.x, g.y, g.z), g.w, &t)
+                                                      : hit_sphere_exact(o, d, mk3(g.x, g.y, g.z), g.w, &t);
+                const int idx = (int)(tag & 0x3fffffffu);
+                if (hit && hit_better(t, idx, best.t, best.idx)) { best.idx = idx; best.t = t; }
+            }
+        }
+        return best;
+    }
+    // ---- A0: uniform scan over the cluster boxes ----
+    for (uint32_t ch = 0; ch < S.nt_chunks; ++ch) {
+        uint32_t m = 0u;
+        const f4 *p = S.top + ch * 64u;
+        const int groups = (int)((S.n_top - ch * 32u + 7u) >> 3) < 4 ? (int)((S.n_top - ch * 32u + 7u) >> 3) : 4;
+        RDR_NOUNROLL
+        for (int g = 0; g < groups; ++g) {
+            uint32_t mm = 0u;
+            RDR_UNROLL
+            for (int j = 0; j < 8; ++j) {
+                float tn;
+                if (bvh_entry_may_hit(rb, p[2 * (g * 8 + j)], p[2 * (g * 8 + j) + 1], finf(), &tn)) mm |= (1u << j);
+            }
+            m |= mm << (g * 8);
+        }
+        scratch[ch * stride] = m;
+    }
+    // ---- A1: members of the lane's clusters;  B whenever the queue fills and at the end ----
+    uint32_t nq = 0u;
+    float prune = finf();
+    uint32_t ch = 0u, m = scratch[0];
+    for (;;) {
+        while (m == 0u && ++ch < S.nt_chunks) m = scratch[ch * stride];
+        if (m == 0u) break;
+        const int k = ffs32(m); m &= m - 1u;
+        const uint32_t payload = f2u(S.top[2 * (ch * 32u + (uint32_t)k) + 1].z);
+        const uint32_t first = payload >> 4, count = payload & 15u;
+        RDR_STAT(stats, nodes_visited);
+        if (count == 1u) {                                       // a primitive on its own: its box was the top entry
+            scratch[(CL_QBASE + nq) * stride] = first; ++nq;
+        } else {
+            const f4 *mb = S.member_box + first;
+            RDR_UNROLL
+            for (uint32_t j = 0; j < 8u; ++j) {
+                if (j < count && member_may_hit(rb, mb[j], prune)) { scratch[(CL_QBASE + nq) * stride] = first + j; ++nq; RDR_STAT(stats, entries_hit); }
+            }
+        }
+        if (nq > (uint32_t)(BVH_QCAP - 8)) {
+            cluster_exact(S, rb, scratch, stride, nq, o, d, best, stats);
+            nq = 0u;
+            if (best.idx >= 0 && !isnan_(best.t)) prune = best.t;
+        }
+    }
+    cluster_exact(S, rb, scratch, stride, nq, o, d, best, stats);
+    return best;
+}
+
+// nearest-hit dispatch of the kernels: MODE 0 = flat scan with cull, 1 = flat scan exact-everything, 2 = BVH,
+// 3 = two-level cluster scan
 template <int MODE>
 RDR_HD Hit trace_any(const SceneView &S, const CullConsts &cc, uint32_t *scratch, uint32_t stride, v3 o, v3 d,
                      TraceStats *stats = nullptr)
 {
+    if (MODE == 3) return trace_cluster(S, cc, scratch, stride, o, d, stats);
     if (MODE == 2) return trace_bvh(S, cc, scratch, stride, o, d, stats);
     if (MODE == 1) return trace_brute<false>(S, cc, scratch, stride, o, d, stats);
     return trace_brute<true>(S, cc, scratch, stride, o, d, stats);

@@ -37,13 +37,14 @@ struct Packed {
         memcpy(blob, tmp.data(), tmp.size());
         P.blob = blob;
         S = scene_view(blob, P.lay);
-        masks.resize(std::max<uint32_t>(std::max(P.lay.ns_pad, P.lay.nc_pad) / 32 + 1, BVH_QCAP));
+        masks.resize(std::max<uint32_t>(std::max(P.lay.ns_pad, P.lay.nc_pad) / 32 + 1, CL_SCRATCH));
     }
 };
 
 Hit trace_mode(int use_cull, const Packed &pk, uint32_t *scratch, v3 o, v3 d, TraceStats *st)
 {
     if (pk.P.lay.mode == 1u) return trace_any<2>(pk.S, pk.P.cull, scratch, 1, o, d, st);
+    if (use_cull == 3) return trace_any<3>(pk.S, pk.P.cull, scratch, 1, o, d, st);
     return use_cull ? trace_any<0>(pk.S, pk.P.cull, scratch, 1, o, d, st) : trace_any<1>(pk.S, pk.P.cull, scratch, 1, o, d, st);
 }
 
@@ -124,6 +125,7 @@ int hs_render(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t samp
         for (int64_t p = 0; p < n; ++p) {
             f4 acc; acc.x = accum[4 * p]; acc.y = accum[4 * p + 1]; acc.z = accum[4 * p + 2]; acc.w = accum[4 * p + 3];
             acc = pk.P.lay.mode == 1u ? render_pixel<2>(pk.P, pk.S, masks.data(), 1, (uint32_t)p, acc, &local)
+                  : use_cull == 3  ? render_pixel<3>(pk.P, pk.S, masks.data(), 1, (uint32_t)p, acc, &local)
                   : use_cull       ? render_pixel<0>(pk.P, pk.S, masks.data(), 1, (uint32_t)p, acc, &local)
                                    : render_pixel<1>(pk.P, pk.S, masks.data(), 1, (uint32_t)p, acc, &local);
             accum[4 * p] = acc.x; accum[4 * p + 1] = acc.y; accum[4 * p + 2] = acc.z; accum[4 * p + 3] = acc.w;
@@ -143,6 +145,7 @@ int hs_trace_path(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t 
     pk.P.seed_lo = (uint32_t)seed; pk.P.seed_hi = (uint32_t)(seed >> 32);
     pk.P.max_bounces = max_bounces;
     *n_steps = pk.P.lay.mode == 1u ? trace_path_lane<2>(pk.P, pk.S, pk.masks.data(), 1, x, y, sample, steps, capacity, rgba)
+               : use_cull == 3    ? trace_path_lane<3>(pk.P, pk.S, pk.masks.data(), 1, x, y, sample, steps, capacity, rgba)
                : use_cull         ? trace_path_lane<0>(pk.P, pk.S, pk.masks.data(), 1, x, y, sample, steps, capacity, rgba)
                                   : trace_path_lane<1>(pk.P, pk.S, pk.masks.data(), 1, x, y, sample, steps, capacity, rgba);
     return RDR_OK;
@@ -218,6 +221,14 @@ int hs_bvh_info(const RdrSceneFlat *sc, uint32_t *n_nodes, uint32_t *mode, uint3
     Packed pk(sc, true);
     if (pk.status != RDR_OK) return pk.status;
     *n_nodes = pk.P.lay.n_nodes; *mode = pk.P.lay.mode; *blob_bytes = pk.P.lay.blob_bytes;
+    return RDR_OK;
+}
+
+int hs_cluster_info(const RdrSceneFlat *sc, uint32_t *n_top, uint32_t *blob_bytes)
+{
+    Packed pk(sc, false);
+    if (pk.status != RDR_OK) return pk.status;
+    *n_top = pk.P.lay.n_top; *blob_bytes = pk.P.lay.blob_bytes;
     return RDR_OK;
 }
 

@@ -55,6 +55,7 @@ def lib():
         L.hs_rng_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
         L.hs_scene_consts.argtypes = [sfp, fp, fp, fp]
         L.hs_bvh_info.argtypes = [sfp, u32p, u32p, u32p]
+        L.hs_cluster_info.argtypes = [sfp, u32p, u32p]
         _lib = L
     return _lib
 
@@ -136,6 +137,16 @@ def rng_block(seed, pixel, sample, bounce, block):
 
 
 BVH = 2      # pass as use_cull to select the hierarchy (1/True = scan + cull, 0/False = scan, exact test on everything)
+
+
+CLUSTER = 3  # two-level cluster scan
+
+
+def cluster_info(scene):
+    f = rb._as_flat(scene)
+    n = C.c_uint32(); nbytes = C.c_uint32()
+    _ok(lib().hs_cluster_info(C.byref(f), C.byref(n), C.byref(nbytes)))
+    return n.value, nbytes.value
 
 
 def bvh_info(scene):

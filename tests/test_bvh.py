@@ -11,6 +11,13 @@ def u32(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
+def test_cluster_shape(hs, benchmark_scene):
+    n_top, nbytes = hs.cluster_info(benchmark_scene)
+    assert n_top == 24                                   # the floor cube on its own + 182 primitives in 23 clusters of <= 8
+    n_top5, _ = hs.cluster_info(ss.config5(64, 36))
+    assert 65 <= n_top5 <= 70
+
+
 def test_hierarchy_shape(hs):
     scene = ss.config4(5000, 64, 36)
     n_nodes, mode, nbytes = hs.bvh_info(scene)
@@ -45,13 +52,13 @@ def test_config5_glass_metal_lattice(hs, orc):
     scene = ss.config5(160, 90)
     assert scene.n_objects == 513
     ids_o, t_o = orc.first_hit(scene)
-    for mode in (True, hs.BVH):
+    for mode in (True, hs.BVH, hs.CLUSTER):
         ids, ts, _ = hs.first_hit(scene, mode)
         assert np.array_equal(ids, ids_o) and np.array_equal(u32(ts), u32(t_o))
     small = scene.with_resolution(64, 36)
     want, stats = orc.render(small, 5, 0, 2, 32, n_threads=orc.max_threads(), want_stats=True)
     assert stats.trace_calls / stats.samples > 25            # closed box: paths rarely end before the bounce limit
-    for mode in (True, hs.BVH):
+    for mode in (True, hs.BVH, hs.CLUSTER):
         got, _ = hs.render(small, 5, 0, 2, 32, use_cull=mode)
         assert np.array_equal(u32(got), u32(want))
 
@@ -74,6 +81,8 @@ def test_coincident_and_nested_primitives(hs, orc, default_scene):
     a_ids, a_t, _ = hs.trace(s, rays, False)
     b_ids, b_t, _ = hs.trace(s, rays, hs.BVH)
     assert np.array_equal(a_ids, b_ids) and np.array_equal(u32(a_t), u32(b_t))
+    c_ids, c_t, _ = hs.trace(s, rays, hs.CLUSTER)
+    assert np.array_equal(a_ids, c_ids) and np.array_equal(u32(a_t), u32(c_t))
     for i in range(0, n, 101):
         idx, t = orc.trace(s, rays[i, :3], rays[i, 3:])
         assert idx == b_ids[i]

@@ -19,7 +19,7 @@ def test_rng_matches_oracle(hs, orc):
         assert hs.rng_block(seed, *args) == orc.rng_block(seed, *args)
 
 
-@pytest.mark.parametrize("cull", [True, False, 2])       # scan + cull, scan exact-everything, BVH
+@pytest.mark.parametrize("cull", [True, False, 2, 3])    # flat scan + cull, flat scan exact-everything, BVH, cluster scan
 def test_first_hit_bit_exact_1080p(hs, orc, benchmark_scene, cull):
     scene = benchmark_scene.with_resolution(1920, 1080)
     ids_o, t_o = orc.first_hit(scene)
@@ -28,13 +28,13 @@ def test_first_hit_bit_exact_1080p(hs, orc, benchmark_scene, cull):
     assert np.array_equal(u32(ts), u32(t_o))
     if cull:   # the cull / the hierarchy keep ~1.4-1.8 of 183 primitives per primary ray
         assert (st.sphere_exact + st.cube_exact) / st.traces < 3.0
-    if cull == 2:
+    if cull in (2, 3):
         assert 1.0 <= st.nodes_visited / st.traces < 12.0
 
 
 def test_first_hit_default_scene(hs, orc, default_scene):
     ids_o, t_o = orc.first_hit(default_scene)
-    for mode in (True, 2):
+    for mode in (True, 2, 3):
         ids, ts, _ = hs.first_hit(default_scene, mode)
         assert np.array_equal(ids, ids_o) and np.array_equal(u32(ts), u32(t_o))
 
@@ -44,7 +44,7 @@ def test_first_hit_default_scene(hs, orc, default_scene):
 def test_accumulator_bit_exact(hs, orc, default_scene, benchmark_scene, name, res, spp, bounces):
     scene = (default_scene if name == "default" else benchmark_scene).with_resolution(*res)
     want = orc.render(scene, 77, 0, spp, bounces, n_threads=orc.max_threads())
-    for cull in (True, False, 2):
+    for cull in (True, False, 2, 3):
         got, _ = hs.render(scene, 77, 0, spp, bounces, use_cull=cull)
         assert np.array_equal(u32(got), u32(want)), (name, cull)
     assert np.array_equal(hs.resolve(want, spp), orc.resolve(want, spp))
@@ -65,7 +65,7 @@ def test_single_path_debug_mode(hs, orc, default_scene, benchmark_scene):
         for _ in range(150):
             x, y, s = int(rng.integers(0, scene.width)), int(rng.integers(0, scene.height)), int(rng.integers(0, 500))
             steps_o, rgba_o = orc.trace_path(scene, x, y, s, 31337, 12)
-            steps_h, rgba_h = hs.trace_path(scene, x, y, s, 31337, 12, use_cull=(2 if s % 2 else True))
+            steps_h, rgba_h = hs.trace_path(scene, x, y, s, 31337, 12, use_cull=(True, 2, 3)[s % 3])
             assert len(steps_o) == len(steps_h)
             for a, b in zip(steps_o, steps_h):
                 assert (a.object, a.lobe, a.front_face) == (b.object, b.lobe, b.front_face)
@@ -110,9 +110,10 @@ def test_ties_and_list_order(hs, orc, default_scene):
     rays = np.concatenate([o, d], 1)
     ids, ts, _ = hs.trace(scene, rays, True)
     ids2, ts2, _ = hs.trace(scene, rays, False)
-    ids3, ts3, _ = hs.trace(scene, rays, 2)
     assert np.array_equal(ids, ids2) and np.array_equal(u32(ts), u32(ts2))
-    assert np.array_equal(ids, ids3) and np.array_equal(u32(ts), u32(ts3))
+    for mode in (2, 3):
+        ids3, ts3, _ = hs.trace(scene, rays, mode)
+        assert np.array_equal(ids, ids3) and np.array_equal(u32(ts), u32(ts3))
     for i in range(0, n, 37):
         idx, t = orc.trace(scene, rays[i, :3], rays[i, 3:])
         assert idx == ids[i]
@@ -134,9 +135,10 @@ def test_degenerate_rays_take_exact_path(hs, orc, benchmark_scene):
     ids, ts, st = hs.trace(benchmark_scene, rays, True)
     assert st.degenerate >= n - 10
     # the hierarchy clamps 1/d instead (no O(N) fallback for axis-parallel rays); only far-away origins are degenerate
-    ids_b, ts_b, st_b = hs.trace(benchmark_scene, rays, 2)
-    assert np.array_equal(ids, ids_b) and np.array_equal(u32(ts), u32(ts_b))
-    assert 150 <= st_b.degenerate <= 250
+    for mode in (2, 3):
+        ids_b, ts_b, st_b = hs.trace(benchmark_scene, rays, mode)
+        assert np.array_equal(ids, ids_b) and np.array_equal(u32(ts), u32(ts_b))
+        assert 150 <= st_b.degenerate <= 250
     for i in range(0, n, 3):
         idx, t = orc.trace(benchmark_scene, rays[i, :3], rays[i, 3:])
         assert idx == ids[i]
