@@ -20,11 +20,15 @@
 
 #if defined(__CUDACC__)
 #define RDR_HD __host__ __device__ __forceinline__
+#define RDR_HD_NOINLINE __host__ __device__ __noinline__
 #define RDR_UNROLL _Pragma("unroll")
 #define RDR_NOUNROLL _Pragma("unroll 1")
+#define RDR_UNROLL4 _Pragma("unroll 4")
 #else
 #define RDR_UNROLL
 #define RDR_NOUNROLL
+#define RDR_UNROLL4
+#define RDR_HD_NOINLINE inline
 #define RDR_HD inline
 #include <math.h>
 #endif
@@ -366,6 +370,7 @@ struct RayCull {
     v3 inv, od, ainv;      // 1/d, o/d, |1/d|
     float a;               // d.d
     float M, Ms, ek;       // sphere margins (see above)
+    float s_ray;           // 2|o|^2 + q_max
     bool degenerate;
 };
 
@@ -378,6 +383,7 @@ RDR_HD RayCull make_ray_cull(v3 o, v3 d, const CullConsts &cc)
     rc.a = fma(d.x, d.x, fma(d.y, d.y, fmul(d.z, d.z)));
     float oo = fma(o.x, o.x, fma(o.y, o.y, fmul(o.z, o.z)));
     float s_ray = fma(2.0f, oo, cc.sphere_q_max);
+    rc.s_ray = s_ray;
     rc.Ms = fmul(1.9073486328125e-06f, s_ray);                    // 2^-19 S (32u; proven need 28u, observed 5.3u)
     rc.M = fmul(rc.a, rc.Ms);
     rc.ek = fmul(1.9073486328125e-06f, fsqrt(fmul(rc.a, s_ray))); // 2^-19 sqrt(a S)
@@ -440,14 +446,12 @@ RDR_HD RayBvh make_ray_bvh(v3 o, v3 d, const CullConsts &cc)
         rb.rc.od = mk3(fmul(o.x, rb.rc.inv.x), fmul(o.y, rb.rc.inv.y), fmul(o.z, rb.rc.inv.z));
         rb.rc.ainv = mk3(fabs_(rb.rc.inv.x), fabs_(rb.rc.inv.y), fabs_(rb.rc.inv.z));
         const float omax = fmax(fmax(fabs_(o.x), fabs_(o.y)), fabs_(o.z));
-        const float s_ray = fdiv(rb.rc.Ms, 1.9073486328125e-06f);
         // same conditions as make_ray_cull minus the 1/d test; a NaN direction component stays degenerate
-        rb.rc.degenerate = !(omax <= cc.origin_bound) || !(rb.rc.a > 1e-30f) || !(rb.rc.a < 1e30f) || !(s_ray < 1e30f) ||
+        rb.rc.degenerate = !(omax <= cc.origin_bound) || !(rb.rc.a > 1e-30f) || !(rb.rc.a < 1e30f) || !(rb.rc.s_ray < 1e30f) ||
                            isnan_(d.x) || isnan_(d.y) || isnan_(d.z);
     }
-    const float s_ray = fdiv(rb.rc.Ms, 1.9073486328125e-06f);
     rb.rho = fadd(fsub(fsqrt(fma(cc.sphere_r_min, cc.sphere_r_min, rb.rc.Ms)), cc.sphere_r_min),
-                  fmul(1.9073486328125e-06f, fsqrt(s_ray)));
+                  fmul(1.9073486328125e-06f, fsqrt(rb.rc.s_ray)));
     rb.rho = fmul(rb.rho, 1.0001f);
     return rb;
 }

@@ -190,6 +190,7 @@ RDR_HD Hit trace_bvh(const SceneView &S, const CullConsts &cc, uint32_t *queue, 
     const RayBvh rb = make_ray_bvh(o, d, cc);
     if (rb.rc.degenerate) {                       // origin outside the scene bound / non-finite ray: exact test on everything
         RDR_STAT(stats, degenerate);
+        RDR_NOUNROLL
         for (uint32_t i = 0; i < S.n_objects; ++i) {
             const uint32_t kind_bits = f2u(S.material[3 * i + 2].w);
             bvh_exact_prim(S, i | (kind_bits ? 0x40000000u : 0u), o, d, best, stats);
@@ -223,10 +224,12 @@ RDR_HD Hit trace_bvh(const SceneView &S, const CullConsts &cc, uint32_t *queue, 
             }
         }
         // ---- phase E ----
+        RDR_NOUNROLL
         for (uint32_t q = 0; q < nq; ++q) {
             const uint32_t payload = queue[q * stride];
             if (!(payload & 0x40000000u)) bvh_exact_prim(S, payload, o, d, best, stats);
         }
+        RDR_NOUNROLL
         for (uint32_t q = 0; q < nq; ++q) {
             const uint32_t payload = queue[q * stride];
             if (payload & 0x40000000u) bvh_exact_prim(S, payload, o, d, best, stats);
@@ -266,15 +269,18 @@ RDR_HD bool member_may_hit(const RayBvh &rb, f4 m, float best)
     return !(tn > tf);
 }
 
-RDR_HD void cluster_exact(const SceneView &S, const RayBvh &rb, uint32_t *scratch, uint32_t stride, uint32_t nq, v3 o, v3 d,
-                          Hit &best, TraceStats *stats)
+// (not inlined: the compiler otherwise duplicates these ~4 KB per call site, and the hot loop must fit the
+// instruction cache -- see DESIGN.md 4.5)
+RDR_HD_NOINLINE Hit cluster_exact(const SceneView &S, const RayCull rc, uint32_t *scratch, uint32_t stride, uint32_t nq, v3 o, v3 d,
+                                  Hit best, TraceStats *stats)
 {
+    RDR_NOUNROLL
     for (uint32_t q = 0; q < nq; ++q) {                     // spheres
         const uint32_t slot = scratch[(CL_QBASE + q) * stride];
         const uint32_t tag = S.member_idx[slot];
         if (tag & 0x40000000u) continue;
         const f4 g = S.member_geom[slot];
-        if (!sphere_may_hit(o, d, rb.rc, g.x, g.y, g.z, fmul(g.w, g.w))) continue;
+        if (!rc.degenerate && !sphere_may_hit(o, d, rc, g.x, g.y, g.z, fmul(g.w, g.w))) continue;
         RDR_STAT(stats, sphere_exact);
         float t;
         if (hit_sphere_exact(o, d, mk3(g.x, g.y, g.z), g.w, &t)) {
@@ -282,6 +288,7 @@ RDR_HD void cluster_exact(const SceneView &S, const RayBvh &rb, uint32_t *scratc
             if (hit_better(t, idx, best.t, best.idx)) { best.idx = idx; best.t = t; }
         }
     }
+    RDR_NOUNROLL
     for (uint32_t q = 0; q < nq; ++q) {                     // cubes
         const uint32_t slot = scratch[(CL_QBASE + q) * stride];
         const uint32_t tag = S.member_idx[slot];
@@ -294,6 +301,7 @@ RDR_HD void cluster_exact(const SceneView &S, const RayBvh &rb, uint32_t *scratc
             if (hit_better(t, idx, best.t, best.idx)) { best.idx = idx; best.t = t; }
         }
     }
+    return best;
 }
 
 RDR_HD Hit trace_cluster(const SceneView &S, const CullConsts &cc, uint32_t *scratch, uint32_t stride, v3 o, v3 d,
@@ -303,67 +311,54 @@ RDR_HD Hit trace_cluster(const SceneView &S, const CullConsts &cc, uint32_t *scr
     RDR_STAT(stats, traces);
     if (S.n_top == 0u) return best;
     const RayBvh rb = make_ray_bvh(o, d, cc);
-    if (rb.rc.degenerate) {                       // origin outside the scene bound / non-finite ray: exact test on everything
-        RDR_STAT(stats, degenerate);
-        for (uint32_t k = 0; k < S.n_top; ++k) {
-            const uint32_t payload = f2u(S.top[2 * k + 1].z);
-            for (uint32_t j = 0; j < (payload & 15u); ++j) {
-                const uint32_t slot = (payload >> 4) + j;
-                const uint32_t tag = S.member_idx[slot];
-                const f4 g = S.member_geom[slot];
-                float t;
-                const bool hit = (tag & 0x40000000u) ? hit_cube_exact(o, d, mk3(g.x, g.y, g.z), g.w, &t)
-                                                      : hit_sphere_exact(o, d, mk3(g.x, g.y, g.z), g.w, &t);
-                const int idx = (int)(tag & 0x3fffffffu);
-                if (hit && hit_better(t, idx, best.t, best.idx)) { best.idx = idx; best.t = t; }
-            }
-        }
-        return best;
-    }
+    // origin outside the scene bound / non-finite ray: no culling, every member goes through the exact tests
+    const bool all = rb.rc.degenerate;
+    if (all) RDR_STAT(stats, degenerate);
     // ---- A0: uniform scan over the cluster boxes ----
     for (uint32_t ch = 0; ch < S.nt_chunks; ++ch) {
         uint32_t m = 0u;
         const f4 *p = S.top + ch * 64u;
-        const int groups = (int)((S.n_top - ch * 32u + 7u) >> 3) < 4 ? (int)((S.n_top - ch * 32u + 7u) >> 3) : 4;
+        const uint32_t left = S.n_top - ch * 32u;
+        const int groups = left >= 32u ? 4 : (int)((left + 7u) >> 3);
         RDR_NOUNROLL
         for (int g = 0; g < groups; ++g) {
             uint32_t mm = 0u;
-            RDR_UNROLL
+            RDR_UNROLL4
             for (int j = 0; j < 8; ++j) {
                 float tn;
                 if (bvh_entry_may_hit(rb, p[2 * (g * 8 + j)], p[2 * (g * 8 + j) + 1], finf(), &tn)) mm |= (1u << j);
             }
             m |= mm << (g * 8);
         }
+        if (all) m = left >= 32u ? 0xffffffffu : (1u << left) - 1u;
         scratch[ch * stride] = m;
     }
-    // ---- A1: members of the lane's clusters;  B whenever the queue fills and at the end ----
+    // ---- A1: members of the lane's clusters into the queue;  B: exact tests whenever it fills, and at the end ----
     uint32_t nq = 0u;
     float prune = finf();
     uint32_t ch = 0u, m = scratch[0];
-    for (;;) {
-        while (m == 0u && ++ch < S.nt_chunks) m = scratch[ch * stride];
-        if (m == 0u) break;
-        const int k = ffs32(m); m &= m - 1u;
-        const uint32_t payload = f2u(S.top[2 * (ch * 32u + (uint32_t)k) + 1].z);
-        const uint32_t first = payload >> 4, count = payload & 15u;
-        RDR_STAT(stats, nodes_visited);
-        if (count == 1u) {                                       // a primitive on its own: its box was the top entry
-            scratch[(CL_QBASE + nq) * stride] = first; ++nq;
-        } else {
+    bool more = true;
+    while (more) {
+        while (more && nq <= (uint32_t)(BVH_QCAP - 8)) {
+            while (m == 0u && ++ch < S.nt_chunks) m = scratch[ch * stride];
+            if (m == 0u) { more = false; break; }
+            const int k = ffs32(m); m &= m - 1u;
+            const uint32_t payload = f2u(S.top[2 * (ch * 32u + (uint32_t)k) + 1].z);
+            const uint32_t first = payload >> 4, count = payload & 15u;
+            RDR_STAT(stats, nodes_visited);
             const f4 *mb = S.member_box + first;
-            RDR_UNROLL
+            RDR_UNROLL4
             for (uint32_t j = 0; j < 8u; ++j) {
-                if (j < count && member_may_hit(rb, mb[j], prune)) { scratch[(CL_QBASE + nq) * stride] = first + j; ++nq; RDR_STAT(stats, entries_hit); }
+                // a cluster of one (a large primitive on its own) was already tested as a top entry
+                if (j < count && (count == 1u || all || member_may_hit(rb, mb[j], prune))) {
+                    scratch[(CL_QBASE + nq) * stride] = first + j; ++nq; RDR_STAT(stats, entries_hit);
+                }
             }
         }
-        if (nq > (uint32_t)(BVH_QCAP - 8)) {
-            cluster_exact(S, rb, scratch, stride, nq, o, d, best, stats);
-            nq = 0u;
-            if (best.idx >= 0 && !isnan_(best.t)) prune = best.t;
-        }
+        best = cluster_exact(S, rb.rc, scratch, stride, nq, o, d, best, stats);
+        nq = 0u;
+        if (best.idx >= 0 && !isnan_(best.t)) prune = best.t;
     }
-    cluster_exact(S, rb, scratch, stride, nq, o, d, best, stats);
     return best;
 }
 
@@ -457,27 +452,37 @@ RDR_HD void lane_accept_hit(LaneState &st, Hit h)
     st.hit = h;
 }
 
-// runs until the lane has a ray that needs tracing (st.alive) or the pixel is finished (!st.alive)
+// Shades st.hit (the nearest hit of the lane's current ray) and runs until the lane holds a ray that needs
+// tracing (st.alive) or the pixel is finished (!st.alive).
+// A miss ends the path with the sky term; the lane then restarts from the cached primary hit BEFORE the shading
+// code, so that in the common case every lane of the warp -- continuing paths and restarted ones alike -- goes
+// through the (expensive, exact-arithmetic) shading code once per iteration, together.  Only a path that uses up
+// max_bounces needs a second pass.
 RDR_HD void lane_shade(const FrameParams &P, const SceneView &S, LaneState &st)
 {
     for (;;) {
-        bool terminated;
-        if (st.hit.idx >= 0) {
-            bool is_sphere;
-            const Material m = load_material(S, st.hit.idx, &is_sphere);
-            const f4 g = S.obj_geom[st.hit.idx];
-            const Surface sf = closest_hit(st.ro, st.rd, st.hit.t, is_sphere, mk3(g.x, g.y, g.z), g.w);
-            const Scatter sc = scatter(st.rd, sf, m, P.seed_lo, P.seed_hi, st.pixel, P.sample_begin + st.s, st.bounce);
-            st.ro = sc.origin; st.rd = sc.dir;
-            st.atten = mul3(st.atten, m.albedo);
-            st.light = add3(st.light, scale3(m.emission, m.emission_strength));
-            ++st.bounce;
-            terminated = st.bounce >= P.max_bounces;
-        } else {
+        if (st.hit.idx < 0) {
+            // miss (cpu.rs:334-338): light += sky * attenuation; the sample is complete
             st.light = add3(st.light, mul3(world_sample(P.world, st.rd), st.atten));
-            terminated = true;
+            st.acc.x = fadd(st.acc.x, st.light.x); st.acc.y = fadd(st.acc.y, st.light.y);
+            st.acc.z = fadd(st.acc.z, st.light.z); st.acc.w = fadd(st.acc.w, 1.0f);
+            if (++st.s >= P.sample_count) { st.alive = false; return; }
+            st.bounce = st.lane_zero; st.hit = st.h0;
+            st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]); st.rd = st.cam_d;
+            st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
+            if (st.hit.idx < 0) continue;              // the primary ray itself misses: every sample is the sky
         }
-        if (!terminated) return;
+        bool is_sphere;
+        const Material m = load_material(S, st.hit.idx, &is_sphere);
+        const f4 g = S.obj_geom[st.hit.idx];
+        const Surface sf = closest_hit(st.ro, st.rd, st.hit.t, is_sphere, mk3(g.x, g.y, g.z), g.w);
+        const Scatter sc = scatter(st.rd, sf, m, P.seed_lo, P.seed_hi, st.pixel, P.sample_begin + st.s, st.bounce);
+        st.ro = sc.origin; st.rd = sc.dir;
+        st.atten = mul3(st.atten, m.albedo);
+        st.light = add3(st.light, scale3(m.emission, m.emission_strength));
+        ++st.bounce;
+        if (st.bounce < P.max_bounces) return;         // the new ray needs tracing
+        // bounce budget used up (cpu.rs:256,341): the sample keeps its emission, no sky term
         st.acc.x = fadd(st.acc.x, st.light.x); st.acc.y = fadd(st.acc.y, st.light.y);
         st.acc.z = fadd(st.acc.z, st.light.z); st.acc.w = fadd(st.acc.w, 1.0f);
         if (++st.s >= P.sample_count) { st.alive = false; return; }
