@@ -166,7 +166,7 @@ struct ClusterSet {
     std::vector<std::vector<uint32_t>> clusters;      // positions into the input array
 };
 
-inline ClusterSet build_clusters(const std::vector<BvhBuildPrim> &prims)
+inline ClusterSet build_clusters(const std::vector<BvhBuildPrim> &prims, uint32_t cap = 8u)
 {
     ClusterSet out;
     const uint32_t n = (uint32_t)prims.size();
@@ -186,13 +186,13 @@ inline ClusterSet build_clusters(const std::vector<BvhBuildPrim> &prims)
     if (rest.empty()) return out;
     // recursive proportional k-way split along the largest centroid axis
     struct Job { uint32_t b, e; int k; };
-    std::vector<Job> todo{{0u, (uint32_t)rest.size(), (int)((rest.size() + 7) / 8)}};
+    std::vector<Job> todo{{0u, (uint32_t)rest.size(), (int)((rest.size() + cap - 1) / cap)}};
     while (!todo.empty()) {
         const Job j = todo.back(); todo.pop_back();
         if (j.k <= 1 || j.e - j.b <= 1) {
             // a group the proportional split left above 8 (cannot happen: k = ceil(n/8)) is still cut here
-            for (uint32_t b = j.b; b < j.e; b += 8)
-                out.clusters.emplace_back(rest.begin() + b, rest.begin() + std::min(j.e, b + 8));
+            for (uint32_t b = j.b; b < j.e; b += cap)
+                out.clusters.emplace_back(rest.begin() + b, rest.begin() + std::min(j.e, b + cap));
             continue;
         }
         float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -204,8 +204,8 @@ inline ClusterSet build_clusters(const std::vector<BvhBuildPrim> &prims)
         const int kl = j.k / 2, kr = j.k - kl;
         // left part gets kl clusters' worth of primitives, at most 8 per cluster
         uint32_t mid = j.b + (uint32_t)(((uint64_t)(j.e - j.b) * kl + j.k - 1) / j.k);
-        mid = std::min(mid, j.b + 8u * (uint32_t)kl);
-        mid = std::max(mid, j.e > 8u * (uint32_t)kr ? j.e - 8u * (uint32_t)kr : j.b);
+        mid = std::min(mid, j.b + cap * (uint32_t)kl);
+        mid = std::max(mid, j.e > cap * (uint32_t)kr ? j.e - cap * (uint32_t)kr : j.b);
         mid = std::max(j.b + 1, std::min(j.e - 1, mid));
         std::nth_element(rest.begin() + j.b, rest.begin() + mid, rest.begin() + j.e,
                          [&](uint32_t x, uint32_t y) { return prims[x].c[axis] < prims[y].c[axis]; });

@@ -61,11 +61,18 @@ __global__ void __launch_bounds__(RDR_BLOCK, 3) render_kernel(const __grid_const
             if (!st.alive) P.accum[pixel] = st.acc;      // nothing to trace (no samples or no bounces)
         }
         if (!__any_sync(0xffffffffu, st.alive)) break;
-        if (st.alive) {
-            lane_accept_hit(st, trace_any<MODE>(S, P.cull, masks, blockDim.x, st.ro, st.rd));
-            lane_shade(P, S, st);
-            if (!st.alive) P.accum[st.pixel] = st.acc;
+        // every lane passes through the same top-level statements each iteration, so the full-mask
+        // __syncwarp()s are safe; they pin the reconvergence points between the phases
+        const bool tracing = st.alive;
+        if (tracing) lane_accept_hit(st, trace_any<MODE>(S, P.cull, masks, blockDim.x, st.ro, st.rd));
+        __syncwarp();
+        if (tracing && st.hit.idx < 0) lane_miss(P, st);
+        __syncwarp();
+        bool shade = st.alive;
+        while (__any_sync(0xffffffffu, shade)) {             // one pass; a second only after a bounce-limit restart
+            if (shade) shade = !lane_shade_hit(P, S, st) && st.alive;
         }
+        if (tracing && !st.alive) P.accum[st.pixel] = st.acc;
     }
 }
 

@@ -46,6 +46,7 @@ struct SceneLayout {
     uint32_t off_sphere_cull, off_cube_cull, off_sphere_geom, off_cube_geom;
     uint32_t off_obj_geom, off_material, off_sphere_idx, off_cube_idx;
     uint32_t n_top, nt_pad, n_members;   // cluster scan: top entries (padded to 32), member slots
+    uint32_t n_direct;                   // the first n_direct (<= 32) top entries are single primitives
     uint32_t off_top, off_member_box, off_member_geom, off_member_idx;
     uint32_t blob_bytes;                 // multiple of 16
 };

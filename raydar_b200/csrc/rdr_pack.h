@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -119,7 +120,13 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
             p.c[0] = g[0]; p.c[1] = g[1]; p.c[2] = g[2]; p.index = i; p.cube = sc->kind[i] == RDR_CUBE;
             p.e = p.cube ? std::fabs(g[3]) * 0.5f + cube_pad : std::fabs(g[3]) + 2.0f * cube_pad;
         }
-        const ClusterSet cs = build_clusters(cprims);
+        const char *cap_env = getenv("RDR_CLUSTER_CAP");          // experiments only
+        ClusterSet cs = build_clusters(cprims, cap_env ? (uint32_t)std::max(2, std::min(8, atoi(cap_env))) : 8u);
+        // single-primitive entries first: the scan pushes them straight to the exact-test queue
+        std::stable_sort(cs.clusters.begin(), cs.clusters.end(),
+                         [](const std::vector<uint32_t> &x, const std::vector<uint32_t> &y) { return (x.size() == 1) > (y.size() == 1); });
+        L.n_direct = 0;
+        while (L.n_direct < cs.clusters.size() && L.n_direct < 32u && cs.clusters[L.n_direct].size() == 1) ++L.n_direct;
         L.n_top = (uint32_t)cs.clusters.size(); L.nt_pad = round_up_u32(L.n_top, 32u);
         if (L.nt_pad > 128u) { err = "too many objects for the shared-memory scan (limit 128 clusters): use RDR_ACCEL_BVH or AUTO"; return RDR_ERR_UNSUPPORTED; }
         L.n_members = 8u * L.n_top;

@@ -17,7 +17,7 @@ struct SceneView {
     uint32_t n_objects;
     const f4 *top, *member_box, *member_geom;       // cluster scan
     const uint32_t *member_idx;
-    uint32_t n_top, nt_chunks;
+    uint32_t n_top, nt_chunks, n_direct;
 };
 
 RDR_HD SceneView scene_view(const unsigned char *base, const SceneLayout &L)
@@ -39,7 +39,7 @@ RDR_HD SceneView scene_view(const unsigned char *base, const SceneLayout &L)
     s.member_box = reinterpret_cast<const f4 *>(base + L.off_member_box);
     s.member_geom = reinterpret_cast<const f4 *>(base + L.off_member_geom);
     s.member_idx = reinterpret_cast<const uint32_t *>(base + L.off_member_idx);
-    s.n_top = L.n_top; s.nt_chunks = L.nt_pad >> 5;
+    s.n_top = L.n_top; s.nt_chunks = L.nt_pad >> 5; s.n_direct = L.n_direct;
     return s;
 }
 
@@ -337,6 +337,16 @@ RDR_HD Hit trace_cluster(const SceneView &S, const CullConsts &cc, uint32_t *scr
     uint32_t nq = 0u;
     float prune = finf();
     uint32_t ch = 0u, m = scratch[0];
+    {   // single-primitive top entries (a floor cube, ...) were tested in A0: straight to the queue (at most 8 here,
+        // any further ones go through the member loop below like clusters of one)
+        uint32_t md = m & (S.n_direct >= 32u ? 0xffffffffu : (1u << S.n_direct) - 1u);
+        RDR_NOUNROLL
+        while (md != 0u && nq < 8u) {
+            const int k = ffs32(md); md &= md - 1u; m &= ~(1u << k);
+            scratch[(CL_QBASE + nq) * stride] = f2u(S.top[2 * k + 1].z) >> 4; ++nq;
+            RDR_STAT(stats, entries_hit);
+        }
+    }
     bool more = true;
     while (more) {
         while (more && nq <= (uint32_t)(BVH_QCAP - 8)) {
@@ -386,9 +396,11 @@ RDR_HD uint32_t lane_varying_zero(uint32_t *scratch)
 // Loop structure ("sample refill"): the reference nests samples > pixels > bounces.  A lane here owns a
 // pixel and alternates two phases until the pixel's samples are used up:
 //   trace       nearest hit of the lane's current ray (the first one is the pixel's primary ray);
-//   lane_shade  shade that hit; when the path ends (miss, or max_bounces traces used) finish the sample and
-//               immediately start the pixel's next one, shading its cached primary hit, until the lane holds
-//               a ray that needs tracing (or the pixel is finished).
+//   lane_miss / lane_shade_hit
+//               a miss ends the path with the sky term and the lane restarts from the cached primary hit BEFORE the
+//               shading code, so continuing paths and restarted ones go through the (expensive, exact-arithmetic)
+//               shading code once per iteration, together; a path that uses up max_bounces finishes its sample
+//               after shading and needs a second pass (rare).
 // The render kernel runs the phases in warp lock-step (one __any_sync per iteration is the reconvergence
 // point) and hands a lane whose pixel is finished the next unclaimed pixel, so every lane enters every
 // trace with a live ray and the scan -- >90 % of the instructions -- runs converged no matter how path
@@ -452,44 +464,46 @@ RDR_HD void lane_accept_hit(LaneState &st, Hit h)
     st.hit = h;
 }
 
-// Shades st.hit (the nearest hit of the lane's current ray) and runs until the lane holds a ray that needs
-// tracing (st.alive) or the pixel is finished (!st.alive).
-// A miss ends the path with the sky term; the lane then restarts from the cached primary hit BEFORE the shading
-// code, so that in the common case every lane of the warp -- continuing paths and restarted ones alike -- goes
-// through the (expensive, exact-arithmetic) shading code once per iteration, together.  Only a path that uses up
-// max_bounces needs a second pass.
-RDR_HD void lane_shade(const FrameParams &P, const SceneView &S, LaneState &st)
+// The traced ray missed (cpu.rs:334-338): light += sky * attenuation, the sample is complete, and the lane
+// restarts from the cached primary hit.  When the primary ray itself misses, every sample of the pixel is the
+// sky and the pixel is finished here.  Afterwards either !st.alive (pixel done) or st.hit.idx >= 0 (to shade).
+RDR_HD void lane_miss(const FrameParams &P, LaneState &st)
 {
     for (;;) {
-        if (st.hit.idx < 0) {
-            // miss (cpu.rs:334-338): light += sky * attenuation; the sample is complete
-            st.light = add3(st.light, mul3(world_sample(P.world, st.rd), st.atten));
-            st.acc.x = fadd(st.acc.x, st.light.x); st.acc.y = fadd(st.acc.y, st.light.y);
-            st.acc.z = fadd(st.acc.z, st.light.z); st.acc.w = fadd(st.acc.w, 1.0f);
-            if (++st.s >= P.sample_count) { st.alive = false; return; }
-            st.bounce = st.lane_zero; st.hit = st.h0;
-            st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]); st.rd = st.cam_d;
-            st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
-            if (st.hit.idx < 0) continue;              // the primary ray itself misses: every sample is the sky
-        }
-        bool is_sphere;
-        const Material m = load_material(S, st.hit.idx, &is_sphere);
-        const f4 g = S.obj_geom[st.hit.idx];
-        const Surface sf = closest_hit(st.ro, st.rd, st.hit.t, is_sphere, mk3(g.x, g.y, g.z), g.w);
-        const Scatter sc = scatter(st.rd, sf, m, P.seed_lo, P.seed_hi, st.pixel, P.sample_begin + st.s, st.bounce);
-        st.ro = sc.origin; st.rd = sc.dir;
-        st.atten = mul3(st.atten, m.albedo);
-        st.light = add3(st.light, scale3(m.emission, m.emission_strength));
-        ++st.bounce;
-        if (st.bounce < P.max_bounces) return;         // the new ray needs tracing
-        // bounce budget used up (cpu.rs:256,341): the sample keeps its emission, no sky term
+        st.light = add3(st.light, mul3(world_sample(P.world, st.rd), st.atten));
         st.acc.x = fadd(st.acc.x, st.light.x); st.acc.y = fadd(st.acc.y, st.light.y);
         st.acc.z = fadd(st.acc.z, st.light.z); st.acc.w = fadd(st.acc.w, 1.0f);
         if (++st.s >= P.sample_count) { st.alive = false; return; }
         st.bounce = st.lane_zero; st.hit = st.h0;
         st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]); st.rd = st.cam_d;
         st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
+        if (st.hit.idx >= 0) return;
     }
+}
+
+// Shades st.hit (idx >= 0): closest_hit, scatter, throughput and emission (cpu.rs:257-333).  Returns true when the
+// lane now holds a ray that needs tracing; false when the bounce budget is used up (cpu.rs:256,341: the sample keeps
+// its emission, no sky term) -- then the sample is finished and either the pixel is done (!st.alive) or the lane
+// has restarted from the primary hit, which needs shading again (rare: call once more).
+RDR_HD bool lane_shade_hit(const FrameParams &P, const SceneView &S, LaneState &st)
+{
+    bool is_sphere;
+    const Material m = load_material(S, st.hit.idx, &is_sphere);
+    const f4 g = S.obj_geom[st.hit.idx];
+    const Surface sf = closest_hit(st.ro, st.rd, st.hit.t, is_sphere, mk3(g.x, g.y, g.z), g.w);
+    const Scatter sc = scatter(st.rd, sf, m, P.seed_lo, P.seed_hi, st.pixel, P.sample_begin + st.s, st.bounce);
+    st.ro = sc.origin; st.rd = sc.dir;
+    st.atten = mul3(st.atten, m.albedo);
+    st.light = add3(st.light, scale3(m.emission, m.emission_strength));
+    ++st.bounce;
+    if (st.bounce < P.max_bounces) return true;
+    st.acc.x = fadd(st.acc.x, st.light.x); st.acc.y = fadd(st.acc.y, st.light.y);
+    st.acc.z = fadd(st.acc.z, st.light.z); st.acc.w = fadd(st.acc.w, 1.0f);
+    if (++st.s >= P.sample_count) { st.alive = false; return false; }
+    st.bounce = st.lane_zero; st.hit = st.h0;
+    st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]); st.rd = st.cam_d;
+    st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
+    return false;
 }
 
 // scalar driver of the phases for one pixel (host simulation; the kernel drives them in warp lock-step)
@@ -502,7 +516,8 @@ RDR_HD f4 render_pixel(const FrameParams &P, const SceneView &S, uint32_t *masks
     lane_start_pixel(P, pixel, acc, st);
     while (st.alive) {
         lane_accept_hit(st, trace_any<MODE>(S, P.cull, masks, stride, st.ro, st.rd, stats));
-        lane_shade(P, S, st);
+        if (st.hit.idx < 0) lane_miss(P, st);
+        while (st.alive && !lane_shade_hit(P, S, st)) {}
     }
     return st.acc;
 }
