@@ -97,11 +97,13 @@ int pack_scene(RdrRenderer *r, const RdrSceneFlat *sc, std::vector<unsigned char
     return st == RDR_OK ? RDR_OK : fail(r, st, "%s", err.c_str());
 }
 
-// kernel variant for a scan-packed blob: 0 flat scan + cull, 1 flat scan exact-everything (debug), 2 cluster scan
+// kernel variant for a scan-packed blob: 0 flat scan + cull, 1 flat scan exact-everything (debug), 2 cluster scan,
+// 3 warp-cooperative cluster scan (AUTO)
 int scan_variant(const RdrRenderer *r)
 {
     if (!r->use_cull) return 1;
-    return r->accel == RDR_ACCEL_BRUTE ? 0 : 2;
+    if (r->accel == RDR_ACCEL_BRUTE) return 0;
+    return r->accel == RDR_ACCEL_CLUSTER ? 2 : 3;
 }
 
 int ensure_device(RdrRenderer *r) { RDR_CUDA(r, cudaSetDevice(r->device)); return RDR_OK; }
@@ -436,7 +438,7 @@ int rdr_set_sample_offset(RdrRenderer *r, uint32_t first_sample)
 int rdr_set_accel(RdrRenderer *r, int accel)
 {
     if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
-    if (accel < RDR_ACCEL_AUTO || accel > RDR_ACCEL_CLUSTER) return fail(r, RDR_ERR_INVALID, "unknown accel %d", accel);
+    if (accel < RDR_ACCEL_AUTO || accel > RDR_ACCEL_COOP) return fail(r, RDR_ERR_INVALID, "unknown accel %d", accel);
     r->accel = accel;
     return RDR_OK;
 }

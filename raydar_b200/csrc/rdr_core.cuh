@@ -374,12 +374,9 @@ struct RayCull {
     bool degenerate;
 };
 
-RDR_HD RayCull make_ray_cull(v3 o, v3 d, const CullConsts &cc)
+// the sphere part of the set-up (no divisions): a, margins, and whether the ray must skip the cull
+RDR_HD void sphere_margins(v3 o, v3 d, const CullConsts &cc, RayCull &rc)
 {
-    RayCull rc;
-    rc.inv = mk3(fdiv(1.0f, d.x), fdiv(1.0f, d.y), fdiv(1.0f, d.z));
-    rc.od = mk3(fmul(o.x, rc.inv.x), fmul(o.y, rc.inv.y), fmul(o.z, rc.inv.z));
-    rc.ainv = mk3(fabs_(rc.inv.x), fabs_(rc.inv.y), fabs_(rc.inv.z));
     rc.a = fma(d.x, d.x, fma(d.y, d.y, fmul(d.z, d.z)));
     float oo = fma(o.x, o.x, fma(o.y, o.y, fmul(o.z, o.z)));
     float s_ray = fma(2.0f, oo, cc.sphere_q_max);
@@ -388,9 +385,19 @@ RDR_HD RayCull make_ray_cull(v3 o, v3 d, const CullConsts &cc)
     rc.M = fmul(rc.a, rc.Ms);
     rc.ek = fmul(1.9073486328125e-06f, fsqrt(fmul(rc.a, s_ray))); // 2^-19 sqrt(a S)
     float omax = fmax(fmax(fabs_(o.x), fabs_(o.y)), fabs_(o.z));
-    float imax = fmax(fmax(rc.ainv.x, rc.ainv.y), rc.ainv.z);
     // all comparisons written so that NaN/inf anywhere => degenerate
-    rc.degenerate = !(omax <= cc.origin_bound) || !(imax < 1e30f) || !(rc.a > 1e-30f) || !(rc.a < 1e30f) || !(s_ray < 1e30f);
+    rc.degenerate = !(omax <= cc.origin_bound) || !(rc.a > 1e-30f) || !(rc.a < 1e30f) || !(s_ray < 1e30f);
+}
+
+RDR_HD RayCull make_ray_cull(v3 o, v3 d, const CullConsts &cc)
+{
+    RayCull rc;
+    rc.inv = mk3(fdiv(1.0f, d.x), fdiv(1.0f, d.y), fdiv(1.0f, d.z));
+    rc.od = mk3(fmul(o.x, rc.inv.x), fmul(o.y, rc.inv.y), fmul(o.z, rc.inv.z));
+    rc.ainv = mk3(fabs_(rc.inv.x), fabs_(rc.inv.y), fabs_(rc.inv.z));
+    sphere_margins(o, d, cc, rc);
+    float imax = fmax(fmax(rc.ainv.x, rc.ainv.y), rc.ainv.z);
+    rc.degenerate = rc.degenerate || !(imax < 1e30f);
     return rc;
 }
 

@@ -29,7 +29,7 @@ __device__ __forceinline__ void stage_blob(unsigned char *dst, const unsigned ch
     }
 }
 
-// dynamic shared memory: [blob][mbarrier (16 B)][masks: max_chunks * blockDim words]
+// dynamic shared memory: [blob][mbarrier (16 B)][scratch] (see scratch_base in rdr_kernels.cu)
 __device__ __forceinline__ uint64_t *bar_ptr(unsigned char *smem, const SceneLayout &L)
 {
     return reinterpret_cast<uint64_t *>(smem + L.blob_bytes);
@@ -37,6 +37,173 @@ __device__ __forceinline__ uint64_t *bar_ptr(unsigned char *smem, const SceneLay
 __device__ __forceinline__ uint32_t *mask_base(unsigned char *smem, const SceneLayout &L)
 {
     return reinterpret_cast<uint32_t *>(smem + L.blob_bytes + 16u);
+}
+
+// ---- warp-cooperative cluster scan (MODE 4) ---------------------------------------------------------------------
+// Same two-level structure and the same tests as trace_cluster (rdr_trace.cuh), but the per-lane, divergent
+// stages are regrouped across the warp so that all 32 lanes stay busy whatever the rays do:
+//   A0   every lane scans the cluster boxes for ITS ray (uniform loop, broadcast loads) -> per-lane cluster mask;
+//   T    the (ray, cluster) pairs of all lanes are compacted into one task list (shuffle prefix sum over the
+//        per-lane counts); lane L then takes tasks L, L+32, ... -- usually some OTHER lane's ray, fetched with
+//        indexed shuffles -- and slab-tests the cluster's members; survivors go to a warp-wide list (shared
+//        atomics);
+//   E    the survivors are again dealt out evenly and get the exact, reference-ordered test (sphere pass, then
+//        cube pass); a hit is folded into the owning ray's winner with a 64-bit atomicMin on the key
+//        (t, original index), which is exactly the first-minimum rule of trace_ray (cpu.rs:344-352);
+//   each lane finally reads back the winner of its own ray.
+// In the per-lane version a warp waits for its busiest lane (measured: 12 of 32 lanes active in the member
+// stage, 3-12 in the exact stage); here the work of a warp is spread evenly.
+// Must be called by all 32 lanes of the warp (alive = false for lanes without a ray).
+struct CoopWarpScratch {
+    unsigned long long *best;     // [32] winner key per lane
+    uint32_t *surv;               // [COOP_SURV_CAP] (owner lane << 20) | member slot
+    uint16_t *tasks;              // [COOP_TASK_CAP] (owner lane << 8) | cluster index within the chunk
+    uint32_t *count;              // [1] survivors
+};
+constexpr uint32_t COOP_TASK_CAP = 1024u;                 // 32 lanes x 32 clusters of one chunk
+constexpr uint32_t COOP_SURV_CAP = 256u;                  // 32 tasks x 8 members per round
+constexpr uint32_t COOP_WARP_BYTES = 32u * 8u + COOP_SURV_CAP * 4u + COOP_TASK_CAP * 2u + 16u;
+
+__device__ __forceinline__ CoopWarpScratch coop_scratch(unsigned char *base, uint32_t warp)
+{
+    unsigned char *p = base + (size_t)warp * COOP_WARP_BYTES;
+    CoopWarpScratch w;
+    w.best = reinterpret_cast<unsigned long long *>(p);
+    w.surv = reinterpret_cast<uint32_t *>(p + 32u * 8u);
+    w.tasks = reinterpret_cast<uint16_t *>(p + 32u * 8u + COOP_SURV_CAP * 4u);
+    w.count = reinterpret_cast<uint32_t *>(p + 32u * 8u + COOP_SURV_CAP * 4u + COOP_TASK_CAP * 2u);
+    return w;
+}
+
+// order-preserving key of a hit: t is -0, >= +0 or NaN (cpu.rs:54-58,90-97); -0 == +0 for the comparison, NaN last
+__device__ __forceinline__ unsigned long long coop_key(float t, int idx)
+{
+    const uint32_t bits = __float_as_uint(t);
+    const uint32_t kt = isnan_(t) ? 0x7fc00000u : (bits & 0x7fffffffu);
+    const uint32_t zflag = (bits == 0x80000000u) ? 1u : 0u;
+    return ((unsigned long long)kt << 32) | ((unsigned long long)(uint32_t)idx << 1) | zflag;
+}
+
+__device__ __forceinline__ Hit trace_cluster_coop(const SceneView &S, const CullConsts &cc, CoopWarpScratch ws, bool alive, v3 o, v3 d)
+{
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const RayBvh rb = make_ray_bvh(o, d, cc);
+    // origin outside the scene bound / non-finite ray: no culling for this ray (every box test passes)
+    const bool all = rb.rc.degenerate;
+    const float rho = rb.rho;
+    ws.best[lane] = ~0ull;
+    if (lane == 0u) *ws.count = 0u;
+    __syncwarp();
+
+    for (uint32_t ch = 0; ch < S.nt_chunks; ++ch) {
+        // ---- A0: this lane's ray against the cluster boxes of the chunk ----
+        uint32_t m = 0u;
+        const uint32_t left = S.n_top - ch * 32u;
+        {
+            const f4 *p = S.top + ch * 64u;
+            const int groups = left >= 32u ? 4 : (int)((left + 7u) >> 3);
+#pragma unroll 1
+            for (int g = 0; g < groups; ++g) {
+                uint32_t mm = 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float tn;
+                    if (bvh_entry_may_hit(rb, p[2 * (g * 8 + j)], p[2 * (g * 8 + j) + 1], finf(), &tn)) mm |= (1u << j);
+                }
+                m |= mm << (g * 8);
+            }
+            if (all) m = FULL;
+            if (left < 32u) m &= (1u << left) - 1u;
+            if (!alive) m = 0u;
+        }
+        // ---- T: compact the (ray, cluster) pairs of the warp into one task list ----
+        const uint32_t cnt = __popc(m);
+        uint32_t pre = cnt;
+#pragma unroll
+        for (uint32_t off = 1u; off < 32u; off <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, pre, off);
+            if (lane >= off) pre += v;
+        }
+        const uint32_t total = __shfl_sync(FULL, pre, 31);
+        {
+            uint32_t pos = pre - cnt, mm = m;
+            while (mm != 0u) {
+                const uint32_t k = (uint32_t)__ffs((int)mm) - 1u; mm &= mm - 1u;
+                ws.tasks[pos++] = (uint16_t)((lane << 8) | k);
+            }
+        }
+        __syncwarp();
+        // ---- rounds of 32 tasks: member tests, then exact tests on the survivors of the round ----
+        for (uint32_t t0 = 0u; t0 < total; t0 += 32u) {
+            const uint32_t t = t0 + lane;
+            const bool has = t < total;
+            const uint32_t task = has ? ws.tasks[t] : (lane << 8);
+            const uint32_t owner = task >> 8;
+            // the owner's ray set-up, fetched by indexed shuffle (every lane takes part)
+            RayBvh r2;
+            r2.rc.inv = mk3(__shfl_sync(FULL, rb.rc.inv.x, owner), __shfl_sync(FULL, rb.rc.inv.y, owner), __shfl_sync(FULL, rb.rc.inv.z, owner));
+            r2.rc.od = mk3(__shfl_sync(FULL, rb.rc.od.x, owner), __shfl_sync(FULL, rb.rc.od.y, owner), __shfl_sync(FULL, rb.rc.od.z, owner));
+            r2.rc.ainv = mk3(fabs_(r2.rc.inv.x), fabs_(r2.rc.inv.y), fabs_(r2.rc.inv.z));
+            r2.rho = __shfl_sync(FULL, rho, owner);
+            const bool owner_all = __shfl_sync(FULL, (int)all, owner) != 0;
+            if (has) {
+                const uint32_t payload = __float_as_uint(S.top[2 * (ch * 32u + (task & 0xffu)) + 1].z);
+                const uint32_t first = payload >> 4, count = payload & 15u;
+                const f4 *mb = S.member_box + first;
+#pragma unroll
+                for (uint32_t j = 0; j < 8u; ++j) {
+                    // a cluster of one (a large primitive on its own) was already tested as a top entry
+                    if (j < count && (count == 1u || owner_all || member_may_hit(r2, mb[j], finf()))) {
+                        const uint32_t pos = atomicAdd(ws.count, 1u);
+                        ws.surv[pos] = (owner << 20) | (first + j);
+                    }
+                }
+            }
+            __syncwarp();
+            const uint32_t n_surv = *ws.count;
+            __syncwarp();
+            if (lane == 0u) *ws.count = 0u;
+            // ---- E: exact tests, dealt out evenly; spheres first, then cubes ----
+            for (uint32_t s0 = 0u; s0 < n_surv; s0 += 32u) {
+                const uint32_t si = s0 + lane;
+                const bool hs = si < n_surv;
+                const uint32_t e = hs ? ws.surv[si] : (lane << 20);
+                const uint32_t own = e >> 20, slot = e & 0xfffffu;
+                const v3 ro = mk3(__shfl_sync(FULL, o.x, own), __shfl_sync(FULL, o.y, own), __shfl_sync(FULL, o.z, own));
+                const v3 rd = mk3(__shfl_sync(FULL, d.x, own), __shfl_sync(FULL, d.y, own), __shfl_sync(FULL, d.z, own));
+                const bool own_all = __shfl_sync(FULL, (int)all, own) != 0;
+                const uint32_t tag = hs ? S.member_idx[slot] : 0u;
+                const f4 g = S.member_geom[hs ? slot : 0u];
+                if (hs && !(tag & 0x40000000u)) {
+                    bool go = true;
+                    if (!own_all) {                                   // cheap conservative sphere test before the exact one
+                        RayCull rc2;
+                        sphere_margins(ro, rd, cc, rc2);
+                        go = rc2.degenerate || sphere_may_hit(ro, rd, rc2, g.x, g.y, g.z, fmul(g.w, g.w));
+                    }
+                    float tt;
+                    if (go && hit_sphere_exact(ro, rd, mk3(g.x, g.y, g.z), g.w, &tt))
+                        atomicMin(&ws.best[own], coop_key(tt, (int)(tag & 0x3fffffffu)));
+                }
+                if (hs && (tag & 0x40000000u)) {
+                    float tt;
+                    if (hit_cube_exact(ro, rd, mk3(g.x, g.y, g.z), g.w, &tt))
+                        atomicMin(&ws.best[own], coop_key(tt, (int)(tag & 0x3fffffffu)));
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    const unsigned long long key = ws.best[lane];
+    Hit h; h.idx = -1; h.t = finf();
+    if (alive && key != ~0ull) {
+        const uint32_t kt = (uint32_t)(key >> 32);
+        h.idx = (int)(((uint32_t)key) >> 1);
+        h.t = __uint_as_float((kt == 0u && (key & 1ull)) ? 0x80000000u : kt);
+    }
+    return h;
 }
 
 }  // namespace rdr

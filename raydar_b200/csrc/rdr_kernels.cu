@@ -31,6 +31,21 @@ __device__ __forceinline__ uint32_t *scratch_base(unsigned char *smem, const Fra
     return P.staged ? mask_base(smem, P.lay) : reinterpret_cast<uint32_t *>(smem);
 }
 
+// nearest hit for every lane of the warp (alive = the lane has a ray).  MODE 4 regroups the work across the warp
+// and must be entered by all 32 lanes; the other searches are per-lane.
+// scratch layout: MODE 4: [one word per lane][per-warp cooperative regions], otherwise [words per lane, strided].
+template <int MODE>
+__device__ __forceinline__ Hit trace_warp(const SceneView &S, const FrameParams &P, uint32_t *scratch0, bool alive, v3 o, v3 d)
+{
+    if (MODE == 4) {
+        unsigned char *coop = reinterpret_cast<unsigned char *>(scratch0 + blockDim.x);
+        return trace_cluster_coop(S, P.cull, coop_scratch(coop, threadIdx.x >> 5), alive, o, d);
+    }
+    Hit h; h.idx = -1; h.t = finf();
+    if (alive) h = trace_any<MODE>(S, P.cull, scratch0 + threadIdx.x, blockDim.x, o, d);
+    return h;
+}
+
 // ---- the sample loop (LaneState / lane_shade / trace_brute in rdr_trace.cuh) ------------------------------
 // Persistent lanes in warp lock-step.  The grid is sized to the machine (SMs x resident CTAs), not to the
 // image.  Each iteration:
@@ -47,11 +62,11 @@ __global__ void __launch_bounds__(RDR_BLOCK, 3) render_kernel(const __grid_const
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const SceneView S = scene_view(stage_scene(smem, P), P.lay);
-    uint32_t *masks = scratch_base(smem, P) + threadIdx.x;
+    uint32_t *scratch0 = scratch_base(smem, P);
     const uint32_t n_pixels = P.cam.width * P.cam.height;
 
     LaneState st;
-    lane_init(st, masks);
+    lane_init(st, scratch0 + threadIdx.x);
     bool exhausted = false;
     for (;;) {
         while (!st.alive && !exhausted) {
@@ -64,7 +79,8 @@ __global__ void __launch_bounds__(RDR_BLOCK, 3) render_kernel(const __grid_const
         // every lane passes through the same top-level statements each iteration, so the full-mask
         // __syncwarp()s are safe; they pin the reconvergence points between the phases
         const bool tracing = st.alive;
-        if (tracing) lane_accept_hit(st, trace_any<MODE>(S, P.cull, masks, blockDim.x, st.ro, st.rd));
+        const Hit h = trace_warp<MODE>(S, P, scratch0, tracing, st.ro, st.rd);
+        if (tracing) lane_accept_hit(st, h);
         __syncwarp();
         if (tracing && st.hit.idx < 0) lane_miss(P, st);
         __syncwarp();
@@ -96,12 +112,13 @@ __global__ void __launch_bounds__(RDR_BLOCK, 2) first_hit_kernel(const __grid_co
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const SceneView S = scene_view(stage_scene(smem, P), P.lay);
-    uint32_t *masks = scratch_base(smem, P) + threadIdx.x;
+    uint32_t *scratch0 = scratch_base(smem, P);
     const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pixel >= P.cam.width * P.cam.height) return;
+    const bool valid = pixel < P.cam.width * P.cam.height;
     const v3 o = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
-    const v3 d = camera_ray_dir(P.cam, pixel % P.cam.width, pixel / P.cam.width);
-    const Hit h = trace_any<MODE>(S, P.cull, masks, blockDim.x, o, d);
+    const v3 d = valid ? camera_ray_dir(P.cam, pixel % P.cam.width, pixel / P.cam.width) : mk3(0.0f, 0.0f, 1.0f);
+    const Hit h = trace_warp<MODE>(S, P, scratch0, valid, o, d);
+    if (!valid) return;
     ids[pixel] = h.idx;
     ts[pixel] = h.idx >= 0 ? h.t : 0.0f;
 }
@@ -113,12 +130,13 @@ __global__ void __launch_bounds__(RDR_BLOCK, 2) kat_trace_kernel(const __grid_co
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const SceneView S = scene_view(stage_scene(smem, P), P.lay);
-    uint32_t *masks = scratch_base(smem, P) + threadIdx.x;
+    uint32_t *scratch0 = scratch_base(smem, P);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const v3 o = mk3(rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]);
-    const v3 d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
-    const Hit h = trace_any<MODE>(S, P.cull, masks, blockDim.x, o, d);
+    const bool valid = i < n;
+    const v3 o = valid ? mk3(rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]) : mk3(0.0f, 0.0f, 0.0f);
+    const v3 d = valid ? mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]) : mk3(0.0f, 0.0f, 1.0f);
+    const Hit h = trace_warp<MODE>(S, P, scratch0, valid, o, d);
+    if (!valid) return;
     ids[i] = h.idx;
     ts[i] = h.idx >= 0 ? h.t : 0.0f;
 }
@@ -132,7 +150,7 @@ __global__ void __launch_bounds__(RDR_BLOCK, 2) trace_path_kernel(const __grid_c
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const SceneView S = scene_view(stage_scene(smem, P), P.lay);
-    uint32_t *masks = scratch_base(smem, P) + threadIdx.x;
+    uint32_t *masks = scratch_base(smem, P) + threadIdx.x;          // (MODE 4 walks the path with its per-lane twin)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     *n_steps = trace_path_lane<MODE>(P, S, masks, blockDim.x, x, y, sample, steps, capacity, rgba);
 }
@@ -190,12 +208,18 @@ static inline uint32_t scratch_words(const SceneLayout &L)
 
 size_t scene_smem_bytes(const SceneLayout &L, bool staged, uint32_t block)
 {
-    return (staged ? (size_t)L.blob_bytes + 16u : 0u) + (size_t)scratch_words(L) * block * sizeof(uint32_t);
+    // sized for the largest user of the scratch area: per-lane words, or (cooperative scan) one word per lane plus
+    // the per-warp regions
+    const size_t per_lane = (size_t)scratch_words(L) * block * sizeof(uint32_t);
+    const size_t coop = L.mode == 0u ? (size_t)block * sizeof(uint32_t) + (size_t)((block + 31u) / 32u) * COOP_WARP_BYTES : 0u;
+    return (staged ? (size_t)L.blob_bytes + 16u : 0u) + (per_lane > coop ? per_lane : coop);
 }
 
 // kernel variant (the MODE template argument): 0 = flat scan + cull, 1 = flat scan exact-everything (debug),
-// 2 = BVH, 3 = two-level cluster scan.  A BVH-packed blob can only be traversed as a BVH.
-static inline int mode_of(const FrameParams &P, int variant) { return P.lay.mode == 1u ? 2 : (variant == 2 ? 3 : variant); }
+// 2 = BVH, 3 = two-level cluster scan (per lane), 4 = the same, warp-cooperative.
+// `variant` (from rdr_api.cpp) numbers the scans of a scan-packed blob: 0, 1, 2 = cluster, 3 = cooperative cluster.
+// A BVH-packed blob can only be traversed as a BVH.
+static inline int mode_of(const FrameParams &P, int variant) { return P.lay.mode == 1u ? 2 : (variant >= 2 ? variant + 1 : variant); }
 
 template <typename K>
 static cudaError_t set_smem(K kernel, size_t bytes)
@@ -205,7 +229,8 @@ static cudaError_t set_smem(K kernel, size_t bytes)
 
 #define RDR_DISPATCH(mode, KERNEL, ...)                                   \
     do {                                                                  \
-        if ((mode) == 3) { KERNEL(3, __VA_ARGS__); }                      \
+        if ((mode) == 4) { KERNEL(4, __VA_ARGS__); }                      \
+        else if ((mode) == 3) { KERNEL(3, __VA_ARGS__); }                 \
         else if ((mode) == 2) { KERNEL(2, __VA_ARGS__); }                 \
         else if ((mode) == 1) { KERNEL(1, __VA_ARGS__); }                 \
         else { KERNEL(0, __VA_ARGS__); }                                  \
