@@ -56,22 +56,23 @@ __device__ __forceinline__ uint32_t *mask_base(unsigned char *smem, const SceneL
 // Must be called by all 32 lanes of the warp (alive = false for lanes without a ray).
 struct CoopWarpScratch {
     unsigned long long *best;     // [32] winner key per lane
-    uint32_t *surv;               // [COOP_SURV_CAP] (owner lane << 20) | member slot
+    uint32_t *surv_s, *surv_c;    // [COOP_SURV_CAP] each: sphere / cube survivors, (owner lane << 20) | member slot
     uint16_t *tasks;              // [COOP_TASK_CAP] (owner lane << 8) | cluster index within the chunk
-    uint32_t *count;              // [1] survivors
+    uint32_t *count;              // [2] sphere, cube survivors
 };
 constexpr uint32_t COOP_TASK_CAP = 1024u;                 // 32 lanes x 32 clusters of one chunk
-constexpr uint32_t COOP_SURV_CAP = 256u;                  // 32 tasks x 8 members per round
-constexpr uint32_t COOP_WARP_BYTES = 32u * 8u + COOP_SURV_CAP * 4u + COOP_TASK_CAP * 2u + 16u;
+constexpr uint32_t COOP_SURV_CAP = 384u;                  // flushed when a list could overflow in the next round (+256)
+constexpr uint32_t COOP_WARP_BYTES = 32u * 8u + 2u * COOP_SURV_CAP * 4u + COOP_TASK_CAP * 2u + 16u;
 
 __device__ __forceinline__ CoopWarpScratch coop_scratch(unsigned char *base, uint32_t warp)
 {
     unsigned char *p = base + (size_t)warp * COOP_WARP_BYTES;
     CoopWarpScratch w;
     w.best = reinterpret_cast<unsigned long long *>(p);
-    w.surv = reinterpret_cast<uint32_t *>(p + 32u * 8u);
-    w.tasks = reinterpret_cast<uint16_t *>(p + 32u * 8u + COOP_SURV_CAP * 4u);
-    w.count = reinterpret_cast<uint32_t *>(p + 32u * 8u + COOP_SURV_CAP * 4u + COOP_TASK_CAP * 2u);
+    w.surv_s = reinterpret_cast<uint32_t *>(p + 32u * 8u);
+    w.surv_c = w.surv_s + COOP_SURV_CAP;
+    w.tasks = reinterpret_cast<uint16_t *>(p + 32u * 8u + 2u * COOP_SURV_CAP * 4u);
+    w.count = reinterpret_cast<uint32_t *>(p + 32u * 8u + 2u * COOP_SURV_CAP * 4u + COOP_TASK_CAP * 2u);
     return w;
 }
 
@@ -84,6 +85,61 @@ __device__ __forceinline__ unsigned long long coop_key(float t, int idx)
     return ((unsigned long long)kt << 32) | ((unsigned long long)(uint32_t)idx << 1) | zflag;
 }
 
+// E: exact tests on the warp's survivor lists, dealt out evenly; a hit is folded into the owner's winner key
+__device__ __forceinline__ void coop_exact(const SceneView &S, const CullConsts &cc, CoopWarpScratch ws, v3 o, v3 d, bool all)
+{
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_s = ws.count[0], n_c = ws.count[1];
+    __syncwarp();
+    if (lane == 0u) { ws.count[0] = 0u; ws.count[1] = 0u; }
+#pragma unroll 1
+    for (uint32_t s0 = 0u; s0 < n_s; s0 += 32u) {                     // spheres
+        const uint32_t si = s0 + lane;
+        const bool hs = si < n_s;
+        const uint32_t e = hs ? ws.surv_s[si] : (lane << 20);
+        const uint32_t own = e >> 20, slot = e & 0xfffffu;
+        const v3 ro = mk3(__shfl_sync(FULL, o.x, own), __shfl_sync(FULL, o.y, own), __shfl_sync(FULL, o.z, own));
+        const v3 rd = mk3(__shfl_sync(FULL, d.x, own), __shfl_sync(FULL, d.y, own), __shfl_sync(FULL, d.z, own));
+        const bool own_all = __shfl_sync(FULL, (int)all, own) != 0;
+        if (hs) {
+            const f4 g = S.member_geom[slot];
+            bool go = true;
+            if (!own_all) {                                           // cheap conservative sphere test before the exact one
+                RayCull rc2;
+                sphere_margins(ro, rd, cc, rc2);
+                go = rc2.degenerate || sphere_may_hit(ro, rd, rc2, g.x, g.y, g.z, fmul(g.w, g.w));
+            }
+            float tt;
+            if (go && hit_sphere_exact(ro, rd, mk3(g.x, g.y, g.z), g.w, &tt))
+                atomicMin(&ws.best[own], coop_key(tt, (int)(S.member_idx[slot] & 0x3fffffffu)));
+        }
+    }
+#pragma unroll 1
+    for (uint32_t s0 = 0u; s0 < n_c; s0 += 32u) {                     // cubes
+        const uint32_t si = s0 + lane;
+        const bool hs = si < n_c;
+        const uint32_t e = hs ? ws.surv_c[si] : (lane << 20);
+        const uint32_t own = e >> 20, slot = e & 0xfffffu;
+        const v3 ro = mk3(__shfl_sync(FULL, o.x, own), __shfl_sync(FULL, o.y, own), __shfl_sync(FULL, o.z, own));
+        const v3 rd = mk3(__shfl_sync(FULL, d.x, own), __shfl_sync(FULL, d.y, own), __shfl_sync(FULL, d.z, own));
+        if (hs) {
+            const f4 g = S.member_geom[slot];
+            float tt;
+            if (hit_cube_exact(ro, rd, mk3(g.x, g.y, g.z), g.w, &tt))
+                atomicMin(&ws.best[own], coop_key(tt, (int)(S.member_idx[slot] & 0x3fffffffu)));
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void coop_push(const SceneView &S, CoopWarpScratch ws, uint32_t owner, uint32_t slot)
+{
+    const bool cube = (S.member_idx[slot] & 0x40000000u) != 0u;
+    const uint32_t pos = atomicAdd(&ws.count[cube ? 1 : 0], 1u);
+    (cube ? ws.surv_c : ws.surv_s)[pos] = (owner << 20) | slot;
+}
+
 __device__ __forceinline__ Hit trace_cluster_coop(const SceneView &S, const CullConsts &cc, CoopWarpScratch ws, bool alive, v3 o, v3 d)
 {
     const uint32_t FULL = 0xffffffffu;
@@ -93,7 +149,7 @@ __device__ __forceinline__ Hit trace_cluster_coop(const SceneView &S, const Cull
     const bool all = rb.rc.degenerate;
     const float rho = rb.rho;
     ws.best[lane] = ~0ull;
-    if (lane == 0u) *ws.count = 0u;
+    if (lane == 0u) { ws.count[0] = 0u; ws.count[1] = 0u; }
     __syncwarp();
 
     for (uint32_t ch = 0; ch < S.nt_chunks; ++ch) {
@@ -117,6 +173,15 @@ __device__ __forceinline__ Hit trace_cluster_coop(const SceneView &S, const Cull
             if (left < 32u) m &= (1u << left) - 1u;
             if (!alive) m = 0u;
         }
+        // single-primitive top entries (at most 4, first chunk): their box was the entry -> straight to the survivors
+        if (ch == 0u && S.n_direct != 0u) {
+            uint32_t md = m & ((1u << S.n_direct) - 1u);
+            m &= ~((1u << S.n_direct) - 1u);
+            while (md != 0u) {
+                const uint32_t k = (uint32_t)__ffs((int)md) - 1u; md &= md - 1u;
+                coop_push(S, ws, lane, __float_as_uint(S.top[2 * k + 1].z) >> 4);
+            }
+        }
         // ---- T: compact the (ray, cluster) pairs of the warp into one task list ----
         const uint32_t cnt = __popc(m);
         uint32_t pre = cnt;
@@ -134,8 +199,11 @@ __device__ __forceinline__ Hit trace_cluster_coop(const SceneView &S, const Cull
             }
         }
         __syncwarp();
-        // ---- rounds of 32 tasks: member tests, then exact tests on the survivors of the round ----
+        // ---- rounds of 32 tasks: slab tests of the cluster members; survivors accumulate in the warp's lists ----
+#pragma unroll 1
         for (uint32_t t0 = 0u; t0 < total; t0 += 32u) {
+            // a round adds at most 256 survivors: run the exact stage first if a list could overflow
+            if (ws.count[0] > COOP_SURV_CAP - 256u || ws.count[1] > COOP_SURV_CAP - 256u) coop_exact(S, cc, ws, o, d, all);
             const uint32_t t = t0 + lane;
             const bool has = t < total;
             const uint32_t task = has ? ws.tasks[t] : (lane << 8);
@@ -153,49 +221,14 @@ __device__ __forceinline__ Hit trace_cluster_coop(const SceneView &S, const Cull
                 const f4 *mb = S.member_box + first;
 #pragma unroll
                 for (uint32_t j = 0; j < 8u; ++j) {
-                    // a cluster of one (a large primitive on its own) was already tested as a top entry
-                    if (j < count && (count == 1u || owner_all || member_may_hit(r2, mb[j], finf()))) {
-                        const uint32_t pos = atomicAdd(ws.count, 1u);
-                        ws.surv[pos] = (owner << 20) | (first + j);
-                    }
-                }
-            }
-            __syncwarp();
-            const uint32_t n_surv = *ws.count;
-            __syncwarp();
-            if (lane == 0u) *ws.count = 0u;
-            // ---- E: exact tests, dealt out evenly; spheres first, then cubes ----
-            for (uint32_t s0 = 0u; s0 < n_surv; s0 += 32u) {
-                const uint32_t si = s0 + lane;
-                const bool hs = si < n_surv;
-                const uint32_t e = hs ? ws.surv[si] : (lane << 20);
-                const uint32_t own = e >> 20, slot = e & 0xfffffu;
-                const v3 ro = mk3(__shfl_sync(FULL, o.x, own), __shfl_sync(FULL, o.y, own), __shfl_sync(FULL, o.z, own));
-                const v3 rd = mk3(__shfl_sync(FULL, d.x, own), __shfl_sync(FULL, d.y, own), __shfl_sync(FULL, d.z, own));
-                const bool own_all = __shfl_sync(FULL, (int)all, own) != 0;
-                const uint32_t tag = hs ? S.member_idx[slot] : 0u;
-                const f4 g = S.member_geom[hs ? slot : 0u];
-                if (hs && !(tag & 0x40000000u)) {
-                    bool go = true;
-                    if (!own_all) {                                   // cheap conservative sphere test before the exact one
-                        RayCull rc2;
-                        sphere_margins(ro, rd, cc, rc2);
-                        go = rc2.degenerate || sphere_may_hit(ro, rd, rc2, g.x, g.y, g.z, fmul(g.w, g.w));
-                    }
-                    float tt;
-                    if (go && hit_sphere_exact(ro, rd, mk3(g.x, g.y, g.z), g.w, &tt))
-                        atomicMin(&ws.best[own], coop_key(tt, (int)(tag & 0x3fffffffu)));
-                }
-                if (hs && (tag & 0x40000000u)) {
-                    float tt;
-                    if (hit_cube_exact(ro, rd, mk3(g.x, g.y, g.z), g.w, &tt))
-                        atomicMin(&ws.best[own], coop_key(tt, (int)(tag & 0x3fffffffu)));
+                    // a cluster of one beyond the first 4 singles was already tested as a top entry
+                    if (j < count && (count == 1u || owner_all || member_may_hit(r2, mb[j], finf()))) coop_push(S, ws, owner, first + j);
                 }
             }
             __syncwarp();
         }
     }
-    __syncwarp();
+    coop_exact(S, cc, ws, o, d, all);
     const unsigned long long key = ws.best[lane];
     Hit h; h.idx = -1; h.t = finf();
     if (alive && key != ~0ull) {

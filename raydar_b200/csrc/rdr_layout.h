@@ -19,7 +19,9 @@
 //   top          f4[2*nt_pad] top-level entries in the hierarchy-entry format of rdr_bvh.h: a cluster of <= 8
 //                             spatially close primitives (box = union) or one large primitive on its own;
 //                             payload = first member position << 4 | member count
-//   member_box   f4[8*n_clusters] (cx, cy, cz, +-(half-extent + pad)), negative = sphere (add the per-ray rho);
+//   member_box   f4[9*n_clusters] (cx, cy, cz, +-(half-extent + pad)), negative = sphere (add the per-ray rho);
+//                             8 members + 1 pad quad per cluster (144-byte stride: lanes on different clusters hit
+//                             different shared-memory banks);
 //                             unused slots (cx = cy = cz = 0, e = -0 is never used: count bounds the loop)
 //   member_geom  f4[..]       exact-test operands (c, size) in member order
 //   member_idx   u32[..]      original object index | cube bit 30
@@ -46,7 +48,7 @@ struct SceneLayout {
     uint32_t off_sphere_cull, off_cube_cull, off_sphere_geom, off_cube_geom;
     uint32_t off_obj_geom, off_material, off_sphere_idx, off_cube_idx;
     uint32_t n_top, nt_pad, n_members;   // cluster scan: top entries (padded to 32), member slots
-    uint32_t n_direct;                   // the first n_direct (<= 32) top entries are single primitives
+    uint32_t n_direct;                   // the first n_direct (<= 4) top entries are single primitives
     uint32_t off_top, off_member_box, off_member_geom, off_member_idx;
     uint32_t blob_bytes;                 // multiple of 16
 };

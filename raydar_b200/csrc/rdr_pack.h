@@ -126,10 +126,10 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
         std::stable_sort(cs.clusters.begin(), cs.clusters.end(),
                          [](const std::vector<uint32_t> &x, const std::vector<uint32_t> &y) { return (x.size() == 1) > (y.size() == 1); });
         L.n_direct = 0;
-        while (L.n_direct < cs.clusters.size() && L.n_direct < 32u && cs.clusters[L.n_direct].size() == 1) ++L.n_direct;
+        while (L.n_direct < cs.clusters.size() && L.n_direct < 4u && cs.clusters[L.n_direct].size() == 1) ++L.n_direct;
         L.n_top = (uint32_t)cs.clusters.size(); L.nt_pad = round_up_u32(L.n_top, 32u);
         if (L.nt_pad > 128u) { err = "too many objects for the shared-memory scan (limit 128 clusters): use RDR_ACCEL_BVH or AUTO"; return RDR_ERR_UNSUPPORTED; }
-        L.n_members = 8u * L.n_top;
+        L.n_members = 9u * L.n_top;           // 8 members + 1 pad quad per cluster: 144-byte stride spreads the banks
         L.off_top = off;         off += 32u * L.nt_pad;
         L.off_member_box = off;  off += 16u * L.n_members;
         L.off_member_geom = off; off += 16u * L.n_members;
@@ -162,7 +162,7 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
             for (uint32_t j = 0; j < members.size(); ++j) {
                 const BvhBuildPrim &p = cprims[members[j]];
                 const float *g = sc->geom + 4 * (size_t)p.index;
-                const uint32_t slot = 8u * k + j;
+                const uint32_t slot = 9u * k + j;
                 float *mb = quad_at(L.off_member_box, slot), *mg = quad_at(L.off_member_geom, slot);
                 mb[0] = p.c[0]; mb[1] = p.c[1]; mb[2] = p.c[2]; mb[3] = p.cube ? p.e : -p.e;
                 mg[0] = g[0]; mg[1] = g[1]; mg[2] = g[2]; mg[3] = g[3];
@@ -178,7 +178,7 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
                 e3[a] = std::nextafter(h * (1.0f + 1e-6f), INFINITY);
             }
             t[3] = e3[0]; t[4] = e3[1]; t[5] = e3[2];
-            const uint32_t payload = ((8u * k) << 4) | (uint32_t)members.size();
+            const uint32_t payload = ((9u * k) << 4) | (uint32_t)members.size();
             memcpy(&t[6], &payload, 4);
             t[7] = any_sphere ? 1.0f : 0.0f;
         }
