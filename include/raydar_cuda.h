@@ -51,8 +51,10 @@ enum { RDR_MAT_STRIDE = 11 };  /* albedo3, roughness, metallic, emission_color3,
  *            of the clusters a ray touches
  *   BVH      8-wide hierarchy (shared memory when it fits, otherwise global memory / L2)
  *   COOP     CLUSTER with the per-lane stages regrouped across the warp (ballot/shuffle work distribution)
- *   AUTO     COOP up to 1024 objects, BVH above */
-enum { RDR_ACCEL_AUTO = 0, RDR_ACCEL_BRUTE = 1, RDR_ACCEL_BVH = 2, RDR_ACCEL_CLUSTER = 3, RDR_ACCEL_COOP = 4 };
+ *   FUSED    COOP rebuilt for the sm_100a issue model: packed FFMA2 box tests, top-level boxes in the constant
+ *            bank, atomics-free survivor compaction (<= 32 top-level entries, i.e. <= 256 objects; COOP above)
+ *   AUTO     FUSED / COOP up to 1024 objects, BVH above */
+enum { RDR_ACCEL_AUTO = 0, RDR_ACCEL_BRUTE = 1, RDR_ACCEL_BVH = 2, RDR_ACCEL_CLUSTER = 3, RDR_ACCEL_COOP = 4, RDR_ACCEL_FUSED = 5 };
 
 typedef struct RdrRenderer RdrRenderer;    /* replaces CpuRenderer state, cpu.rs:111-116 */
 typedef struct RdrScene RdrScene;          /* host-side loaded scene, scene/mod.rs:13-18 */

@@ -98,12 +98,13 @@ int pack_scene(RdrRenderer *r, const RdrSceneFlat *sc, std::vector<unsigned char
 }
 
 // kernel variant for a scan-packed blob: 0 flat scan + cull, 1 flat scan exact-everything (debug), 2 cluster scan,
-// 3 warp-cooperative cluster scan (AUTO)
+// 3 warp-cooperative cluster scan, 4 fused scan (AUTO; falls back to 3 above 32 top-level entries)
 int scan_variant(const RdrRenderer *r)
 {
     if (!r->use_cull) return 1;
     if (r->accel == RDR_ACCEL_BRUTE) return 0;
-    return r->accel == RDR_ACCEL_CLUSTER ? 2 : 3;
+    if (r->accel == RDR_ACCEL_CLUSTER) return 2;
+    return r->accel == RDR_ACCEL_COOP ? 3 : 4;              // AUTO / FUSED: fused scan (<= 32 top entries), else cooperative
 }
 
 int ensure_device(RdrRenderer *r) { RDR_CUDA(r, cudaSetDevice(r->device)); return RDR_OK; }
@@ -438,7 +439,7 @@ int rdr_set_sample_offset(RdrRenderer *r, uint32_t first_sample)
 int rdr_set_accel(RdrRenderer *r, int accel)
 {
     if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
-    if (accel < RDR_ACCEL_AUTO || accel > RDR_ACCEL_COOP) return fail(r, RDR_ERR_INVALID, "unknown accel %d", accel);
+    if (accel < RDR_ACCEL_AUTO || accel > RDR_ACCEL_FUSED) return fail(r, RDR_ERR_INVALID, "unknown accel %d", accel);
     r->accel = accel;
     return RDR_OK;
 }

@@ -1,0 +1,260 @@
+// rdr_fused.cuh -- the fused two-level scan (MODE 5): the warp-cooperative cluster scan of rdr_device.cuh rebuilt
+// around what the issue-slot profile of sm_100a rewards (profiles/microbench_pipes_r01l.txt):
+//
+//   * packed FP32: the box tests run two boxes per instruction (fma.rn.f32x2 -> SASS FFMA2: two FMAs in ONE issue
+//     slot; the kernel is issue-bound, not FMA-pipe-bound).  The boxes are stored pair-wise in FFMA2 operand order;
+//     the per-ray constants enter as broadcast scalars with |x| / -|x| operand modifiers, so they cost no registers;
+//   * A0 (ray x every top-level box) reads the boxes from the kernel parameters with uniform constant-bank loads
+//     (LDCU.128 into uniform registers): no shared-memory traffic at all in the uniform stage;
+//   * no atomics and no divergent pushes on the survivor path: the member stage leaves an 8-bit mask per (ray, cluster)
+//     task, the masks are compacted into the warp's survivor lists with one packed shuffle prefix sum (sphere count in
+//     the low half, cube count in the high half), and the list lengths live in (warp-uniform) registers;
+//   * one call site for each exact stage (the loop flushes full groups of 32 and, after the last round, the rest), and
+//     no sphere pre-test in front of the exact sphere test (under SIMT it never saves the exact test, it only adds to it);
+//   * a ray that must skip the cull (origin outside the scene bound, non-finite) zeroes its slab constants: every box
+//     test then evaluates to tn = tf = 0 and passes, so no "test everything" flag travels with the tasks.
+//
+// The stages and the winner rule are those of trace_cluster / trace_cluster_coop: conservative boxes only choose which
+// primitives get the exact, reference-ordered test; the winner is the (t, original index) minimum of trace_ray
+// (cpu.rs:344-352), folded per ray with a 64-bit atomicMin on an order-preserving key.
+// Device-only; must be entered by all 32 lanes of a warp.  Needs lay.fused_ok (<= 32 top entries) and a staged blob.
+#pragma once
+
+#include "rdr_device.cuh"
+
+namespace rdr {
+
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 bc2(float a) { f32x2 r; asm("mov.b64 %0, {%1,%1};" : "=l"(r) : "f"(a)); return r; }
+__device__ __forceinline__ void un2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// per-warp scratch of the fused scan (shared memory)
+constexpr uint32_t FUSED_TASK_CAP = 32u * FUSED_MAX_TOP;      // every ray against every cluster
+constexpr uint32_t FUSED_SURV_CAP = 128u + 31u + 256u + 1u;   // direct entries + carried remainder + one round of 32 x 8
+constexpr uint32_t FUSED_WARP_BYTES = 32u * 8u + FUSED_TASK_CAP * 2u + 2u * FUSED_SURV_CAP * 2u;
+
+struct FusedWarp {
+    unsigned long long *best;     // [32] winner key per lane
+    uint16_t *tasks;              // [FUSED_TASK_CAP]  owner lane << 8 | top entry
+    uint16_t *surv_s, *surv_c;    // [FUSED_SURV_CAP]  owner lane << 11 | member slot
+};
+
+__device__ __forceinline__ FusedWarp fused_warp(unsigned char *base, uint32_t warp)
+{
+    unsigned char *p = base + (size_t)warp * FUSED_WARP_BYTES;
+    FusedWarp w;
+    w.best = reinterpret_cast<unsigned long long *>(p);
+    w.tasks = reinterpret_cast<uint16_t *>(p + 256u);
+    w.surv_s = w.tasks + FUSED_TASK_CAP;
+    w.surv_c = w.surv_s + FUSED_SURV_CAP;
+    return w;
+}
+
+// view of the staged blob for the fused scan; built from the `extern __shared__` array itself so that every access
+// compiles to LDS/STS with 32-bit addresses (the generic SceneView pointers compile to LD.E with 64-bit address maths)
+struct FusedView {
+    const f4 *pair_block, *member_geom, *obj_geom, *material;
+    const uint32_t *member_idx;
+};
+
+__device__ __forceinline__ FusedView fused_view(const unsigned char *smem, const SceneLayout &L)
+{
+    FusedView v;
+    v.pair_block = reinterpret_cast<const f4 *>(smem + L.off_pair_block);
+    v.member_geom = reinterpret_cast<const f4 *>(smem + L.off_member_geom);
+    v.member_idx = reinterpret_cast<const uint32_t *>(smem + L.off_member_idx);
+    v.obj_geom = reinterpret_cast<const f4 *>(smem + L.off_obj_geom);
+    v.material = reinterpret_cast<const f4 *>(smem + L.off_material);
+    return v;
+}
+
+// inclusive prefix sum over the warp
+__device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, uint32_t lane)
+{
+#pragma unroll
+    for (uint32_t off = 1u; off < 32u; off <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= off) v += u;
+    }
+    return v;
+}
+
+// Appends the survivors of this lane's task -- bit j of `bits` = member slot first + j * stride of ray `owner`, the low
+// `ns` bits are spheres -- to the warp's lists.  n_s / n_c: list lengths, warp-uniform.
+__device__ __forceinline__ void fused_append(FusedWarp ws, uint32_t lane, uint32_t owner, uint32_t first, uint32_t stride,
+                                             uint32_t bits, uint32_t ns, uint32_t &n_s, uint32_t &n_c)
+{
+    uint32_t sb = bits & ((1u << ns) - 1u), cb = bits ^ sb;
+    const uint32_t packed = __popc(sb) | (__popc(cb) << 16);
+    const uint32_t incl = warp_scan_incl(packed, lane);
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t excl = incl - packed;
+    uint32_t ps = n_s + (excl & 0xffffu), pc = n_c + (excl >> 16);
+    const uint32_t tag = owner << 11;
+    while (sb != 0u) {
+        const uint32_t j = (uint32_t)__ffs((int)sb) - 1u; sb &= sb - 1u;
+        ws.surv_s[ps++] = (uint16_t)(tag | (first + j * stride));
+    }
+    while (cb != 0u) {
+        const uint32_t j = (uint32_t)__ffs((int)cb) - 1u; cb &= cb - 1u;
+        ws.surv_c[pc++] = (uint16_t)(tag | (first + j * stride));
+    }
+    n_s += total & 0xffffu; n_c += total >> 16;
+    __syncwarp();
+}
+
+// exact, reference-ordered test of survivors [base, base + n) of a list (n <= 32), one per lane; the owner's ray
+// comes by indexed shuffle; a hit is folded into the owner's winner key
+template <bool SPHERE>
+__device__ __forceinline__ void fused_exact(const FusedView &V, FusedWarp ws, uint32_t lane, const uint16_t *list, uint32_t base,
+                                            uint32_t n, v3 o, v3 d)
+{
+    const uint32_t FULL = 0xffffffffu;
+    const bool has = lane < n;
+    const uint32_t e = has ? (uint32_t)list[base + lane] : (lane << 11);
+    const uint32_t own = e >> 11, slot = e & 0x7ffu;
+    const v3 ro = mk3(__shfl_sync(FULL, o.x, own), __shfl_sync(FULL, o.y, own), __shfl_sync(FULL, o.z, own));
+    const v3 rd = mk3(__shfl_sync(FULL, d.x, own), __shfl_sync(FULL, d.y, own), __shfl_sync(FULL, d.z, own));
+    if (has) {
+        const f4 g = V.member_geom[slot];
+        float tt;
+        const bool hit = SPHERE ? hit_sphere_exact(ro, rd, mk3(g.x, g.y, g.z), g.w, &tt) : hit_cube_exact(ro, rd, mk3(g.x, g.y, g.z), g.w, &tt);
+        if (hit) atomicMin(&ws.best[own], coop_key(tt, (int)(V.member_idx[slot] & 0x3fffffffu)));
+    }
+    __syncwarp();
+}
+
+// two boxes (A, B) against one ray: bit 0 / bit 1 of the result = box A / B may be hit.
+//   c*: centres, e*: half-extents (already inflated), r*: the ray's 1/d, n*: -(o/d)
+__device__ __forceinline__ uint32_t slab_pair(f32x2 cx, f32x2 cy, f32x2 cz, f32x2 ex, f32x2 ey, f32x2 ez,
+                                              float rx, float ry, float rz, float nx, float ny, float nz)
+{
+    const f32x2 tcx = fma2(cx, bc2(rx), bc2(nx)), tcy = fma2(cy, bc2(ry), bc2(ny)), tcz = fma2(cz, bc2(rz), bc2(nz));
+    float nxa, nxb, nya, nyb, nza, nzb, fxa, fxb, fya, fyb, fza, fzb;
+    un2(fma2(ex, bc2(-fabsf(rx)), tcx), nxa, nxb); un2(fma2(ey, bc2(-fabsf(ry)), tcy), nya, nyb); un2(fma2(ez, bc2(-fabsf(rz)), tcz), nza, nzb);
+    un2(fma2(ex, bc2(fabsf(rx)), tcx), fxa, fxb); un2(fma2(ey, bc2(fabsf(ry)), tcy), fya, fyb); un2(fma2(ez, bc2(fabsf(rz)), tcz), fza, fzb);
+    const float tna = fmaxf(fmaxf(nxa, nya), fmaxf(nza, 0.0f)), tfa = fminf(fminf(fxa, fya), fza);
+    const float tnb = fmaxf(fmaxf(nxb, nyb), fmaxf(nzb, 0.0f)), tfb = fminf(fminf(fxb, fyb), fzb);
+    return (tna > tfa ? 0u : 1u) | (tnb > tfb ? 0u : 2u);
+}
+
+__device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams &P, FusedWarp ws, bool alive, v3 o, v3 d)
+{
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+
+    // ---- ray set-up (make_ray_bvh, rdr_core.cuh): slab constants, per-ray sphere-box inflation rho ----
+    float rx = __frcp_rn(d.x), ry = __frcp_rn(d.y), rz = __frcp_rn(d.z);        // == 1.0f / d, correctly rounded
+    const float big = 1e30f;
+    if (!(fabsf(rx) < big)) rx = copysignf(big, d.x);                            // zero / denormal component: clamped slab
+    if (!(fabsf(ry) < big)) ry = copysignf(big, d.y);
+    if (!(fabsf(rz) < big)) rz = copysignf(big, d.z);
+    const float a = fma(d.x, d.x, fma(d.y, d.y, fmul(d.z, d.z)));
+    const float oo = fma(o.x, o.x, fma(o.y, o.y, fmul(o.z, o.z)));
+    const float s_ray = fma(2.0f, oo, P.cull.sphere_q_max);
+    const float Ms = fmul(1.9073486328125e-06f, s_ray);
+    const float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+    const bool degenerate = !(omax <= P.cull.origin_bound) || !(a > 1e-30f) || !(a < 1e30f) || !(s_ray < 1e30f) ||
+                            isnan_(d.x) || isnan_(d.y) || isnan_(d.z);
+    float rho = fadd(fsub(fsqrt(fma(P.cull.sphere_r_min, P.cull.sphere_r_min, Ms)), P.cull.sphere_r_min),
+                     fmul(1.9073486328125e-06f, fsqrt(s_ray)));
+    rho = fmul(rho, 1.0001f);
+    float nx = fneg(fmul(o.x, rx)), ny = fneg(fmul(o.y, ry)), nz = fneg(fmul(o.z, rz));
+    if (degenerate) { rx = ry = rz = 0.0f; nx = ny = nz = 0.0f; rho = 0.0f; }    // every box test passes (tn = tf = 0)
+
+    ws.best[lane] = ~0ull;
+
+    // ---- A0: this lane's ray against every top-level box, two per FFMA2, operands from the constant bank ----
+    uint32_t m = 0u;
+    {
+        const f32x2 rho2 = bc2(rho);
+#pragma unroll
+        for (uint32_t k = 0; k < FUSED_MAX_TOP / 2u; ++k) {
+            if ((k & 3u) == 0u && 2u * k >= P.lay.n_top) break;
+            const TopPair &t = P.top.pair[k];
+            const f32x2 sp = pk2(t.sphere[0], t.sphere[1]);
+            const f32x2 ex = fma2(sp, rho2, pk2(t.ex[0], t.ex[1])), ey = fma2(sp, rho2, pk2(t.ey[0], t.ey[1])), ez = fma2(sp, rho2, pk2(t.ez[0], t.ez[1]));
+            m |= slab_pair(pk2(t.cx[0], t.cx[1]), pk2(t.cy[0], t.cy[1]), pk2(t.cz[0], t.cz[1]), ex, ey, ez, rx, ry, rz, nx, ny, nz) << (2u * k);
+        }
+        if (P.lay.n_top < 32u) m &= (1u << P.lay.n_top) - 1u;
+        if (!alive) m = 0u;
+    }
+
+    uint32_t n_s = 0u, n_c = 0u;                                                 // survivor list lengths (warp-uniform)
+    // single-primitive top entries: their box was the entry -> straight to the survivor lists (member slot = 9 * entry)
+    if (P.lay.n_direct != 0u) {
+        const uint32_t dmask = (1u << P.lay.n_direct) - 1u;
+        fused_append(ws, lane, lane, 0u, 9u, m & dmask, P.lay.ns_direct, n_s, n_c);
+        m &= ~dmask;
+    }
+
+    // ---- T: compact the (ray, cluster) pairs of the warp into one task list ----
+    const uint32_t cnt = __popc(m);
+    const uint32_t pre = warp_scan_incl(cnt, lane);
+    const uint32_t total = __shfl_sync(FULL, pre, 31);
+    {
+        uint32_t pos = pre - cnt, mm = m;
+        while (mm != 0u) {
+            const uint32_t k = (uint32_t)__ffs((int)mm) - 1u; mm &= mm - 1u;
+            ws.tasks[pos++] = (uint16_t)((lane << 8) | k);
+        }
+    }
+    __syncwarp();
+
+    // ---- rounds of 32 tasks: M member boxes -> 8-bit masks -> survivor lists;  E exact tests on full groups of 32,
+    //      and on whatever is left after the last round ----
+#pragma unroll 1
+    for (uint32_t t0 = 0u;; t0 += 32u) {
+        const bool last = t0 >= total;
+        if (!last) {
+            const uint32_t t = t0 + lane;
+            const bool has = t < total;
+            const uint32_t task = has ? (uint32_t)ws.tasks[t] : (lane << 8);
+            const uint32_t owner = task >> 8;
+            const float qx = __shfl_sync(FULL, rx, owner), qy = __shfl_sync(FULL, ry, owner), qz = __shfl_sync(FULL, rz, owner);
+            const float mx = __shfl_sync(FULL, nx, owner), my = __shfl_sync(FULL, ny, owner), mz = __shfl_sync(FULL, nz, owner);
+            const f32x2 rho2 = bc2(__shfl_sync(FULL, rho, owner));
+            const f4 *blk = V.pair_block + 13u * (task & 0xffu);
+            uint32_t bits = 0u, desc = 0u;
+#pragma unroll
+            for (uint32_t p = 0; p < 4u; ++p) {
+                const f4 q0 = blk[3u * p], q1 = blk[3u * p + 1u];
+                float sa, sb;
+                if (p == 0u) { const f4 q2 = blk[2]; sa = q2.x; sb = q2.y; desc = __float_as_uint(q2.z); }
+                else { const float2 q2 = *reinterpret_cast<const float2 *>(blk + 3u * p + 2u); sa = q2.x; sb = q2.y; }
+                const f32x2 e = fma2(pk2(sa, sb), rho2, pk2(q1.z, q1.w));
+                bits |= slab_pair(pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), e, e, e, qx, qy, qz, mx, my, mz) << (2u * p);
+            }
+            bits &= (1u << (desc & 15u)) - 1u;
+            if (!has) bits = 0u;
+            fused_append(ws, lane, owner, desc >> 8, 1u, bits, (desc >> 4) & 15u, n_s, n_c);
+        }
+#pragma unroll 1
+        while (n_s >= 32u || (last && n_s != 0u)) {
+            const uint32_t n = n_s < 32u ? n_s : 32u;
+            n_s -= n;
+            fused_exact<true>(V, ws, lane, ws.surv_s, n_s, n, o, d);
+        }
+#pragma unroll 1
+        while (n_c >= 32u || (last && n_c != 0u)) {
+            const uint32_t n = n_c < 32u ? n_c : 32u;
+            n_c -= n;
+            fused_exact<false>(V, ws, lane, ws.surv_c, n_c, n, o, d);
+        }
+        if (last) break;
+    }
+    __syncwarp();
+    const unsigned long long key = ws.best[lane];
+    Hit h; h.idx = -1; h.t = finf();
+    if (alive && key != ~0ull) {
+        const uint32_t kt = (uint32_t)(key >> 32);
+        h.idx = (int)(((uint32_t)key) >> 1);
+        h.t = __uint_as_float((kt == 0u && (key & 1ull)) ? 0x80000000u : kt);
+    }
+    return h;
+}
+
+}  // namespace rdr

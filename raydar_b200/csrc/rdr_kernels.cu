@@ -11,6 +11,7 @@
 
 #include "raydar_cuda.h"
 #include "rdr_device.cuh"
+#include "rdr_fused.cuh"
 #include "rdr_launch.h"
 
 namespace rdr {
@@ -20,15 +21,19 @@ namespace rdr {
 // (BVH_QCAP words), strided by the block size so that lanes hit distinct banks.
 // A scene whose blob does not fit (FrameParams::staged == 0: large BVH scenes) is read in place from
 // global memory / L2 and only the scratch words live in shared memory.
+// MODE 5 (fused scan) always runs on a staged blob: returning `smem` itself (not a select between two pointers)
+// lets the compiler prove the address space, so every scene access becomes an LDS with a 32-bit address.
+template <int MODE>
 __device__ __forceinline__ const unsigned char *stage_scene(unsigned char *smem, const FrameParams &P)
 {
-    if (!P.staged) return P.blob;
+    if (MODE != 5 && !P.staged) return P.blob;
     stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
     return smem;
 }
+template <int MODE>
 __device__ __forceinline__ uint32_t *scratch_base(unsigned char *smem, const FrameParams &P)
 {
-    return P.staged ? mask_base(smem, P.lay) : reinterpret_cast<uint32_t *>(smem);
+    return (MODE == 5 || P.staged) ? mask_base(smem, P.lay) : reinterpret_cast<uint32_t *>(smem);
 }
 
 // nearest hit for every lane of the warp (alive = the lane has a ray).  MODE 4 regroups the work across the warp
@@ -37,6 +42,11 @@ __device__ __forceinline__ uint32_t *scratch_base(unsigned char *smem, const Fra
 template <int MODE>
 __device__ __forceinline__ Hit trace_warp(const SceneView &S, const FrameParams &P, uint32_t *scratch0, bool alive, v3 o, v3 d)
 {
+    if (MODE == 5) {
+        FusedView V;
+        V.pair_block = S.pair_block; V.member_geom = S.member_geom; V.member_idx = S.member_idx; V.obj_geom = S.obj_geom; V.material = S.material;
+        return trace_fused(V, P, fused_warp(reinterpret_cast<unsigned char *>(scratch0 + blockDim.x), threadIdx.x >> 5), alive, o, d);
+    }
     if (MODE == 4) {
         unsigned char *coop = reinterpret_cast<unsigned char *>(scratch0 + blockDim.x);
         return trace_cluster_coop(S, P.cull, coop_scratch(coop, threadIdx.x >> 5), alive, o, d);
@@ -61,8 +71,8 @@ template <int MODE>
 __global__ void __launch_bounds__(RDR_BLOCK, 3) render_kernel(const __grid_constant__ FrameParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const SceneView S = scene_view(stage_scene(smem, P), P.lay);
-    uint32_t *scratch0 = scratch_base(smem, P);
+    const SceneView S = scene_view(stage_scene<MODE>(smem, P), P.lay);
+    uint32_t *scratch0 = scratch_base<MODE>(smem, P);
     const uint32_t n_pixels = P.cam.width * P.cam.height;
 
     LaneState st;
@@ -111,8 +121,8 @@ __global__ void __launch_bounds__(RDR_BLOCK, 2) first_hit_kernel(const __grid_co
                                                                 int32_t *__restrict__ ids, float *__restrict__ ts)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const SceneView S = scene_view(stage_scene(smem, P), P.lay);
-    uint32_t *scratch0 = scratch_base(smem, P);
+    const SceneView S = scene_view(stage_scene<MODE>(smem, P), P.lay);
+    uint32_t *scratch0 = scratch_base<MODE>(smem, P);
     const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = pixel < P.cam.width * P.cam.height;
     const v3 o = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
@@ -129,8 +139,8 @@ __global__ void __launch_bounds__(RDR_BLOCK, 2) kat_trace_kernel(const __grid_co
                                                                 int32_t *__restrict__ ids, float *__restrict__ ts)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const SceneView S = scene_view(stage_scene(smem, P), P.lay);
-    uint32_t *scratch0 = scratch_base(smem, P);
+    const SceneView S = scene_view(stage_scene<MODE>(smem, P), P.lay);
+    uint32_t *scratch0 = scratch_base<MODE>(smem, P);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     const v3 o = valid ? mk3(rays[6 * i + 0], rays[6 * i + 1], rays[6 * i + 2]) : mk3(0.0f, 0.0f, 0.0f);
@@ -149,8 +159,8 @@ __global__ void __launch_bounds__(RDR_BLOCK, 2) trace_path_kernel(const __grid_c
                                                                  float *__restrict__ rgba)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const SceneView S = scene_view(stage_scene(smem, P), P.lay);
-    uint32_t *masks = scratch_base(smem, P) + threadIdx.x;          // (MODE 4 walks the path with its per-lane twin)
+    const SceneView S = scene_view(stage_scene<MODE>(smem, P), P.lay);
+    uint32_t *masks = scratch_base<MODE>(smem, P) + threadIdx.x;          // (MODE 4 walks the path with its per-lane twin)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     *n_steps = trace_path_lane<MODE>(P, S, masks, blockDim.x, x, y, sample, steps, capacity, rgba);
 }
@@ -211,15 +221,21 @@ size_t scene_smem_bytes(const SceneLayout &L, bool staged, uint32_t block)
     // sized for the largest user of the scratch area: per-lane words, or (cooperative scan) one word per lane plus
     // the per-warp regions
     const size_t per_lane = (size_t)scratch_words(L) * block * sizeof(uint32_t);
-    const size_t coop = L.mode == 0u ? (size_t)block * sizeof(uint32_t) + (size_t)((block + 31u) / 32u) * COOP_WARP_BYTES : 0u;
+    const size_t warp_bytes = COOP_WARP_BYTES > FUSED_WARP_BYTES ? COOP_WARP_BYTES : FUSED_WARP_BYTES;
+    const size_t coop = L.mode == 0u ? (size_t)block * sizeof(uint32_t) + (size_t)((block + 31u) / 32u) * warp_bytes : 0u;
     return (staged ? (size_t)L.blob_bytes + 16u : 0u) + (per_lane > coop ? per_lane : coop);
 }
 
 // kernel variant (the MODE template argument): 0 = flat scan + cull, 1 = flat scan exact-everything (debug),
 // 2 = BVH, 3 = two-level cluster scan (per lane), 4 = the same, warp-cooperative.
-// `variant` (from rdr_api.cpp) numbers the scans of a scan-packed blob: 0, 1, 2 = cluster, 3 = cooperative cluster.
-// A BVH-packed blob can only be traversed as a BVH.
-static inline int mode_of(const FrameParams &P, int variant) { return P.lay.mode == 1u ? 2 : (variant >= 2 ? variant + 1 : variant); }
+// `variant` (from rdr_api.cpp) numbers the scans of a scan-packed blob: 0, 1, 2 = cluster, 3 = cooperative cluster,
+// 4 = fused scan (needs lay.fused_ok, else the cooperative scan runs).  A BVH-packed blob can only be traversed as a BVH.
+static inline int mode_of(const FrameParams &P, int variant)
+{
+    if (P.lay.mode == 1u) return 2;
+    if (variant == 4 && !(P.lay.fused_ok && P.staged)) variant = 3;
+    return variant >= 2 ? variant + 1 : variant;
+}
 
 template <typename K>
 static cudaError_t set_smem(K kernel, size_t bytes)
@@ -229,7 +245,8 @@ static cudaError_t set_smem(K kernel, size_t bytes)
 
 #define RDR_DISPATCH(mode, KERNEL, ...)                                   \
     do {                                                                  \
-        if ((mode) == 4) { KERNEL(4, __VA_ARGS__); }                      \
+        if ((mode) == 5) { KERNEL(5, __VA_ARGS__); }                      \
+        else if ((mode) == 4) { KERNEL(4, __VA_ARGS__); }                 \
         else if ((mode) == 3) { KERNEL(3, __VA_ARGS__); }                 \
         else if ((mode) == 2) { KERNEL(2, __VA_ARGS__); }                 \
         else if ((mode) == 1) { KERNEL(1, __VA_ARGS__); }                 \

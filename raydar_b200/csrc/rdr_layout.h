@@ -25,6 +25,14 @@
 //                             unused slots (cx = cy = cz = 0, e = -0 is never used: count bounds the loop)
 //   member_geom  f4[..]       exact-test operands (c, size) in member order
 //   member_idx   u32[..]      original object index | cube bit 30
+//   (within a cluster the spheres come first; the single-primitive top entries come first, spheres first)
+//
+//   -- pair-packed copy of the same clusters for the fused scan (rdr_fused.cuh), FFMA2 operand order --
+//   pair_block   f4[13*n_top] per cluster 4 member pairs (A, B) x 3 quads + 1 pad quad (208-byte stride):
+//                             (cxA, cxB, cyA, cyB) (czA, czB, eA, eB) (sphereA, sphereB, desc*, 0)
+//                             e = half-extent + pad (>= 0), sphere = 1.0 | 0.0 (the box grows by sphere * rho);
+//                             desc (pair 0 only) = first member slot << 8 | spheres in the cluster << 4 | members
+//   The top-level boxes of the fused scan travel in the kernel parameters (FrameParams::top, constant bank).
 //
 // ns_pad / nc_pad are the list lengths rounded up to 32 (one candidate-mask word per chunk).
 // Every lane of a warp reads the same primitive at the same time, so all shared-memory reads in
@@ -50,7 +58,19 @@ struct SceneLayout {
     uint32_t n_top, nt_pad, n_members;   // cluster scan: top entries (padded to 32), member slots
     uint32_t n_direct;                   // the first n_direct (<= 4) top entries are single primitives
     uint32_t off_top, off_member_box, off_member_geom, off_member_idx;
+    uint32_t off_pair_block;             // fused scan: pair-packed member boxes (13 quads per top entry)
+    uint32_t fused_ok;                   // 1: n_top <= 32, FrameParams::top is filled and the fused scan may run
+    uint32_t ns_direct;                  // spheres among the first n_direct single-primitive entries (they come first)
     uint32_t blob_bytes;                 // multiple of 16
+};
+
+// Top-level boxes of the fused scan, two entries (A, B) per record in FFMA2 operand order.  They are read with
+// uniform constant-bank loads (LDCU.128) straight from the kernel parameters: no shared-memory traffic in the
+// uniform stage.  Unused entries have e = -1 (never hit).
+constexpr uint32_t FUSED_MAX_TOP = 32u;
+struct alignas(8) TopPair { float cx[2], cy[2], cz[2], ex[2], ey[2], ez[2], sphere[2]; };
+struct TopParams {
+    TopPair pair[FUSED_MAX_TOP / 2];
 };
 
 struct FrameParams {
@@ -66,6 +86,7 @@ struct FrameParams {
     uint32_t max_bounces;
     uint32_t sample_begin;               // global index of the first sample of this launch
     uint32_t sample_count;               // samples per pixel in this launch
+    TopParams top;                       // fused scan only (lay.fused_ok)
 };
 
 struct Hit { int idx; float t; };

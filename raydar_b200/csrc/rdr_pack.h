@@ -123,10 +123,20 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
         const char *cap_env = getenv("RDR_CLUSTER_CAP");          // experiments only
         ClusterSet cs = build_clusters(cprims, cap_env ? (uint32_t)std::max(2, std::min(8, atoi(cap_env))) : 8u);
         // single-primitive entries first: the scan pushes them straight to the exact-test queue
+        // ... spheres before cubes among them, and spheres before cubes inside every cluster (the fused scan splits
+        // a cluster's survivor bits into a sphere and a cube part with one mask)
+        for (auto &members : cs.clusters)
+            std::stable_sort(members.begin(), members.end(), [&](uint32_t x, uint32_t y) { return !cprims[x].cube && cprims[y].cube; });
         std::stable_sort(cs.clusters.begin(), cs.clusters.end(),
-                         [](const std::vector<uint32_t> &x, const std::vector<uint32_t> &y) { return (x.size() == 1) > (y.size() == 1); });
-        L.n_direct = 0;
-        while (L.n_direct < cs.clusters.size() && L.n_direct < 4u && cs.clusters[L.n_direct].size() == 1) ++L.n_direct;
+                         [&](const std::vector<uint32_t> &x, const std::vector<uint32_t> &y) {
+                             const int kx = x.size() == 1 ? (cprims[x[0]].cube ? 1 : 0) : 2, ky = y.size() == 1 ? (cprims[y[0]].cube ? 1 : 0) : 2;
+                             return kx < ky;
+                         });
+        L.n_direct = 0; L.ns_direct = 0;
+        while (L.n_direct < cs.clusters.size() && L.n_direct < 4u && cs.clusters[L.n_direct].size() == 1) {
+            if (!cprims[cs.clusters[L.n_direct][0]].cube) ++L.ns_direct;
+            ++L.n_direct;
+        }
         L.n_top = (uint32_t)cs.clusters.size(); L.nt_pad = round_up_u32(L.n_top, 32u);
         if (L.nt_pad > 128u) { err = "too many objects for the shared-memory scan (limit 128 clusters): use RDR_ACCEL_BVH or AUTO"; return RDR_ERR_UNSUPPORTED; }
         L.n_members = 9u * L.n_top;           // 8 members + 1 pad quad per cluster: 144-byte stride spreads the banks
@@ -134,6 +144,9 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
         L.off_member_box = off;  off += 16u * L.n_members;
         L.off_member_geom = off; off += 16u * L.n_members;
         L.off_member_idx = off;  off += 4u * L.n_members;
+        off = round_up_u32(off, 16u);
+        L.fused_ok = L.n_top <= FUSED_MAX_TOP ? 1u : 0u;
+        L.off_pair_block = off;  if (L.fused_ok) off += 16u * 13u * L.n_top;
         L.blob_bytes = std::max(16u, round_up_u32(off, 16u));
 
         blob.assign(L.blob_bytes, 0);
@@ -155,6 +168,8 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
             float *t = reinterpret_cast<float *>(blob.data() + L.off_top) + 8 * (size_t)k;
             t[3] = t[4] = t[5] = -1.0f;
         }
+        for (uint32_t k = 0; k < FUSED_MAX_TOP / 2u; ++k)                // unused top pairs: e = -1
+            for (int h = 0; h < 2; ++h) P.top.pair[k].ex[h] = P.top.pair[k].ey[h] = P.top.pair[k].ez[h] = -1.0f;
         for (uint32_t k = 0; k < L.n_top; ++k) {
             const std::vector<uint32_t> &members = cs.clusters[k];
             float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -181,6 +196,30 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
             const uint32_t payload = ((9u * k) << 4) | (uint32_t)members.size();
             memcpy(&t[6], &payload, 4);
             t[7] = any_sphere ? 1.0f : 0.0f;
+            if (L.fused_ok) {
+                TopPair &tp = P.top.pair[k >> 1];
+                const int h = (int)(k & 1u);
+                tp.cx[h] = t[0]; tp.cy[h] = t[1]; tp.cz[h] = t[2];
+                tp.ex[h] = e3[0]; tp.ey[h] = e3[1]; tp.ez[h] = e3[2];
+                tp.sphere[h] = t[7];
+                // pair-packed member boxes: 4 pairs x 3 quads (+ 1 pad quad) per cluster
+                float *blk = quad_at(L.off_pair_block, 13u * k);
+                uint32_t n_sph = 0;
+                for (uint32_t j = 0; j < 8u; ++j) {
+                    float *q = blk + 12u * (j >> 1);
+                    const uint32_t hh = j & 1u;
+                    if (j < members.size()) {
+                        const BvhBuildPrim &p = cprims[members[j]];
+                        q[0 + hh] = p.c[0]; q[2 + hh] = p.c[1]; q[4 + hh] = p.c[2]; q[6 + hh] = p.e;
+                        q[8 + hh] = p.cube ? 0.0f : 1.0f;
+                        if (!p.cube) ++n_sph;
+                    } else {
+                        q[6 + hh] = -1.0f;                           // unused slot (also masked out by the member count)
+                    }
+                }
+                const uint32_t desc = ((9u * k) << 8) | (n_sph << 4) | (uint32_t)members.size();
+                memcpy(&blk[10], &desc, 4);
+            }
         }
         fill_objects();
     }

@@ -18,6 +18,7 @@ struct SceneView {
     const f4 *top, *member_box, *member_geom;       // cluster scan
     const uint32_t *member_idx;
     uint32_t n_top, nt_chunks, n_direct;
+    const f4 *pair_block;                           // fused scan
 };
 
 RDR_HD SceneView scene_view(const unsigned char *base, const SceneLayout &L)
@@ -40,6 +41,7 @@ RDR_HD SceneView scene_view(const unsigned char *base, const SceneLayout &L)
     s.member_geom = reinterpret_cast<const f4 *>(base + L.off_member_geom);
     s.member_idx = reinterpret_cast<const uint32_t *>(base + L.off_member_idx);
     s.n_top = L.n_top; s.nt_chunks = L.nt_pad >> 5; s.n_direct = L.n_direct;
+    s.pair_block = reinterpret_cast<const f4 *>(base + L.off_pair_block);
     return s;
 }
 
@@ -378,7 +380,7 @@ template <int MODE>
 RDR_HD Hit trace_any(const SceneView &S, const CullConsts &cc, uint32_t *scratch, uint32_t stride, v3 o, v3 d,
                      TraceStats *stats = nullptr)
 {
-    if (MODE == 3 || MODE == 4) return trace_cluster(S, cc, scratch, stride, o, d, stats);   // 4: per-lane twin of the cooperative scan
+    if (MODE >= 3) return trace_cluster(S, cc, scratch, stride, o, d, stats);   // 4, 5: per-lane twin of the cooperative / fused scan
     if (MODE == 2) return trace_bvh(S, cc, scratch, stride, o, d, stats);
     if (MODE == 1) return trace_brute<false>(S, cc, scratch, stride, o, d, stats);
     return trace_brute<true>(S, cc, scratch, stride, o, d, stats);
