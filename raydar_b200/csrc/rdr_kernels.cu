@@ -9,6 +9,8 @@
 //   kat_* kernels      per-function known-answer entry points
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "raydar_cuda.h"
 #include "rdr_device.cuh"
 #include "rdr_fused.cuh"
@@ -67,8 +69,8 @@ __device__ __forceinline__ Hit trace_warp(const SceneView &S, const FrameParams 
 //      accumulator (one 16-byte store per pixel per launch, after one 16-byte load when it claimed it).
 // A pixel is always processed by exactly one lane with its samples in ascending order, so results do not
 // depend on the schedule (bit-identical to the per-pixel host loop).
-template <int MODE>
-__global__ void __launch_bounds__(RDR_BLOCK, 3) render_kernel(const __grid_constant__ FrameParams P)
+template <int MODE, int BLOCK, int MIN_CTAS>
+__global__ void __launch_bounds__(BLOCK, MIN_CTAS) render_kernel(const __grid_constant__ FrameParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const SceneView S = scene_view(stage_scene<MODE>(smem, P), P.lay);
@@ -216,14 +218,24 @@ static inline uint32_t scratch_words(const SceneLayout &L)
     return chunks > CL_SCRATCH ? chunks : CL_SCRATCH;       // flat-scan masks or cluster masks + queue
 }
 
+// dynamic shared memory of one CTA running kernel variant `mode` (the MODE template argument)
+static size_t mode_smem_bytes(const SceneLayout &L, bool staged, uint32_t block, int mode)
+{
+    const size_t warps = (block + 31u) / 32u;
+    size_t scratch;
+    if (mode == 5) scratch = (size_t)block * sizeof(uint32_t) + warps * FUSED_WARP_BYTES;         // one word per lane + per-warp regions
+    else if (mode == 4) scratch = (size_t)block * sizeof(uint32_t) + warps * COOP_WARP_BYTES;
+    else scratch = (size_t)scratch_words(L) * block * sizeof(uint32_t);                           // per-lane words
+    return (staged ? (size_t)L.blob_bytes + 16u : 0u) + scratch;
+}
+
+// the largest footprint any variant of this layout needs (feasibility check in rdr_api.cpp)
 size_t scene_smem_bytes(const SceneLayout &L, bool staged, uint32_t block)
 {
-    // sized for the largest user of the scratch area: per-lane words, or (cooperative scan) one word per lane plus
-    // the per-warp regions
-    const size_t per_lane = (size_t)scratch_words(L) * block * sizeof(uint32_t);
-    const size_t warp_bytes = COOP_WARP_BYTES > FUSED_WARP_BYTES ? COOP_WARP_BYTES : FUSED_WARP_BYTES;
-    const size_t coop = L.mode == 0u ? (size_t)block * sizeof(uint32_t) + (size_t)((block + 31u) / 32u) * warp_bytes : 0u;
-    return (staged ? (size_t)L.blob_bytes + 16u : 0u) + (per_lane > coop ? per_lane : coop);
+    if (L.mode == 1u) return mode_smem_bytes(L, staged, block, 2);
+    size_t m = mode_smem_bytes(L, staged, block, 0);
+    for (int mode = 3; mode <= 5; ++mode) { const size_t b = mode_smem_bytes(L, staged, block, mode); if (b > m) m = b; }
+    return m;
 }
 
 // kernel variant (the MODE template argument): 0 = flat scan + cull, 1 = flat scan exact-everything (debug),
@@ -240,7 +252,11 @@ static inline int mode_of(const FrameParams &P, int variant)
 template <typename K>
 static cudaError_t set_smem(K kernel, size_t bytes)
 {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    // the kernels keep their working set in shared memory: take the largest carve-out so that the resident CTA count is
+    // set by the footprint, not by the default L1/shared split
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 #define RDR_DISPATCH(mode, KERNEL, ...)                                   \
@@ -253,35 +269,75 @@ static cudaError_t set_smem(K kernel, size_t bytes)
         else { KERNEL(0, __VA_ARGS__); }                                  \
     } while (0)
 
+// CTA shape of the render kernel.  The scans that keep per-lane state only (MODE 0-4) run 3 CTAs of 256 threads per
+// SM (80 registers).  The fused scan (MODE 5) is latency-bound on its shuffle / shared-memory chains and wants more
+// resident warps: ONE large CTA per SM shares a single staged copy of the scene, which leaves the shared memory for
+// the warps' scratch.  Measured (profiles/sweep_r01n.txt, Msamples/s): 1 x 768 threads @ 80 registers 5276, 3 x 256 @ 80
+// 5221, 1 x 896 @ 72 5250, 1 x 1024 @ 64 4917 (spills) -> 1 x 768.  RDR_FUSED_CTA (experiments) = 0: 3 x 256,
+// 1: 1 x 896, 2: 1 x 1024, 3: 1 x 768 (default).
+static int fused_cta_config()
+{
+    static int cfg = -1;
+    if (cfg < 0) { const char *e = getenv("RDR_FUSED_CTA"); cfg = e ? atoi(e) : 3; if (cfg < 0 || cfg > 3) cfg = 3; }
+    return cfg;
+}
+static uint32_t render_block(int mode)
+{
+    if (mode != 5) return RDR_BLOCK;
+    switch (fused_cta_config()) { case 1: return 896u; case 2: return 1024u; case 3: return 768u; default: return RDR_BLOCK; }
+}
+
+// calls F(kernel) with the render kernel instantiation for `mode`
+#define RDR_RENDER_DISPATCH(mode, F)                                                                  \
+    do {                                                                                              \
+        if ((mode) == 5) {                                                                            \
+            switch (fused_cta_config()) {                                                             \
+            case 1: F((render_kernel<5, 896, 1>)); break;                                             \
+            case 2: F((render_kernel<5, 1024, 1>)); break;                                            \
+            case 3: F((render_kernel<5, 768, 1>)); break;                                             \
+            default: F((render_kernel<5, RDR_BLOCK, 3>)); break;                                      \
+            }                                                                                         \
+        }                                                                                             \
+        else if ((mode) == 4) { F((render_kernel<4, RDR_BLOCK, 3>)); }                                \
+        else if ((mode) == 3) { F((render_kernel<3, RDR_BLOCK, 3>)); }                                \
+        else if ((mode) == 2) { F((render_kernel<2, RDR_BLOCK, 3>)); }                                \
+        else if ((mode) == 1) { F((render_kernel<1, RDR_BLOCK, 3>)); }                                \
+        else { F((render_kernel<0, RDR_BLOCK, 3>)); }                                                 \
+    } while (0)
+
 cudaError_t launch_render(const FrameParams &P, int variant, int resident_ctas, cudaStream_t stream)
 {
     const uint32_t n_pixels = P.cam.width * P.cam.height;
     if (n_pixels == 0u) return cudaSuccess;
-    const size_t smem = scene_smem_bytes(P.lay, P.staged != 0u, RDR_BLOCK);
+    const int mode = mode_of(P, variant);
+    const uint32_t block = render_block(mode);
+    const size_t smem = mode_smem_bytes(P.lay, P.staged != 0u, block, mode);
     // persistent grid: every resident CTA slot of the device, but no more CTAs than there are pixels to hand out
     uint32_t grid = (uint32_t)(resident_ctas > 0 ? resident_ctas : 1);
-    const uint32_t needed = (n_pixels + RDR_BLOCK - 1u) / RDR_BLOCK;
+    const uint32_t needed = (n_pixels + block - 1u) / block;
     if (grid > needed) grid = needed;
     cudaError_t e = cudaMemsetAsync(P.pixel_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-#define RDR_K(M, ...) do { if ((e = set_smem(render_kernel<M>, smem)) != cudaSuccess) return e; render_kernel<M><<<grid, RDR_BLOCK, smem, stream>>>(P); } while (0)
-    RDR_DISPATCH(mode_of(P, variant), RDR_K, 0);
-#undef RDR_K
+#define RDR_F(K) do { if ((e = set_smem(K, smem)) != cudaSuccess) return e; K<<<grid, block, smem, stream>>>(P); } while (0)
+    RDR_RENDER_DISPATCH(mode, RDR_F);
+#undef RDR_F
     return cudaGetLastError();
 }
 
 // resident CTAs of render_kernel on the current device for this scene's shared-memory footprint
 cudaError_t render_resident_ctas(const FrameParams &P, int variant, int *out)
 {
-    const size_t smem = scene_smem_bytes(P.lay, P.staged != 0u, RDR_BLOCK);
+    const int mode = mode_of(P, variant);
+    const uint32_t block = render_block(mode);
+    const size_t smem = mode_smem_bytes(P.lay, P.staged != 0u, block, mode);
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-#define RDR_K(M, ...) do { if ((e = set_smem(render_kernel<M>, smem)) != cudaSuccess) return e; \
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<M>, RDR_BLOCK, smem); } while (0)
-    RDR_DISPATCH(mode_of(P, variant), RDR_K, 0);
-#undef RDR_K
+#define RDR_F(K) do { if ((e = set_smem(K, smem)) != cudaSuccess) return e; \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, K, (int)block, smem); } while (0)
+    RDR_RENDER_DISPATCH(mode, RDR_F);
+#undef RDR_F
     if (e != cudaSuccess) return e;
     *out = sms * (per_sm > 0 ? per_sm : 1);
     return cudaSuccess;
@@ -298,7 +354,7 @@ cudaError_t launch_first_hit(const FrameParams &P, int variant, int32_t *ids, fl
 {
     const uint32_t n_pixels = P.cam.width * P.cam.height;
     if (n_pixels == 0u) return cudaSuccess;
-    const size_t smem = scene_smem_bytes(P.lay, P.staged != 0u, RDR_BLOCK);
+    const size_t smem = mode_smem_bytes(P.lay, P.staged != 0u, RDR_BLOCK, mode_of(P, variant));
     const uint32_t grid = (n_pixels + RDR_BLOCK - 1u) / RDR_BLOCK;
     cudaError_t e;
 #define RDR_K(M, ...) do { if ((e = set_smem(first_hit_kernel<M>, smem)) != cudaSuccess) return e; first_hit_kernel<M><<<grid, RDR_BLOCK, smem, stream>>>(P, ids, ts); } while (0)
@@ -311,7 +367,7 @@ cudaError_t launch_kat_trace(const FrameParams &P, int variant, uint32_t n, cons
                              cudaStream_t stream)
 {
     if (n == 0u) return cudaSuccess;
-    const size_t smem = scene_smem_bytes(P.lay, P.staged != 0u, RDR_BLOCK);
+    const size_t smem = mode_smem_bytes(P.lay, P.staged != 0u, RDR_BLOCK, mode_of(P, variant));
     const uint32_t grid = (n + RDR_BLOCK - 1u) / RDR_BLOCK;
     cudaError_t e;
 #define RDR_K(M, ...) do { if ((e = set_smem(kat_trace_kernel<M>, smem)) != cudaSuccess) return e; kat_trace_kernel<M><<<grid, RDR_BLOCK, smem, stream>>>(P, n, rays, ids, ts); } while (0)
@@ -323,7 +379,7 @@ cudaError_t launch_kat_trace(const FrameParams &P, int variant, uint32_t n, cons
 cudaError_t launch_trace_path(const FrameParams &P, int variant, uint32_t x, uint32_t y, uint32_t sample,
                               RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float *rgba, cudaStream_t stream)
 {
-    const size_t smem = scene_smem_bytes(P.lay, P.staged != 0u, 32);
+    const size_t smem = mode_smem_bytes(P.lay, P.staged != 0u, 32, mode_of(P, variant));
     cudaError_t e;
 #define RDR_K(M, ...) do { if ((e = set_smem(trace_path_kernel<M>, smem)) != cudaSuccess) return e; trace_path_kernel<M><<<1, 32, smem, stream>>>(P, x, y, sample, steps, capacity, n_steps, rgba); } while (0)
     RDR_DISPATCH(mode_of(P, variant), RDR_K, 0);

@@ -16,6 +16,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 tail -2 $OUT/ncu_launches_$TAG.log
 echo "== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_kernel -c 1 -o $OUT/prof_$TAG -f \
-    python bench.py --steps 1 --warmup 0 --spp 16 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1
+    python bench.py --steps 1 --warmup 0 --spp 64 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1
 tail -2 $OUT/ncu_full_$TAG.log
 ls -la $OUT
