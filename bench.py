@@ -269,28 +269,36 @@ def run_b200(a):
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
                        "step": "fresh accumulator + spp samples/pixel in one kernel launch"
                                + (" + NCCL reduce to rank 0" if world > 1 else "") + " + resolve to RGBA8"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(scene_blob_bytes(rb, flat)),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(r.scene_device_bytes()),
                     "d2h_bytes_per_step": n_pixels * 4, "ms_per_step": dt_e2e / a.steps * 1e3},
             "gpu_launches": int(launches),
             "clocks": clock_info,
         }
         cpu = None
-        traces_per_sample = 3.10
+        # mean trace_ray calls per sample, counted by the oracle; re-counted below when the CPU leg runs
+        traces_per_sample = {("benchmark.rscn", 12): 3.1028}.get((os.path.basename(a.scene), a.bounces))
         if not a.no_cpu_baseline and world == 1:
             v, sample, traces_per_sample, cores, _ = cpu_run(a, a.cpu_seconds)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         n_sph = int((np.ctypeslib.as_array(flat.kind, (flat.n_objects,)) == rb.SPHERE).sum())
         n_cub = flat.n_objects - n_sph
-        f_sample = flops_per_sample(n_sph, n_cub, traces_per_sample)
-        achieved = (n_pixels * a.spp) / (kernel_ms * 1e-3) * f_sample / 1e12
+        # scenes whose trace count is unknown (no CPU leg in this run) and scenes traversed through the BVH have no
+        # brute-force-scan roofline: only the raw Msamples/s is reported for them
+        have_roofline = traces_per_sample is not None and flat.n_objects <= 1024
+        f_sample = flops_per_sample(n_sph, n_cub, traces_per_sample) if have_roofline else None
+        achieved = (n_pixels * a.spp) / (kernel_ms * 1e-3) * f_sample / 1e12 if have_roofline else None
+        traffic, traffic_src = ncu_traffic()
+        headline = os.path.basename(a.scene) == "benchmark.rscn" and a.bounces == 12
         out["roofline"] = {
-            "bound": "fp32", "kernel": "render_kernel<cull>", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-            "frac": achieved / fp32_peak, "traffic": None,
+            "bound": "fp32", "kernel": "render_kernel (fused two-level scan)" if a.accel in ("auto", "fused") else f"render_kernel ({a.accel})",
+            "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+            "frac": achieved / fp32_peak if have_roofline else None, "traffic": traffic if headline and (a.width, a.height) == (1920, 1080) else None,
+            "traffic_source": traffic_src,
             "kernel_ms": kernel_ms, "flops_per_sample": f_sample, "traces_per_sample": traces_per_sample,
             "peak_source": f"{sm_count} SMs x 128 lanes x 2 flop x sm_max_mhz from {peak_src}",
             "note": "FP32-pipe bound (no dense contraction, HBM traffic is 32 B/pixel/launch); achieved = algorithmic "
                     "flops of the reference's brute-force scan per launch / CUDA-event kernel time",
-            "hbm_algorithmic_bytes_per_launch": n_pixels * 32 + int(scene_blob_bytes(rb, flat)),
+            "hbm_algorithmic_bytes_per_launch": n_pixels * 32 + int(r.scene_device_bytes()),
         }
         if cpu:
             out["cpu_baseline"] = cpu
@@ -300,13 +308,16 @@ def run_b200(a):
     r.close()
 
 
-def scene_blob_bytes(rb, flat):
-    # bytes of the packed scene blob uploaded by rdr_new_frame: 16 B cull + 16 B exact + 4 B index per padded list slot,
-    # 16 B geometry + 48 B material per object (raydar_b200/csrc/rdr_layout.h)
-    kinds = np.ctypeslib.as_array(flat.kind, (flat.n_objects,)) if flat.n_objects else np.zeros(0, np.uint32)
-    ns = int((kinds == rb.SPHERE).sum()); nc = int(flat.n_objects - ns)
-    pad = lambda v: (v + 31) // 32 * 32
-    return 36 * (pad(ns) + pad(nc)) + 64 * flat.n_objects
+def ncu_traffic():
+    """DRAM bytes of one render-kernel launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    written by scripts/ncu_summary.py).  Per launch the kernel touches every pixel's accumulator once each way, so the
+    figure does not depend on spp."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    return d.get("dram_bytes_per_launch"), d.get("source")
 
 
 if __name__ == "__main__":

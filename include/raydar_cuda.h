@@ -147,6 +147,8 @@ int rdr_stream(RdrRenderer *r, void **cuda_stream);
 int rdr_synchronize(RdrRenderer *r);
 /* number of kernels launched by this handle so far */
 uint64_t rdr_launch_count(const RdrRenderer *r);
+/* bytes of the packed scene that rdr_new_frame uploads to the device for the current frame (0 without a frame) */
+uint64_t rdr_scene_device_bytes(const RdrRenderer *r);
 
 /* single-process multi-GPU: one sub-renderer per device, sample ranges split evenly, accumulators
  * combined with one ncclReduce(sum, f32) onto devices[0] before resolve. */

@@ -34,6 +34,7 @@ EXPORTS = [
     "rdr_profiler", "rdr_sample_count", "rdr_max_sample_count", "rdr_max_bounces", "rdr_set_max_sample_count",
     "rdr_set_max_bounces", "rdr_reset_frame", "rdr_set_seed", "rdr_set_sample_offset", "rdr_set_accel", "rdr_render_samples",
     "rdr_resolve", "rdr_read_accum", "rdr_accum_device_ptr", "rdr_stream", "rdr_synchronize", "rdr_launch_count",
+    "rdr_scene_device_bytes",
     "rdr_create_multi", "rdr_first_hit", "rdr_trace_path", "rdr_kat_hit_sphere", "rdr_kat_hit_cube",
     "rdr_kat_trace", "rdr_kat_camera_rays", "rdr_kat_rng", "rdr_scene_load_rscn", "rdr_scene_default",
     "rdr_scene_set_resolution", "rdr_scene_override_resolution", "rdr_scene_flat", "rdr_scene_free",
@@ -122,6 +123,7 @@ def load_library():
     L.rdr_stream.argtypes = [vp, C.POINTER(vp)]
     L.rdr_synchronize.argtypes = [vp]
     L.rdr_launch_count.argtypes = [vp]; L.rdr_launch_count.restype = C.c_uint64
+    L.rdr_scene_device_bytes.argtypes = [vp]; L.rdr_scene_device_bytes.restype = C.c_uint64
     L.rdr_first_hit.argtypes = [vp, i32p, fp]
     L.rdr_trace_path.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(RdrPathStep), C.c_uint32, u32p, fp]
     L.rdr_kat_hit_sphere.argtypes = [vp, C.c_uint32, fp, fp, fp, i32p]
@@ -306,6 +308,7 @@ class Renderer:
     def render_samples(self, n: int) -> None: _check(self._L.rdr_render_samples(self._h, n), self._h)
     def synchronize(self) -> None: _check(self._L.rdr_synchronize(self._h), self._h)
     def launch_count(self) -> int: return self._L.rdr_launch_count(self._h)
+    def scene_device_bytes(self) -> int: return self._L.rdr_scene_device_bytes(self._h)
 
     def resolve(self, divisor: int = 0) -> np.ndarray:
         img = np.empty((*self._shape, 4), np.uint8)

@@ -386,6 +386,12 @@ int rdr_synchronize(RdrRenderer *r)
     return RDR_OK;
 }
 
+uint64_t rdr_scene_device_bytes(const RdrRenderer *r)
+{
+    if (r && r->multi) return rdr::multi_scene_device_bytes(r->multi);
+    return (r && r->has_frame) ? (uint64_t)r->params.lay.blob_bytes : 0u;
+}
+
 uint64_t rdr_launch_count(const RdrRenderer *r) { return r ? (r->multi ? rdr::multi_launch_count(r->multi) : r->launches) : 0; }
 
 int rdr_profiler(const RdrRenderer *r, RdrProfiler *out)

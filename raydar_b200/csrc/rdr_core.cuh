@@ -309,10 +309,11 @@ RDR_HD Scatter scatter(v3 rd, const Surface &s, const Material &m,
     if (lobe == 1u) {
         dir = add3(s.n, r);
         if (dot3(dir, s.n) < 0.0f) dir = neg3(dir);
-    } else if (lobe == 2u) {
-        dir = normalize3(add3(reflect3(rd, s.n), scale3(r, roughness)));
     } else {
-        dir = normalize3(add3(refract3(rdn, s.n, ior), scale3(r, roughness)));
+        // specular and refracted lobes share normalize(base + r * roughness): one copy of that code for both
+        // (lanes of a warp that took different lobes run it together)
+        const v3 base = (lobe == 2u) ? reflect3(rd, s.n) : refract3(rdn, s.n, ior);
+        dir = normalize3(add3(base, scale3(r, roughness)));
     }
 
     Scatter out;

@@ -87,20 +87,20 @@ __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, uint32_t lane)
 __device__ __forceinline__ void fused_append(FusedWarp ws, uint32_t lane, uint32_t owner, uint32_t first, uint32_t stride,
                                              uint32_t bits, uint32_t ns, uint32_t &n_s, uint32_t &n_c)
 {
-    uint32_t sb = bits & ((1u << ns) - 1u), cb = bits ^ sb;
+    const uint32_t sb = bits & ((1u << ns) - 1u), cb = bits ^ sb;
     const uint32_t packed = __popc(sb) | (__popc(cb) << 16);
     const uint32_t incl = warp_scan_incl(packed, lane);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     const uint32_t excl = incl - packed;
     uint32_t ps = n_s + (excl & 0xffffu), pc = n_c + (excl >> 16);
     const uint32_t tag = owner << 11;
-    while (sb != 0u) {
-        const uint32_t j = (uint32_t)__ffs((int)sb) - 1u; sb &= sb - 1u;
-        ws.surv_s[ps++] = (uint16_t)(tag | (first + j * stride));
-    }
-    while (cb != 0u) {
-        const uint32_t j = (uint32_t)__ffs((int)cb) - 1u; cb &= cb - 1u;
-        ws.surv_c[pc++] = (uint16_t)(tag | (first + j * stride));
+    // one loop for both lists (surv_c = surv_s + FUSED_SURV_CAP): the low ns bits go to the sphere list
+    pc += FUSED_SURV_CAP;
+    while (bits != 0u) {
+        const uint32_t j = (uint32_t)__ffs((int)bits) - 1u; bits &= bits - 1u;
+        const bool sphere = j < ns;
+        ws.surv_s[sphere ? ps : pc] = (uint16_t)(tag | (first + j * stride));
+        ps += sphere ? 1u : 0u; pc += sphere ? 0u : 1u;
     }
     n_s += total & 0xffffu; n_c += total >> 16;
     __syncwarp();

@@ -225,6 +225,8 @@ int multi_synchronize(RdrRenderer *owner, MultiGpu *m)
     return RDR_OK;
 }
 
+uint64_t multi_scene_device_bytes(const MultiGpu *m) { return m->child.empty() ? 0u : rdr_scene_device_bytes(m->child[0]); }
+
 uint64_t multi_launch_count(const MultiGpu *m)
 {
     uint64_t n = 0;

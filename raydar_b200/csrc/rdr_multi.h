@@ -23,6 +23,7 @@ int multi_resolve(RdrRenderer *owner, MultiGpu *m, uint32_t divisor, uint8_t *rg
 int multi_read_accum(RdrRenderer *owner, MultiGpu *m, float *dst);
 int multi_synchronize(RdrRenderer *owner, MultiGpu *m);
 uint64_t multi_launch_count(const MultiGpu *m);
+uint64_t multi_scene_device_bytes(const MultiGpu *m);      // per device
 uint32_t multi_sample_count(const MultiGpu *m);
 int multi_profiler(const MultiGpu *m, RdrProfiler *out);
 void multi_set_config(MultiGpu *m, const RdrConfig &config);

@@ -21,6 +21,14 @@ want = ['gpu__time_duration.sum', 'sm__throughput.avg.pct_of_peak_sustained_elap
         'smsp__sass_thread_inst_executed_op_fadd_pred_on.sum', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum', 'smsp__inst_executed_op_shared_ld.sum']
 print("kernel:", rows[2][hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?")
+if len(sys.argv) > 3 and sys.argv[2] == "--traffic-json":
+    import json
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = sum(float(rows[2][hdr.index(k)]) * scale[rows[1][hdr.index(k)]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    with open(sys.argv[3], "w") as f:
+        json.dump({"dram_bytes_per_launch": tot, "kernel": rows[2][hdr.index("Kernel Name")],
+                   "source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch, " + rep.split("/")[-1]
+                             + " (1920x1080, 64 spp; per-launch traffic does not depend on spp)"}, f, indent=1)
 for i, h in enumerate(hdr):
     if h in want:
         print(f"{h:80s} {rows[1][i]:>12s} {rows[2][i]}")
