@@ -252,6 +252,8 @@ int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene)
         P.staged = (staged_need + 1024u) * 2u <= (size_t)smem_sm && staged_need <= (size_t)smem_optin ? 1u : 0u;
     } else {
         P.staged = 1u;
+        // the fused scan runs one large CTA per SM: when the scene plus its scratch does not fit, the cooperative scan runs
+        if (P.lay.fused_ok && rdr::fused_smem_bytes(P.lay) > (size_t)smem_optin) P.lay.fused_ok = 0u;
         if (staged_need > (size_t)smem_optin) {
             r->has_frame = false;
             return fail(r, RDR_ERR_UNSUPPORTED, "scene needs %zu B of shared memory for the brute-force scan (limit %d); use RDR_ACCEL_BVH / AUTO",

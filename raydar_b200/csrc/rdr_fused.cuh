@@ -53,23 +53,13 @@ __device__ __forceinline__ FusedWarp fused_warp(unsigned char *base, uint32_t wa
     return w;
 }
 
-// view of the staged blob for the fused scan; built from the `extern __shared__` array itself so that every access
-// compiles to LDS/STS with 32-bit addresses (the generic SceneView pointers compile to LD.E with 64-bit address maths)
+// the fused scan's sections of the staged blob.  The kernel derives the pointers from the `extern __shared__` array
+// itself (stage_scene<5> in rdr_kernels.cu), so every access compiles to LDS with a 32-bit address; a pointer that
+// might also be global compiles to LD.E with 64-bit address arithmetic.
 struct FusedView {
-    const f4 *pair_block, *member_geom, *obj_geom, *material;
+    const f4 *pair_block, *member_geom;       // member_geom / member_idx: the fused clustering's own arrays (slot = C * cluster + member)
     const uint32_t *member_idx;
 };
-
-__device__ __forceinline__ FusedView fused_view(const unsigned char *smem, const SceneLayout &L)
-{
-    FusedView v;
-    v.pair_block = reinterpret_cast<const f4 *>(smem + L.off_pair_block);
-    v.member_geom = reinterpret_cast<const f4 *>(smem + L.off_member_geom);
-    v.member_idx = reinterpret_cast<const uint32_t *>(smem + L.off_member_idx);
-    v.obj_geom = reinterpret_cast<const f4 *>(smem + L.off_obj_geom);
-    v.material = reinterpret_cast<const f4 *>(smem + L.off_material);
-    return v;
-}
 
 // inclusive prefix sum over the warp
 __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, uint32_t lane)
@@ -122,7 +112,7 @@ __device__ __forceinline__ void fused_exact(const FusedView &V, FusedWarp ws, ui
         const f4 g = V.member_geom[slot];
         float tt;
         const bool hit = SPHERE ? hit_sphere_exact(ro, rd, mk3(g.x, g.y, g.z), g.w, &tt) : hit_cube_exact(ro, rd, mk3(g.x, g.y, g.z), g.w, &tt);
-        if (hit) atomicMin(&ws.best[own], coop_key(tt, (int)(V.member_idx[slot] & 0x3fffffffu)));
+        if (hit) atomicMin(&ws.best[own], coop_key(tt, (int)V.member_idx[slot]));
     }
     __syncwarp();
 }
@@ -141,6 +131,8 @@ __device__ __forceinline__ uint32_t slab_pair(f32x2 cx, f32x2 cy, f32x2 cz, f32x
     return (tna > tfa ? 0u : 1u) | (tnb > tfb ? 0u : 2u);
 }
 
+// CAP8: the clusters have 8 member slots (scenes up to ~250 objects): one member step per round, resolved at compile time
+template <bool CAP8>
 __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams &P, FusedWarp ws, bool alive, v3 o, v3 d)
 {
     const uint32_t FULL = 0xffffffffu;
@@ -173,21 +165,21 @@ __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams
         const f32x2 rho2 = bc2(rho);
 #pragma unroll
         for (uint32_t k = 0; k < FUSED_MAX_TOP / 2u; ++k) {
-            if ((k & 3u) == 0u && 2u * k >= P.lay.n_top) break;
+            if ((k & 3u) == 0u && 2u * k >= P.lay.fused_top) break;
             const TopPair &t = P.top.pair[k];
             const f32x2 sp = pk2(t.sphere[0], t.sphere[1]);
             const f32x2 ex = fma2(sp, rho2, pk2(t.ex[0], t.ex[1])), ey = fma2(sp, rho2, pk2(t.ey[0], t.ey[1])), ez = fma2(sp, rho2, pk2(t.ez[0], t.ez[1]));
             m |= slab_pair(pk2(t.cx[0], t.cx[1]), pk2(t.cy[0], t.cy[1]), pk2(t.cz[0], t.cz[1]), ex, ey, ez, rx, ry, rz, nx, ny, nz) << (2u * k);
         }
-        if (P.lay.n_top < 32u) m &= (1u << P.lay.n_top) - 1u;
+        if (P.lay.fused_top < 32u) m &= (1u << P.lay.fused_top) - 1u;
         if (!alive) m = 0u;
     }
 
     uint32_t n_s = 0u, n_c = 0u;                                                 // survivor list lengths (warp-uniform)
-    // single-primitive top entries: their box was the entry -> straight to the survivor lists (member slot = 9 * entry)
-    if (P.lay.n_direct != 0u) {
-        const uint32_t dmask = (1u << P.lay.n_direct) - 1u;
-        fused_append(ws, lane, lane, 0u, 9u, m & dmask, P.lay.ns_direct, n_s, n_c);
+    // single-primitive top entries: their box was the entry -> straight to the survivor lists (member slot = C * entry)
+    if (P.lay.fused_direct != 0u) {
+        const uint32_t dmask = (1u << P.lay.fused_direct) - 1u;
+        fused_append(ws, lane, lane, 0u, CAP8 ? 8u : P.lay.fused_cap, m & dmask, P.lay.fused_ns_direct, n_s, n_c);
         m &= ~dmask;
     }
 
@@ -204,10 +196,12 @@ __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams
     }
     __syncwarp();
 
-    // ---- rounds of 32 tasks: M member boxes -> 8-bit masks -> survivor lists;  E exact tests on full groups of 32,
-    //      and on whatever is left after the last round ----
+    // ---- rounds of 32 tasks x groups of 8 members: M member boxes -> 8-bit masks -> survivor lists;  E exact tests on
+    //      full groups of 32 survivors, and on whatever is left after the last round ----
+    const uint32_t per_round = CAP8 ? 1u : (P.lay.fused_cap >> 3);   // 8 members (4 pairs) per step; C is a multiple of 8
+    uint32_t t0 = 0u, g = 0u;
 #pragma unroll 1
-    for (uint32_t t0 = 0u;; t0 += 32u) {
+    for (;;) {
         const bool last = t0 >= total;
         if (!last) {
             const uint32_t t = t0 + lane;
@@ -217,20 +211,27 @@ __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams
             const float qx = __shfl_sync(FULL, rx, owner), qy = __shfl_sync(FULL, ry, owner), qz = __shfl_sync(FULL, rz, owner);
             const float mx = __shfl_sync(FULL, nx, owner), my = __shfl_sync(FULL, ny, owner), mz = __shfl_sync(FULL, nz, owner);
             const f32x2 rho2 = bc2(__shfl_sync(FULL, rho, owner));
-            const f4 *blk = V.pair_block + 13u * (task & 0xffu);
+            const f4 *blk = V.pair_block + (CAP8 ? 13u : P.lay.fused_stride) * (task & 0xffu);
+            const uint32_t m0 = CAP8 ? 0u : 8u * g;               // first member of this step
+            const f4 *pb = blk + 3u * (m0 >> 1);
             uint32_t bits = 0u, desc = 0u;
+            if (!CAP8) desc = __float_as_uint(blk[2].z);
 #pragma unroll
             for (uint32_t p = 0; p < 4u; ++p) {
-                const f4 q0 = blk[3u * p], q1 = blk[3u * p + 1u];
-                float sa, sb;
-                if (p == 0u) { const f4 q2 = blk[2]; sa = q2.x; sb = q2.y; desc = __float_as_uint(q2.z); }
-                else { const float2 q2 = *reinterpret_cast<const float2 *>(blk + 3u * p + 2u); sa = q2.x; sb = q2.y; }
-                const f32x2 e = fma2(pk2(sa, sb), rho2, pk2(q1.z, q1.w));
+                const f4 q0 = pb[3u * p], q1 = pb[3u * p + 1u];
+                float2 q2;
+                if (CAP8 && p == 0u) { const f4 q = pb[2]; q2.x = q.x; q2.y = q.y; desc = __float_as_uint(q.z); }   // flags + desc in one LDS.128
+                else q2 = *reinterpret_cast<const float2 *>(pb + 3u * p + 2u);
+                const f32x2 e = fma2(pk2(q2.x, q2.y), rho2, pk2(q1.z, q1.w));
                 bits |= slab_pair(pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), e, e, e, qx, qy, qz, mx, my, mz) << (2u * p);
             }
-            bits &= (1u << (desc & 15u)) - 1u;
+            const uint32_t count = desc & 63u, n_sph = (desc >> 6) & 63u;
+            const uint32_t left = count > m0 ? count - m0 : 0u;   // members of this cluster in this step
+            bits &= left >= 8u ? 0xffu : (1u << left) - 1u;
             if (!has) bits = 0u;
-            fused_append(ws, lane, owner, desc >> 8, 1u, bits, (desc >> 4) & 15u, n_s, n_c);
+            const uint32_t ns = n_sph > m0 ? (n_sph - m0 < 8u ? n_sph - m0 : 8u) : 0u;
+            fused_append(ws, lane, owner, (desc >> 12) + m0, 1u, bits, ns, n_s, n_c);
+            if (CAP8 || ++g == per_round) { g = 0u; t0 += 32u; }
         }
 #pragma unroll 1
         while (n_s >= 32u || (last && n_s != 0u)) {

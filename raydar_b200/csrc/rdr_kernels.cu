@@ -28,14 +28,14 @@ namespace rdr {
 template <int MODE>
 __device__ __forceinline__ const unsigned char *stage_scene(unsigned char *smem, const FrameParams &P)
 {
-    if (MODE != 5 && !P.staged) return P.blob;
+    if (MODE < 5 && !P.staged) return P.blob;
     stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
     return smem;
 }
 template <int MODE>
 __device__ __forceinline__ uint32_t *scratch_base(unsigned char *smem, const FrameParams &P)
 {
-    return (MODE == 5 || P.staged) ? mask_base(smem, P.lay) : reinterpret_cast<uint32_t *>(smem);
+    return (MODE >= 5 || P.staged) ? mask_base(smem, P.lay) : reinterpret_cast<uint32_t *>(smem);
 }
 
 // nearest hit for every lane of the warp (alive = the lane has a ray).  MODE 4 regroups the work across the warp
@@ -44,10 +44,10 @@ __device__ __forceinline__ uint32_t *scratch_base(unsigned char *smem, const Fra
 template <int MODE>
 __device__ __forceinline__ Hit trace_warp(const SceneView &S, const FrameParams &P, uint32_t *scratch0, bool alive, v3 o, v3 d)
 {
-    if (MODE == 5) {
+    if (MODE == 5 || MODE == 6) {
         FusedView V;
-        V.pair_block = S.pair_block; V.member_geom = S.member_geom; V.member_idx = S.member_idx; V.obj_geom = S.obj_geom; V.material = S.material;
-        return trace_fused(V, P, fused_warp(reinterpret_cast<unsigned char *>(scratch0 + blockDim.x), threadIdx.x >> 5), alive, o, d);
+        V.pair_block = S.pair_block; V.member_geom = S.fused_geom; V.member_idx = S.fused_idx;
+        return trace_fused<MODE == 5>(V, P, fused_warp(reinterpret_cast<unsigned char *>(scratch0 + blockDim.x), threadIdx.x >> 5), alive, o, d);
     }
     if (MODE == 4) {
         unsigned char *coop = reinterpret_cast<unsigned char *>(scratch0 + blockDim.x);
@@ -223,7 +223,7 @@ static size_t mode_smem_bytes(const SceneLayout &L, bool staged, uint32_t block,
 {
     const size_t warps = (block + 31u) / 32u;
     size_t scratch;
-    if (mode == 5) scratch = (size_t)block * sizeof(uint32_t) + warps * FUSED_WARP_BYTES;         // one word per lane + per-warp regions
+    if (mode >= 5) scratch = (size_t)block * sizeof(uint32_t) + warps * FUSED_WARP_BYTES;        // one word per lane + per-warp regions
     else if (mode == 4) scratch = (size_t)block * sizeof(uint32_t) + warps * COOP_WARP_BYTES;
     else scratch = (size_t)scratch_words(L) * block * sizeof(uint32_t);                           // per-lane words
     return (staged ? (size_t)L.blob_bytes + 16u : 0u) + scratch;
@@ -234,7 +234,7 @@ size_t scene_smem_bytes(const SceneLayout &L, bool staged, uint32_t block)
 {
     if (L.mode == 1u) return mode_smem_bytes(L, staged, block, 2);
     size_t m = mode_smem_bytes(L, staged, block, 0);
-    for (int mode = 3; mode <= 5; ++mode) { const size_t b = mode_smem_bytes(L, staged, block, mode); if (b > m) m = b; }
+    for (int mode = 3; mode <= 4; ++mode) { const size_t b = mode_smem_bytes(L, staged, block, mode); if (b > m) m = b; }
     return m;
 }
 
@@ -246,6 +246,7 @@ static inline int mode_of(const FrameParams &P, int variant)
 {
     if (P.lay.mode == 1u) return 2;
     if (variant == 4 && !(P.lay.fused_ok && P.staged)) variant = 3;
+    if (variant == 4) return P.lay.fused_cap == 8u ? 5 : 6;           // fused scan: 8-member clusters resolved at compile time
     return variant >= 2 ? variant + 1 : variant;
 }
 
@@ -261,7 +262,8 @@ static cudaError_t set_smem(K kernel, size_t bytes)
 
 #define RDR_DISPATCH(mode, KERNEL, ...)                                   \
     do {                                                                  \
-        if ((mode) == 5) { KERNEL(5, __VA_ARGS__); }                      \
+        if ((mode) == 6) { KERNEL(6, __VA_ARGS__); }                      \
+        else if ((mode) == 5) { KERNEL(5, __VA_ARGS__); }                 \
         else if ((mode) == 4) { KERNEL(4, __VA_ARGS__); }                 \
         else if ((mode) == 3) { KERNEL(3, __VA_ARGS__); }                 \
         else if ((mode) == 2) { KERNEL(2, __VA_ARGS__); }                 \
@@ -283,14 +285,16 @@ static int fused_cta_config()
 }
 static uint32_t render_block(int mode)
 {
-    if (mode != 5) return RDR_BLOCK;
+    if (mode < 5) return RDR_BLOCK;
+    if (mode == 6) return 768u;
     switch (fused_cta_config()) { case 1: return 896u; case 2: return 1024u; case 3: return 768u; default: return RDR_BLOCK; }
 }
 
 // calls F(kernel) with the render kernel instantiation for `mode`
 #define RDR_RENDER_DISPATCH(mode, F)                                                                  \
     do {                                                                                              \
-        if ((mode) == 5) {                                                                            \
+        if ((mode) == 6) { F((render_kernel<6, 768, 1>)); }                                           \
+        else if ((mode) == 5) {                                                                       \
             switch (fused_cta_config()) {                                                             \
             case 1: F((render_kernel<5, 896, 1>)); break;                                             \
             case 2: F((render_kernel<5, 1024, 1>)); break;                                            \
@@ -304,6 +308,8 @@ static uint32_t render_block(int mode)
         else if ((mode) == 1) { F((render_kernel<1, RDR_BLOCK, 3>)); }                                \
         else { F((render_kernel<0, RDR_BLOCK, 3>)); }                                                 \
     } while (0)
+
+size_t fused_smem_bytes(const SceneLayout &L) { return mode_smem_bytes(L, true, render_block(5), 5); }
 
 cudaError_t launch_render(const FrameParams &P, int variant, int resident_ctas, cudaStream_t stream)
 {

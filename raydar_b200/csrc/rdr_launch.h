@@ -15,6 +15,7 @@ struct SceneLayout;
 struct f4;
 
 size_t scene_smem_bytes(const SceneLayout &L, bool staged, uint32_t block);
+size_t fused_smem_bytes(const SceneLayout &L);       // dynamic shared memory of one CTA of the fused render kernel
 cudaError_t launch_render(const FrameParams &P, int variant, int resident_ctas, cudaStream_t stream);
 cudaError_t render_resident_ctas(const FrameParams &P, int variant, int *out);
 cudaError_t launch_resolve(const f4 *accum, uchar4 *out, uint32_t n_pixels, float divisor, cudaStream_t stream);

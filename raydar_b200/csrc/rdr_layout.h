@@ -27,12 +27,17 @@
 //   member_idx   u32[..]      original object index | cube bit 30
 //   (within a cluster the spheres come first; the single-primitive top entries come first, spheres first)
 //
-//   -- pair-packed copy of the same clusters for the fused scan (rdr_fused.cuh), FFMA2 operand order --
-//   pair_block   f4[13*n_top] per cluster 4 member pairs (A, B) x 3 quads + 1 pad quad (208-byte stride):
+//   -- the fused scan (rdr_fused.cuh) has its own clustering of the same primitives: at most 32 top-level entries,
+//      so the cluster size C grows with the scene (8 up to ~250 objects, then 16, 24, 32) --
+//   pair_block   f4[stride*n_top]  per cluster C/2 member pairs (A, B) x 3 quads in FFMA2 operand order, padded to an
+//                             odd number of quads (lanes on different clusters spread over the banks):
 //                             (cxA, cxB, cyA, cyB) (czA, czB, eA, eB) (sphereA, sphereB, desc*, 0)
 //                             e = half-extent + pad (>= 0), sphere = 1.0 | 0.0 (the box grows by sphere * rho);
-//                             desc (pair 0 only) = first member slot << 8 | spheres in the cluster << 4 | members
-//   The top-level boxes of the fused scan travel in the kernel parameters (FrameParams::top, constant bank).
+//                             desc (pair 0 only) = first member slot << 12 | spheres in the cluster << 6 | members
+//   fused_geom   f4[C*n_top]  exact-test operands (c, size), slot = C * cluster + member (spheres first)
+//   fused_idx    u32[C*n_top] original object index
+//   The top-level boxes of the fused scan travel in the kernel parameters (FrameParams::top, constant bank); the
+//   leading single-primitive entries (<= 4, spheres first) skip the member stage.
 //
 // ns_pad / nc_pad are the list lengths rounded up to 32 (one candidate-mask word per chunk).
 // Every lane of a warp reads the same primitive at the same time, so all shared-memory reads in
@@ -58,9 +63,13 @@ struct SceneLayout {
     uint32_t n_top, nt_pad, n_members;   // cluster scan: top entries (padded to 32), member slots
     uint32_t n_direct;                   // the first n_direct (<= 4) top entries are single primitives
     uint32_t off_top, off_member_box, off_member_geom, off_member_idx;
-    uint32_t off_pair_block;             // fused scan: pair-packed member boxes (13 quads per top entry)
-    uint32_t fused_ok;                   // 1: n_top <= 32, FrameParams::top is filled and the fused scan may run
-    uint32_t ns_direct;                  // spheres among the first n_direct single-primitive entries (they come first)
+    // fused scan (its own clustering, see above)
+    uint32_t fused_ok;                   // 1: FrameParams::top and the sections below are filled and the fused scan may run
+    uint32_t fused_top;                  // top-level entries (<= 32)
+    uint32_t fused_cap;                  // C: member slots per cluster (8, 16, 24 or 32)
+    uint32_t fused_stride;               // quads per cluster in pair_block (3 * C/2 rounded up to odd)
+    uint32_t fused_direct, fused_ns_direct;   // leading single-primitive entries (<= 4) and the spheres among them
+    uint32_t off_pair_block, off_fused_geom, off_fused_idx;
     uint32_t blob_bytes;                 // multiple of 16
 };
 

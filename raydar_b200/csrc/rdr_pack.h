@@ -132,11 +132,8 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
                              const int kx = x.size() == 1 ? (cprims[x[0]].cube ? 1 : 0) : 2, ky = y.size() == 1 ? (cprims[y[0]].cube ? 1 : 0) : 2;
                              return kx < ky;
                          });
-        L.n_direct = 0; L.ns_direct = 0;
-        while (L.n_direct < cs.clusters.size() && L.n_direct < 4u && cs.clusters[L.n_direct].size() == 1) {
-            if (!cprims[cs.clusters[L.n_direct][0]].cube) ++L.ns_direct;
-            ++L.n_direct;
-        }
+        L.n_direct = 0;
+        while (L.n_direct < cs.clusters.size() && L.n_direct < 4u && cs.clusters[L.n_direct].size() == 1) ++L.n_direct;
         L.n_top = (uint32_t)cs.clusters.size(); L.nt_pad = round_up_u32(L.n_top, 32u);
         if (L.nt_pad > 128u) { err = "too many objects for the shared-memory scan (limit 128 clusters): use RDR_ACCEL_BVH or AUTO"; return RDR_ERR_UNSUPPORTED; }
         L.n_members = 9u * L.n_top;           // 8 members + 1 pad quad per cluster: 144-byte stride spreads the banks
@@ -145,8 +142,33 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
         L.off_member_geom = off; off += 16u * L.n_members;
         L.off_member_idx = off;  off += 4u * L.n_members;
         off = round_up_u32(off, 16u);
-        L.fused_ok = L.n_top <= FUSED_MAX_TOP ? 1u : 0u;
-        L.off_pair_block = off;  if (L.fused_ok) off += 16u * 13u * L.n_top;
+        // the fused scan's own clustering: the smallest cluster size (8, 16, 24, 32) that leaves <= 32 top entries
+        ClusterSet fs;
+        for (uint32_t cap = 8u; cap <= 32u; cap += 8u) {
+            fs = build_clusters(cprims, cap);
+            L.fused_cap = cap;
+            if (fs.clusters.size() <= FUSED_MAX_TOP) break;
+        }
+        L.fused_ok = (n > 0u && fs.clusters.size() <= FUSED_MAX_TOP) ? 1u : 0u;
+        if (L.fused_ok) {
+            for (auto &members : fs.clusters)
+                std::stable_sort(members.begin(), members.end(), [&](uint32_t x, uint32_t y) { return !cprims[x].cube && cprims[y].cube; });
+            std::stable_sort(fs.clusters.begin(), fs.clusters.end(),
+                             [&](const std::vector<uint32_t> &x, const std::vector<uint32_t> &y) {
+                                 const int kx = x.size() == 1 ? (cprims[x[0]].cube ? 1 : 0) : 2, ky = y.size() == 1 ? (cprims[y[0]].cube ? 1 : 0) : 2;
+                                 return kx < ky;
+                             });
+            L.fused_top = (uint32_t)fs.clusters.size();
+            while (L.fused_direct < L.fused_top && L.fused_direct < 4u && fs.clusters[L.fused_direct].size() == 1) {
+                if (!cprims[fs.clusters[L.fused_direct][0]].cube) ++L.fused_ns_direct;
+                ++L.fused_direct;
+            }
+            L.fused_stride = 3u * (L.fused_cap / 2u);
+            if ((L.fused_stride & 1u) == 0u) ++L.fused_stride;
+            L.off_pair_block = off; off += 16u * L.fused_stride * L.fused_top;
+            L.off_fused_geom = off; off += 16u * L.fused_cap * L.fused_top;
+            L.off_fused_idx = off;  off += 4u * L.fused_cap * L.fused_top;
+        }
         L.blob_bytes = std::max(16u, round_up_u32(off, 16u));
 
         blob.assign(L.blob_bytes, 0);
@@ -196,30 +218,41 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
             const uint32_t payload = ((9u * k) << 4) | (uint32_t)members.size();
             memcpy(&t[6], &payload, 4);
             t[7] = any_sphere ? 1.0f : 0.0f;
-            if (L.fused_ok) {
-                TopPair &tp = P.top.pair[k >> 1];
-                const int h = (int)(k & 1u);
-                tp.cx[h] = t[0]; tp.cy[h] = t[1]; tp.cz[h] = t[2];
-                tp.ex[h] = e3[0]; tp.ey[h] = e3[1]; tp.ez[h] = e3[2];
-                tp.sphere[h] = t[7];
-                // pair-packed member boxes: 4 pairs x 3 quads (+ 1 pad quad) per cluster
-                float *blk = quad_at(L.off_pair_block, 13u * k);
-                uint32_t n_sph = 0;
-                for (uint32_t j = 0; j < 8u; ++j) {
-                    float *q = blk + 12u * (j >> 1);
-                    const uint32_t hh = j & 1u;
-                    if (j < members.size()) {
-                        const BvhBuildPrim &p = cprims[members[j]];
-                        q[0 + hh] = p.c[0]; q[2 + hh] = p.c[1]; q[4 + hh] = p.c[2]; q[6 + hh] = p.e;
-                        q[8 + hh] = p.cube ? 0.0f : 1.0f;
-                        if (!p.cube) ++n_sph;
-                    } else {
-                        q[6 + hh] = -1.0f;                           // unused slot (also masked out by the member count)
-                    }
-                }
-                const uint32_t desc = ((9u * k) << 8) | (n_sph << 4) | (uint32_t)members.size();
-                memcpy(&blk[10], &desc, 4);
+        }
+        for (uint32_t k = 0; L.fused_ok && k < L.fused_top; ++k) {
+            const std::vector<uint32_t> &members = fs.clusters[k];
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            bool any_sphere = false;
+            uint32_t n_sph = 0;
+            float *blk = quad_at(L.off_pair_block, L.fused_stride * k);
+            for (uint32_t j = 0; j < L.fused_cap; ++j) {
+                float *q = blk + 12u * (j >> 1);
+                const uint32_t hh = j & 1u;
+                if (j >= members.size()) { q[6 + hh] = -1.0f; continue; }      // unused slot (also masked out by the member count)
+                const BvhBuildPrim &p = cprims[members[j]];
+                const float *g = sc->geom + 4 * (size_t)p.index;
+                q[0 + hh] = p.c[0]; q[2 + hh] = p.c[1]; q[4 + hh] = p.c[2]; q[6 + hh] = p.e;
+                q[8 + hh] = p.cube ? 0.0f : 1.0f;
+                float *fg = quad_at(L.off_fused_geom, L.fused_cap * k + j);
+                fg[0] = g[0]; fg[1] = g[1]; fg[2] = g[2]; fg[3] = g[3];
+                reinterpret_cast<uint32_t *>(blob.data() + L.off_fused_idx)[L.fused_cap * k + j] = p.index;
+                for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p.c[a] - p.e); hi[a] = std::max(hi[a], p.c[a] + p.e); }
+                any_sphere |= !p.cube;
+                if (!p.cube) ++n_sph;
             }
+            const uint32_t desc = ((L.fused_cap * k) << 12) | (n_sph << 6) | (uint32_t)members.size();
+            memcpy(&blk[10], &desc, 4);
+            TopPair &tp = P.top.pair[k >> 1];
+            const int h = (int)(k & 1u);
+            float c3[3], e3[3];
+            for (int a = 0; a < 3; ++a) {
+                c3[a] = 0.5f * (lo[a] + hi[a]);
+                const float hx = std::max(hi[a] - c3[a], c3[a] - lo[a]);
+                e3[a] = std::nextafter(hx * (1.0f + 1e-6f), INFINITY);
+            }
+            tp.cx[h] = c3[0]; tp.cy[h] = c3[1]; tp.cz[h] = c3[2];
+            tp.ex[h] = e3[0]; tp.ey[h] = e3[1]; tp.ez[h] = e3[2];
+            tp.sphere[h] = any_sphere ? 1.0f : 0.0f;
         }
         fill_objects();
     }

@@ -18,7 +18,8 @@ struct SceneView {
     const f4 *top, *member_box, *member_geom;       // cluster scan
     const uint32_t *member_idx;
     uint32_t n_top, nt_chunks, n_direct;
-    const f4 *pair_block;                           // fused scan
+    const f4 *pair_block, *fused_geom;              // fused scan
+    const uint32_t *fused_idx;
 };
 
 RDR_HD SceneView scene_view(const unsigned char *base, const SceneLayout &L)
@@ -42,6 +43,8 @@ RDR_HD SceneView scene_view(const unsigned char *base, const SceneLayout &L)
     s.member_idx = reinterpret_cast<const uint32_t *>(base + L.off_member_idx);
     s.n_top = L.n_top; s.nt_chunks = L.nt_pad >> 5; s.n_direct = L.n_direct;
     s.pair_block = reinterpret_cast<const f4 *>(base + L.off_pair_block);
+    s.fused_geom = reinterpret_cast<const f4 *>(base + L.off_fused_geom);
+    s.fused_idx = reinterpret_cast<const uint32_t *>(base + L.off_fused_idx);
     return s;
 }
 

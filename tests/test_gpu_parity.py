@@ -230,6 +230,35 @@ def test_bvh_config5_glass_metal_32_bounces(rb, orc):
         r.close()
 
 
+@pytest.mark.parametrize("n", [40, 300, 700, 1000])
+def test_fused_scan_cluster_sizes(rb, orc, n):
+    """The fused scan keeps <= 32 top-level entries by growing the clusters (8, 16, 24, 32 members): random scenes of
+    n objects + a ground cube, first hits, arbitrary rays (incl. degenerate ones) and a small multi-bounce render
+    against the oracle's linear scan."""
+    import synth_scenes as ss
+    scene = ss.config4(n, 96, 54)
+    r = rb.Renderer(rb.RendererConfig(2, 12)); r.set_seed(21); r.set_accel(rb.ACCEL_FUSED)
+    r.new_frame(scene)
+    ids_o, t_o = orc.first_hit(scene)
+    ids_g, t_g = r.first_hit()
+    assert np.array_equal(ids_o, ids_g) and np.array_equal(u32(t_o), u32(t_g))
+    rng = np.random.default_rng(n)
+    rays = random_rays(rng, 4001, scale=60.0)
+    rays[:, 1] = np.abs(rays[:, 1]) * 0.5
+    rays[::50, 3 + (np.arange(len(rays[::50])) % 3)] = 0.0
+    rays[::77, :3] *= 1e4
+    ids_g, t_g = r.kat_trace(rays)
+    for i in range(0, len(rays), 5):
+        idx, t = orc.trace(scene, rays[i, :3], rays[i, 3:])
+        assert idx == ids_g[i], i
+        if idx >= 0:
+            assert u32(np.float32(t)) == u32(t_g[i])
+    want = orc.render(scene, 21, 0, 2, 12, n_threads=orc.max_threads())
+    r.render_frame(scene)
+    assert np.array_equal(u32(want), u32(r.read_accum()))
+    r.close()
+
+
 def test_edge_cases(rb, orc, default_scene):
     # zero objects: every sample is the sky
     empty = default_scene.with_resolution(32, 16)
