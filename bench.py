@@ -63,12 +63,21 @@ def flops_per_sample(n_spheres, n_cubes, traces_per_sample):
 
 
 # ---- CPU arm: the oracle port of the reference's CPU backend ---------------------------------------------
+def host_cores():
+    """Cores this process may run on.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to every rank, and
+    the reference arm is meant to use all the host threads it can (the oracle passes the count in a num_threads clause)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_run(a, target_seconds, threads=None):
     """Times the oracle on a bounded sample of the workload: the full-resolution frame at a reduced spp
     (samples/s does not depend on spp).  Returns (Msamples/s, description, traces_per_sample, cores)."""
     from oracle import orc
     scene = orc.load_rscn(a.scene).with_resolution(a.width, a.height)
-    threads = threads or orc.max_threads()
+    threads = threads or host_cores()
     t0 = time.perf_counter()
     _, st = orc.render(scene, a.seed, 0, 1, a.bounces, n_threads=threads, want_stats=True)
     t1 = time.perf_counter() - t0
@@ -87,7 +96,7 @@ def run_reference(a):
         return
     from oracle import orc
     scene = orc.load_rscn(a.scene).with_resolution(a.width, a.height)
-    threads = orc.max_threads()
+    threads = host_cores()
     # size a step (a bounded sample of the frame: full resolution, reduced spp) to a few seconds
     t0 = time.perf_counter(); orc.render(scene, a.seed, 0, 1, a.bounces, n_threads=threads); t1 = time.perf_counter() - t0
     spp = int(max(1, min(16, round(4.0 / max(t1, 1e-3)))))
