@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0x5EED)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--accel", default="auto", choices=["auto", "brute", "bvh", "cluster", "coop", "fused"], help="nearest-hit search of the CUDA backend")
+    ap.add_argument("--accel", default="auto", choices=["auto", "brute", "bvh", "cluster", "coop", "fused", "bvh2"], help="nearest-hit search of the CUDA backend")
     return ap.parse_args()
 
 
@@ -191,7 +191,7 @@ def run_b200(a):
     n_pixels = a.width * a.height
     r = rb.Renderer(rb.RendererConfig(a.spp, a.bounces), device=local)
     r.set_seed(a.seed)
-    r.set_accel({"auto": rb.ACCEL_AUTO, "brute": rb.ACCEL_BRUTE, "bvh": rb.ACCEL_BVH, "cluster": rb.ACCEL_CLUSTER, "coop": rb.ACCEL_COOP, "fused": rb.ACCEL_FUSED}[a.accel])
+    r.set_accel({"auto": rb.ACCEL_AUTO, "brute": rb.ACCEL_BRUTE, "bvh": rb.ACCEL_BVH, "cluster": rb.ACCEL_CLUSTER, "coop": rb.ACCEL_COOP, "fused": rb.ACCEL_FUSED, "bvh2": rb.ACCEL_BVH_COOP}[a.accel])
     r.set_sample_offset(rank * a.spp)                    # weak scaling: every rank renders spp samples of its own range
     r.new_frame(flat)
     ptr, nbytes = r.accum_device_ptr()

@@ -53,8 +53,10 @@ enum { RDR_MAT_STRIDE = 11 };  /* albedo3, roughness, metallic, emission_color3,
  *   COOP     CLUSTER with the per-lane stages regrouped across the warp (ballot/shuffle work distribution)
  *   FUSED    COOP rebuilt for the sm_100a issue model: packed FFMA2 box tests, top-level boxes in the constant
  *            bank, atomics-free survivor compaction (<= 32 top-level entries, i.e. <= 256 objects; COOP above)
- *   AUTO     FUSED / COOP up to 1024 objects, BVH above */
-enum { RDR_ACCEL_AUTO = 0, RDR_ACCEL_BRUTE = 1, RDR_ACCEL_BVH = 2, RDR_ACCEL_CLUSTER = 3, RDR_ACCEL_COOP = 4, RDR_ACCEL_FUSED = 5 };
+ *   BVH_COOP the hierarchy in pair-packed form (<= 32 root entries, 8-wide nodes), traversed by the whole warp from one
+ *            shared task stack (FFMA2 pair tests, prefix-sum compaction, pruning by the best exact hit so far)
+ *   AUTO     FUSED / COOP up to 1024 objects, BVH_COOP above */
+enum { RDR_ACCEL_AUTO = 0, RDR_ACCEL_BRUTE = 1, RDR_ACCEL_BVH = 2, RDR_ACCEL_CLUSTER = 3, RDR_ACCEL_COOP = 4, RDR_ACCEL_FUSED = 5, RDR_ACCEL_BVH_COOP = 6 };
 
 typedef struct RdrRenderer RdrRenderer;    /* replaces CpuRenderer state, cpu.rs:111-116 */
 typedef struct RdrScene RdrScene;          /* host-side loaded scene, scene/mod.rs:13-18 */

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(_HERE, "libraydar_cuda.so")
 
 SPHERE, CUBE = 0, 1
 WORLD_SKY, WORLD_SOLID, WORLD_TRANSPARENT = 0, 1, 2
-ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH, ACCEL_CLUSTER, ACCEL_COOP, ACCEL_FUSED = 0, 1, 2, 3, 4, 5
+ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH, ACCEL_CLUSTER, ACCEL_COOP, ACCEL_FUSED, ACCEL_BVH_COOP = 0, 1, 2, 3, 4, 5, 6
 MAT_STRIDE = 11
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_IO, ERR_PARSE, ERR_NCCL, ERR_NOMEM = range(8)
 

@@ -55,6 +55,7 @@ struct RdrRenderer {
     bool use_cull = true;
 
     bool has_frame = false;
+    bool has_frame_layout_bvh = false;   // the current frame was packed as a hierarchy (AUTO above the threshold)
     FrameParams params{};
     unsigned char *d_blob = nullptr; size_t blob_capacity = 0;
     rdr::f4 *d_accum = nullptr; uchar4 *d_rgba = nullptr; size_t pixel_capacity = 0;
@@ -92,7 +93,8 @@ int pack_scene(RdrRenderer *r, const RdrSceneFlat *sc, std::vector<unsigned char
 {
     std::string err;
     // RDR_ACCEL_AUTO: the two-level scan while the cluster masks fit (<= 128 clusters), the hierarchy above
-    const bool use_bvh = r->accel == RDR_ACCEL_BVH || (r->accel == RDR_ACCEL_AUTO && sc && sc->n_objects > RDR_AUTO_BVH_THRESHOLD);
+    const bool use_bvh = r->accel == RDR_ACCEL_BVH || r->accel == RDR_ACCEL_BVH_COOP ||
+                         (r->accel == RDR_ACCEL_AUTO && sc && sc->n_objects > RDR_AUTO_BVH_THRESHOLD);
     const int st = rdr::pack_scene_blob(sc, use_bvh, blob, P, err);
     return st == RDR_OK ? RDR_OK : fail(r, st, "%s", err.c_str());
 }
@@ -104,7 +106,11 @@ int scan_variant(const RdrRenderer *r)
     if (!r->use_cull) return 1;
     if (r->accel == RDR_ACCEL_BRUTE) return 0;
     if (r->accel == RDR_ACCEL_CLUSTER) return 2;
-    return r->accel == RDR_ACCEL_COOP ? 3 : 4;              // AUTO / FUSED: fused scan (<= 32 top entries), else cooperative
+    if (r->accel == RDR_ACCEL_COOP) return 3;
+    if (r->accel == RDR_ACCEL_BVH) return 6;                // hierarchy, per-lane traversal
+    if (r->accel == RDR_ACCEL_BVH_COOP) return 5;           // hierarchy, warp-cooperative traversal
+    if (r->accel == RDR_ACCEL_AUTO && r->has_frame_layout_bvh) return 5;
+    return 4;                                               // AUTO / FUSED: fused scan (<= 32 top entries), else cooperative
 }
 
 int ensure_device(RdrRenderer *r) { RDR_CUDA(r, cudaSetDevice(r->device)); return RDR_OK; }
@@ -291,6 +297,7 @@ int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene)
     r->params = P;
     r->sample_count = 0;
     r->has_frame = true;
+    r->has_frame_layout_bvh = P.lay.mode == 1u;
     return RDR_OK;
 }
 
@@ -447,7 +454,7 @@ int rdr_set_sample_offset(RdrRenderer *r, uint32_t first_sample)
 int rdr_set_accel(RdrRenderer *r, int accel)
 {
     if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
-    if (accel < RDR_ACCEL_AUTO || accel > RDR_ACCEL_FUSED) return fail(r, RDR_ERR_INVALID, "unknown accel %d", accel);
+    if (accel < RDR_ACCEL_AUTO || accel > RDR_ACCEL_BVH_COOP) return fail(r, RDR_ERR_INVALID, "unknown accel %d", accel);
     r->accel = accel;
     return RDR_OK;
 }

@@ -159,6 +159,154 @@ private:
     }
 };
 
+// ---- pair-packed hierarchy for the warp-cooperative traversal (rdr_bvh2.cuh) -----------------------------------
+// Same boxes and the same conservative rules as BvhBuilder, different shape and storage:
+//   root   <= 32 entries, returned as 16 TopPair records (FFMA2 operand order) that travel in the kernel parameters,
+//          plus their payloads;
+//   node   8 entries = 4 pairs (A, B) x 4 quads + 1 header quad (17 quads, 272 B):
+//            (cxA, cxB, cyA, cyB) (czA, czB, exA, exB) (eyA, eyB, ezA, ezB) (sphereA, sphereB, payloadA, payloadB)
+//          header: (primitive mask, cube mask, valid mask, 0) over the 8 entries, bit = entry
+//   payload as in BvhBuilder: bit 31 = primitive (else child node index), bit 30 = cube, low 30 bits = index.
+struct Bvh2Root {
+    float cx[32], cy[32], cz[32], ex[32], ey[32], ez[32], sphere[32];
+    uint32_t payload[32];
+    uint32_t n = 0;
+};
+
+class Bvh2Builder {
+public:
+    static constexpr int NODE_FLOATS = 68;
+    std::vector<float> nodes;
+    Bvh2Root root;
+    int max_depth = 0;
+
+    bool build(std::vector<BvhBuildPrim> prims)
+    {
+        nodes.clear(); max_depth = 0; root = Bvh2Root();
+        for (int k = 0; k < 32; ++k) { root.ex[k] = root.ey[k] = root.ez[k] = -1.0f; root.payload[k] = 0xffffffffu; }
+        prims_ = std::move(prims);
+        order_.resize(prims_.size());
+        for (size_t i = 0; i < order_.size(); ++i) order_[i] = (uint32_t)i;
+        if (prims_.empty()) return true;
+        std::vector<Entry> entries;
+        make_entries(0u, (uint32_t)order_.size(), 32, 4, 1, entries);
+        root.n = (uint32_t)entries.size();
+        for (uint32_t k = 0; k < root.n; ++k) {
+            const Entry &e = entries[k];
+            root.cx[k] = e.box.c[0]; root.cy[k] = e.box.c[1]; root.cz[k] = e.box.c[2];
+            root.ex[k] = e.box.e[0]; root.ey[k] = e.box.e[1]; root.ez[k] = e.box.e[2];
+            root.sphere[k] = e.box.sphere ? 1.0f : 0.0f;
+            root.payload[k] = e.payload;
+        }
+        return max_depth <= BVH_MAX_DEPTH;
+    }
+
+    uint32_t n_nodes() const { return (uint32_t)(nodes.size() / NODE_FLOATS); }
+
+private:
+    struct Entry { BvhBox box; uint32_t payload; };
+    std::vector<BvhBuildPrim> prims_;
+    std::vector<uint32_t> order_;
+
+    BvhBox prim_box(const BvhBuildPrim &p) const { return BvhBox{{p.c[0], p.c[1], p.c[2]}, {p.e, p.e, p.e}, !p.cube}; }
+
+    BvhBox range_box(uint32_t b, uint32_t e) const
+    {
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        bool sphere = false;
+        for (uint32_t i = b; i < e; ++i) {
+            const BvhBuildPrim &p = prims_[order_[i]];
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p.c[a] - p.e); hi[a] = std::max(hi[a], p.c[a] + p.e); }
+            sphere |= !p.cube;
+        }
+        BvhBox box; box.sphere = sphere;
+        for (int a = 0; a < 3; ++a) {
+            box.c[a] = 0.5f * (lo[a] + hi[a]);
+            const float h = std::max(hi[a] - box.c[a], box.c[a] - lo[a]);
+            box.e[a] = std::nextafter(h * (1.0f + 1e-6f), INFINITY);
+        }
+        return box;
+    }
+
+    void split(uint32_t b, uint32_t e, int k, std::vector<std::pair<uint32_t, uint32_t>> &out)
+    {
+        if (k <= 1 || e - b <= 1) { out.emplace_back(b, e); return; }
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t i = b; i < e; ++i)
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], prims_[order_[i]].c[a]); hi[a] = std::max(hi[a], prims_[order_[i]].c[a]); }
+        int axis = 0;
+        if (hi[1] - lo[1] > hi[axis] - lo[axis]) axis = 1;
+        if (hi[2] - lo[2] > hi[axis] - lo[axis]) axis = 2;
+        const int kl = k / 2, kr = k - kl;
+        uint32_t mid = b + (uint32_t)(((uint64_t)(e - b) * kl) / k);
+        mid = std::max(b + 1, std::min(e - 1, mid));
+        std::nth_element(order_.begin() + b, order_.begin() + mid, order_.begin() + e,
+                         [&](uint32_t x, uint32_t y) { return prims_[x].c[axis] < prims_[y].c[axis]; });
+        split(b, mid, kl, out);
+        split(mid, e, kr, out);
+    }
+
+    static uint32_t prim_payload(const BvhBuildPrim &p) { return BVH_PRIM_BIT | (p.cube ? BVH_CUBE_BIT : 0u) | (p.index & BVH_INDEX_MASK); }
+
+    // the <= width entries that cover order_[b, e): primitives when they fit, otherwise up to max_direct large
+    // primitives as direct entries and a k-way split of the rest into child nodes (or single primitives)
+    void make_entries(uint32_t b, uint32_t e, int width, int max_direct, int depth, std::vector<Entry> &out)
+    {
+        max_depth = std::max(max_depth, depth);
+        if (e - b <= (uint32_t)width) {
+            for (uint32_t i = b; i < e; ++i) out.push_back(Entry{prim_box(prims_[order_[i]]), prim_payload(prims_[order_[i]])});
+            return;
+        }
+        const BvhBox nb = range_box(b, e);
+        const float big = 0.3f * std::max(nb.e[0], std::max(nb.e[1], nb.e[2]));
+        uint32_t rest = b;
+        int slot = 0;
+        for (uint32_t i = b; i < e && slot < max_direct; ++i) {
+            if (prims_[order_[i]].e > big) {
+                out.push_back(Entry{prim_box(prims_[order_[i]]), prim_payload(prims_[order_[i]])});
+                std::swap(order_[i], order_[rest]);
+                ++rest; ++slot;
+            }
+        }
+        std::vector<std::pair<uint32_t, uint32_t>> groups;
+        split(rest, e, width - slot, groups);
+        for (const auto &g : groups) {
+            if (g.second == g.first) continue;
+            if (g.second - g.first == 1) { out.push_back(Entry{prim_box(prims_[order_[g.first]]), prim_payload(prims_[order_[g.first]])}); continue; }
+            const uint32_t child = n_nodes();
+            nodes.resize(nodes.size() + NODE_FLOATS, 0.0f);
+            out.push_back(Entry{range_box(g.first, g.second), child});
+            std::vector<Entry> sub;
+            make_entries(g.first, g.second, BVH_WIDTH, 3, depth + 1, sub);
+            write_node(child, sub);
+        }
+    }
+
+    void write_node(uint32_t node, const std::vector<Entry> &entries)
+    {
+        float *p = nodes.data() + (size_t)node * NODE_FLOATS;
+        uint32_t prim_mask = 0u, cube_mask = 0u, valid_mask = 0u;
+        for (int k = 0; k < BVH_WIDTH; ++k) {
+            float *q = p + 16 * (k >> 1);
+            const int h = k & 1;
+            if (k >= (int)entries.size()) {
+                q[6 + h] = q[8 + h] = q[10 + h] = -1.0f;           // unused: e = -1 (and masked out by valid_mask)
+                const uint32_t none = 0xffffffffu; memcpy(&q[14 + h], &none, 4);
+                continue;
+            }
+            const Entry &e = entries[k];
+            q[0 + h] = e.box.c[0]; q[2 + h] = e.box.c[1]; q[4 + h] = e.box.c[2];
+            q[6 + h] = e.box.e[0]; q[8 + h] = e.box.e[1]; q[10 + h] = e.box.e[2];
+            q[12 + h] = e.box.sphere ? 1.0f : 0.0f;
+            memcpy(&q[14 + h], &e.payload, 4);
+            valid_mask |= 1u << k;
+            if (e.payload & BVH_PRIM_BIT) prim_mask |= 1u << k;
+            if ((e.payload & BVH_PRIM_BIT) && (e.payload & BVH_CUBE_BIT)) cube_mask |= 1u << k;
+        }
+        memcpy(&p[64], &prim_mask, 4); memcpy(&p[65], &cube_mask, 4); memcpy(&p[66], &valid_mask, 4);
+    }
+};
+
 // ---- two-level clustering for the cluster scan -----------------------------------------------------------------
 // Groups the primitives into spatially coherent clusters of <= 8 (k-way median splits, k = ceil(n / 8), so the
 // clusters come out nearly full); primitives that are large compared with the scene (a floor cube) stay alone.

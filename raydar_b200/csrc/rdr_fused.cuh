@@ -119,16 +119,64 @@ __device__ __forceinline__ void fused_exact(const FusedView &V, FusedWarp ws, ui
 
 // two boxes (A, B) against one ray: bit 0 / bit 1 of the result = box A / B may be hit.
 //   c*: centres, e*: half-extents (already inflated), r*: the ray's 1/d, n*: -(o/d)
+template <bool BOUNDED = false>
 __device__ __forceinline__ uint32_t slab_pair(f32x2 cx, f32x2 cy, f32x2 cz, f32x2 ex, f32x2 ey, f32x2 ez,
-                                              float rx, float ry, float rz, float nx, float ny, float nz)
+                                              float rx, float ry, float rz, float nx, float ny, float nz, float best = 0.0f)
 {
     const f32x2 tcx = fma2(cx, bc2(rx), bc2(nx)), tcy = fma2(cy, bc2(ry), bc2(ny)), tcz = fma2(cz, bc2(rz), bc2(nz));
     float nxa, nxb, nya, nyb, nza, nzb, fxa, fxb, fya, fyb, fza, fzb;
     un2(fma2(ex, bc2(-fabsf(rx)), tcx), nxa, nxb); un2(fma2(ey, bc2(-fabsf(ry)), tcy), nya, nyb); un2(fma2(ez, bc2(-fabsf(rz)), tcz), nza, nzb);
     un2(fma2(ex, bc2(fabsf(rx)), tcx), fxa, fxb); un2(fma2(ey, bc2(fabsf(ry)), tcy), fya, fyb); un2(fma2(ez, bc2(fabsf(rz)), tcz), fza, fzb);
-    const float tna = fmaxf(fmaxf(nxa, nya), fmaxf(nza, 0.0f)), tfa = fminf(fminf(fxa, fya), fza);
-    const float tnb = fmaxf(fmaxf(nxb, nyb), fmaxf(nzb, 0.0f)), tfb = fminf(fminf(fxb, fyb), fzb);
+    // BOUNDED: a box whose entry distance exceeds the ray's best exact t so far cannot hold the winner (ties kept);
+    // min.f32 ignores a NaN operand, so "no hit yet" is passed as NaN
+    const float tna = fmaxf(fmaxf(nxa, nya), fmaxf(nza, 0.0f)), tfa = BOUNDED ? fminf(fminf(fxa, fya), fminf(fza, best)) : fminf(fminf(fxa, fya), fza);
+    const float tnb = fmaxf(fmaxf(nxb, nyb), fmaxf(nzb, 0.0f)), tfb = BOUNDED ? fminf(fminf(fxb, fyb), fminf(fzb, best)) : fminf(fminf(fxb, fyb), fzb);
     return (tna > tfa ? 0u : 1u) | (tnb > tfb ? 0u : 2u);
+}
+
+// slab constants of one ray for the pair tests (make_ray_bvh, rdr_core.cuh): r = 1/d (clamped to +-1e30 for zero /
+// denormal components), n = -(o/d), rho = per-ray inflation of sphere-flagged boxes.  A ray that must skip the cull
+// (origin outside the scene bound, non-finite) gets all-zero constants: every box test then passes (tn = tf = 0).
+struct SlabRay { float rx, ry, rz, nx, ny, nz, rho; };
+
+__device__ __forceinline__ SlabRay slab_ray_setup(const CullConsts &cc, v3 o, v3 d)
+{
+    SlabRay R;
+    R.rx = __frcp_rn(d.x); R.ry = __frcp_rn(d.y); R.rz = __frcp_rn(d.z);         // == 1.0f / d, correctly rounded
+    const float big = 1e30f;
+    if (!(fabsf(R.rx) < big)) R.rx = copysignf(big, d.x);
+    if (!(fabsf(R.ry) < big)) R.ry = copysignf(big, d.y);
+    if (!(fabsf(R.rz) < big)) R.rz = copysignf(big, d.z);
+    const float a = fma(d.x, d.x, fma(d.y, d.y, fmul(d.z, d.z)));
+    const float oo = fma(o.x, o.x, fma(o.y, o.y, fmul(o.z, o.z)));
+    const float s_ray = fma(2.0f, oo, cc.sphere_q_max);
+    const float Ms = fmul(1.9073486328125e-06f, s_ray);
+    const float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+    const bool degenerate = !(omax <= cc.origin_bound) || !(a > 1e-30f) || !(a < 1e30f) || !(s_ray < 1e30f) ||
+                            isnan_(d.x) || isnan_(d.y) || isnan_(d.z);
+    R.rho = fadd(fsub(fsqrt(fma(cc.sphere_r_min, cc.sphere_r_min, Ms)), cc.sphere_r_min), fmul(1.9073486328125e-06f, fsqrt(s_ray)));
+    R.rho = fmul(R.rho, 1.0001f);
+    R.nx = fneg(fmul(o.x, R.rx)); R.ny = fneg(fmul(o.y, R.ry)); R.nz = fneg(fmul(o.z, R.rz));
+    if (degenerate) { R.rx = R.ry = R.rz = 0.0f; R.nx = R.ny = R.nz = 0.0f; R.rho = 0.0f; }
+    return R;
+}
+
+// the ray against the first n_top (<= 32) top-level boxes of the kernel parameters: bit k = box k may be hit.
+// Fully unrolled so that every operand is a compile-time constant-bank address (LDCU.128 into uniform registers).
+__device__ __forceinline__ uint32_t top_scan(const TopParams &T, uint32_t n_top, const SlabRay &R)
+{
+    uint32_t m = 0u;
+    const f32x2 rho2 = bc2(R.rho);
+#pragma unroll
+    for (uint32_t k = 0; k < FUSED_MAX_TOP / 2u; ++k) {
+        if ((k & 3u) == 0u && 2u * k >= n_top) break;
+        const TopPair &t = T.pair[k];
+        const f32x2 sp = pk2(t.sphere[0], t.sphere[1]);
+        const f32x2 ex = fma2(sp, rho2, pk2(t.ex[0], t.ex[1])), ey = fma2(sp, rho2, pk2(t.ey[0], t.ey[1])), ez = fma2(sp, rho2, pk2(t.ez[0], t.ez[1]));
+        m |= slab_pair(pk2(t.cx[0], t.cx[1]), pk2(t.cy[0], t.cy[1]), pk2(t.cz[0], t.cz[1]), ex, ey, ez, R.rx, R.ry, R.rz, R.nx, R.ny, R.nz) << (2u * k);
+    }
+    if (n_top < 32u) m &= (1u << n_top) - 1u;
+    return m;
 }
 
 // CAP8: the clusters have 8 member slots (scenes up to ~250 objects): one member step per round, resolved at compile time
@@ -138,42 +186,14 @@ __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
 
-    // ---- ray set-up (make_ray_bvh, rdr_core.cuh): slab constants, per-ray sphere-box inflation rho ----
-    float rx = __frcp_rn(d.x), ry = __frcp_rn(d.y), rz = __frcp_rn(d.z);        // == 1.0f / d, correctly rounded
-    const float big = 1e30f;
-    if (!(fabsf(rx) < big)) rx = copysignf(big, d.x);                            // zero / denormal component: clamped slab
-    if (!(fabsf(ry) < big)) ry = copysignf(big, d.y);
-    if (!(fabsf(rz) < big)) rz = copysignf(big, d.z);
-    const float a = fma(d.x, d.x, fma(d.y, d.y, fmul(d.z, d.z)));
-    const float oo = fma(o.x, o.x, fma(o.y, o.y, fmul(o.z, o.z)));
-    const float s_ray = fma(2.0f, oo, P.cull.sphere_q_max);
-    const float Ms = fmul(1.9073486328125e-06f, s_ray);
-    const float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
-    const bool degenerate = !(omax <= P.cull.origin_bound) || !(a > 1e-30f) || !(a < 1e30f) || !(s_ray < 1e30f) ||
-                            isnan_(d.x) || isnan_(d.y) || isnan_(d.z);
-    float rho = fadd(fsub(fsqrt(fma(P.cull.sphere_r_min, P.cull.sphere_r_min, Ms)), P.cull.sphere_r_min),
-                     fmul(1.9073486328125e-06f, fsqrt(s_ray)));
-    rho = fmul(rho, 1.0001f);
-    float nx = fneg(fmul(o.x, rx)), ny = fneg(fmul(o.y, ry)), nz = fneg(fmul(o.z, rz));
-    if (degenerate) { rx = ry = rz = 0.0f; nx = ny = nz = 0.0f; rho = 0.0f; }    // every box test passes (tn = tf = 0)
+    const SlabRay R = slab_ray_setup(P.cull, o, d);
+    const float rx = R.rx, ry = R.ry, rz = R.rz, nx = R.nx, ny = R.ny, nz = R.nz, rho = R.rho;
 
     ws.best[lane] = ~0ull;
 
     // ---- A0: this lane's ray against every top-level box, two per FFMA2, operands from the constant bank ----
-    uint32_t m = 0u;
-    {
-        const f32x2 rho2 = bc2(rho);
-#pragma unroll
-        for (uint32_t k = 0; k < FUSED_MAX_TOP / 2u; ++k) {
-            if ((k & 3u) == 0u && 2u * k >= P.lay.fused_top) break;
-            const TopPair &t = P.top.pair[k];
-            const f32x2 sp = pk2(t.sphere[0], t.sphere[1]);
-            const f32x2 ex = fma2(sp, rho2, pk2(t.ex[0], t.ex[1])), ey = fma2(sp, rho2, pk2(t.ey[0], t.ey[1])), ez = fma2(sp, rho2, pk2(t.ez[0], t.ez[1]));
-            m |= slab_pair(pk2(t.cx[0], t.cx[1]), pk2(t.cy[0], t.cy[1]), pk2(t.cz[0], t.cz[1]), ex, ey, ez, rx, ry, rz, nx, ny, nz) << (2u * k);
-        }
-        if (P.lay.fused_top < 32u) m &= (1u << P.lay.fused_top) - 1u;
-        if (!alive) m = 0u;
-    }
+    uint32_t m = top_scan(P.top, P.lay.fused_top, R);
+    if (!alive) m = 0u;
 
     uint32_t n_s = 0u, n_c = 0u;                                                 // survivor list lengths (warp-uniform)
     // single-primitive top entries: their box was the entry -> straight to the survivor lists (member slot = C * entry)

@@ -14,6 +14,7 @@
 #include "raydar_cuda.h"
 #include "rdr_device.cuh"
 #include "rdr_fused.cuh"
+#include "rdr_bvh2.cuh"
 #include "rdr_launch.h"
 
 namespace rdr {
@@ -28,14 +29,14 @@ namespace rdr {
 template <int MODE>
 __device__ __forceinline__ const unsigned char *stage_scene(unsigned char *smem, const FrameParams &P)
 {
-    if (MODE < 5 && !P.staged) return P.blob;
+    if (MODE == 7 || (MODE < 5 && !P.staged)) return P.blob;       // MODE 7 reads the scene in place (global memory / L2)
     stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
     return smem;
 }
 template <int MODE>
 __device__ __forceinline__ uint32_t *scratch_base(unsigned char *smem, const FrameParams &P)
 {
-    return (MODE >= 5 || P.staged) ? mask_base(smem, P.lay) : reinterpret_cast<uint32_t *>(smem);
+    return (MODE != 7 && (MODE >= 5 || P.staged)) ? mask_base(smem, P.lay) : reinterpret_cast<uint32_t *>(smem);
 }
 
 // nearest hit for every lane of the warp (alive = the lane has a ray).  MODE 4 regroups the work across the warp
@@ -44,6 +45,7 @@ __device__ __forceinline__ uint32_t *scratch_base(unsigned char *smem, const Fra
 template <int MODE>
 __device__ __forceinline__ Hit trace_warp(const SceneView &S, const FrameParams &P, uint32_t *scratch0, bool alive, v3 o, v3 d)
 {
+    if (MODE == 7) return trace_bvh2(S, P, bvh2_warp(reinterpret_cast<unsigned char *>(scratch0 + blockDim.x), threadIdx.x >> 5), alive, o, d);
     if (MODE == 5 || MODE == 6) {
         FusedView V;
         V.pair_block = S.pair_block; V.member_geom = S.fused_geom; V.member_idx = S.fused_idx;
@@ -223,6 +225,7 @@ static size_t mode_smem_bytes(const SceneLayout &L, bool staged, uint32_t block,
 {
     const size_t warps = (block + 31u) / 32u;
     size_t scratch;
+    if (mode == 7) return (size_t)block * sizeof(uint32_t) + warps * BVH2_WARP_BYTES;              // never staged
     if (mode >= 5) scratch = (size_t)block * sizeof(uint32_t) + warps * FUSED_WARP_BYTES;        // one word per lane + per-warp regions
     else if (mode == 4) scratch = (size_t)block * sizeof(uint32_t) + warps * COOP_WARP_BYTES;
     else scratch = (size_t)scratch_words(L) * block * sizeof(uint32_t);                           // per-lane words
@@ -244,7 +247,7 @@ size_t scene_smem_bytes(const SceneLayout &L, bool staged, uint32_t block)
 // 4 = fused scan (needs lay.fused_ok, else the cooperative scan runs).  A BVH-packed blob can only be traversed as a BVH.
 static inline int mode_of(const FrameParams &P, int variant)
 {
-    if (P.lay.mode == 1u) return 2;
+    if (P.lay.mode == 1u) return (variant == 5 && P.lay.bvh2_ok) ? 7 : 2;      // hierarchy: warp-cooperative or per-lane traversal
     if (variant == 4 && !(P.lay.fused_ok && P.staged)) variant = 3;
     if (variant == 4) return P.lay.fused_cap == 8u ? 5 : 6;           // fused scan: 8-member clusters resolved at compile time
     return variant >= 2 ? variant + 1 : variant;
@@ -262,7 +265,8 @@ static cudaError_t set_smem(K kernel, size_t bytes)
 
 #define RDR_DISPATCH(mode, KERNEL, ...)                                   \
     do {                                                                  \
-        if ((mode) == 6) { KERNEL(6, __VA_ARGS__); }                      \
+        if ((mode) == 7) { KERNEL(7, __VA_ARGS__); }                      \
+        else if ((mode) == 6) { KERNEL(6, __VA_ARGS__); }                 \
         else if ((mode) == 5) { KERNEL(5, __VA_ARGS__); }                 \
         else if ((mode) == 4) { KERNEL(4, __VA_ARGS__); }                 \
         else if ((mode) == 3) { KERNEL(3, __VA_ARGS__); }                 \
@@ -286,14 +290,15 @@ static int fused_cta_config()
 static uint32_t render_block(int mode)
 {
     if (mode < 5) return RDR_BLOCK;
-    if (mode == 6) return 768u;
+    if (mode >= 6) return 768u;
     switch (fused_cta_config()) { case 1: return 896u; case 2: return 1024u; case 3: return 768u; default: return RDR_BLOCK; }
 }
 
 // calls F(kernel) with the render kernel instantiation for `mode`
 #define RDR_RENDER_DISPATCH(mode, F)                                                                  \
     do {                                                                                              \
-        if ((mode) == 6) { F((render_kernel<6, 768, 1>)); }                                           \
+        if ((mode) == 7) { F((render_kernel<7, 768, 1>)); }                                           \
+        else if ((mode) == 6) { F((render_kernel<6, 768, 1>)); }                                      \
         else if ((mode) == 5) {                                                                       \
             switch (fused_cta_config()) {                                                             \
             case 1: F((render_kernel<5, 896, 1>)); break;                                             \

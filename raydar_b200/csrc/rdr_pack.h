@@ -83,17 +83,39 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
             p.e = p.cube ? std::fabs(g[3]) * 0.5f + cube_pad : std::fabs(g[3]) + 2.0f * cube_pad;
         }
         BvhBuilder builder;
+        Bvh2Builder builder2;
+        const bool ok2 = builder2.build(prims);
         if (builder.build(std::move(prims))) {
             L.mode = 1u;
             L.n_nodes = builder.n_nodes();
+            L.bvh2_ok = ok2 ? 1u : 0u;
+            L.n_nodes2 = ok2 ? builder2.n_nodes() : 0u;
+            L.bvh2_root = ok2 ? builder2.root.n : 0u;
             uint64_t off = 0;
             L.off_nodes = (uint32_t)off; off += 256ull * L.n_nodes;
             L.off_obj_geom = (uint32_t)off; off += 16ull * n;
             L.off_material = (uint32_t)off; off += 48ull * n;
+            L.off_nodes2 = (uint32_t)off; off += 272ull * L.n_nodes2;
             if (off > 0xfffffff0ull) { err = "scene too large"; return RDR_ERR_INVALID; }
             L.blob_bytes = std::max(16u, round_up_u32((uint32_t)off, 16u));
             blob.assign(L.blob_bytes, 0);
             memcpy(blob.data() + L.off_nodes, builder.nodes.data(), 256ull * L.n_nodes);
+            if (L.n_nodes2) memcpy(blob.data() + L.off_nodes2, builder2.nodes.data(), 272ull * L.n_nodes2);
+            if (ok2) {
+                const Bvh2Root &R = builder2.root;
+                for (uint32_t k = 0; k < FUSED_MAX_TOP; ++k) {
+                    TopPair &tp = P.top.pair[k >> 1];
+                    const int h = (int)(k & 1u);
+                    tp.cx[h] = R.cx[k]; tp.cy[h] = R.cy[k]; tp.cz[h] = R.cz[k];
+                    tp.ex[h] = R.ex[k]; tp.ey[h] = R.ey[k]; tp.ez[h] = R.ez[k];
+                    tp.sphere[h] = R.sphere[k];
+                    P.top.payload[k] = R.payload[k];
+                    if (k < R.n && (R.payload[k] & BVH_PRIM_BIT)) {
+                        P.top.prim_mask |= 1u << k;
+                        if (R.payload[k] & BVH_CUBE_BIT) P.top.cube_mask |= 1u << k;
+                    }
+                }
+            }
             fill_objects();
             bvh_done = true;
         }

@@ -383,6 +383,7 @@ template <int MODE>
 RDR_HD Hit trace_any(const SceneView &S, const CullConsts &cc, uint32_t *scratch, uint32_t stride, v3 o, v3 d,
                      TraceStats *stats = nullptr)
 {
+    if (MODE == 7) return trace_bvh(S, cc, scratch, stride, o, d, stats);       // per-lane twin of the cooperative traversal
     if (MODE >= 3) return trace_cluster(S, cc, scratch, stride, o, d, stats);   // 4, 5: per-lane twin of the cooperative / fused scan
     if (MODE == 2) return trace_bvh(S, cc, scratch, stride, o, d, stats);
     if (MODE == 1) return trace_brute<false>(S, cc, scratch, stride, o, d, stats);

@@ -5,6 +5,7 @@
 // Built by tests/conftest.py with g++ -O2 -ffp-contract=off -mfma (explicit fma() calls map to one
 // hardware FMA exactly as FFMA does on the device; nothing else may be contracted).
 // libraydar_cuda.so never contains or calls this file.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -41,8 +42,59 @@ struct Packed {
     }
 };
 
+// Scalar walk of the pair-packed hierarchy of the warp-cooperative traversal (rdr_bvh2.cuh runs on the device only):
+// checks what the host can check -- the builder's boxes, masks and payloads, and the root in the kernel parameters --
+// with the same conservative entry test and the same exact tests / winner rule.
+Hit trace_bvh2_scalar(const Packed &pk, v3 o, v3 d, TraceStats *st)
+{
+    const SceneView &S = pk.S;
+    Hit best; best.idx = -1; best.t = finf();
+    const RayBvh rb = make_ray_bvh(o, d, pk.P.cull);
+    const bool all = rb.rc.degenerate;
+    if (st) { st->traces++; if (all) st->degenerate++; }
+    auto prune = [&]() { return (best.idx >= 0 && !isnan_(best.t)) ? best.t : finf(); };
+    std::vector<uint32_t> stack;
+    auto visit = [&](f4 q0, f4 q1, uint32_t payload, bool is_prim, bool is_cube) {
+        float tn;
+        if (!all && !bvh_entry_may_hit(rb, q0, q1, prune(), &tn)) return;
+        if (is_prim) {
+            // the header masks must agree with the payload bits
+            if (!(payload & 0x80000000u) || ((payload & 0x40000000u) != 0u) != is_cube) { best.idx = -2; return; }
+            bvh_exact_prim(S, payload, o, d, best, st);
+        } else {
+            if (payload & 0x80000000u) { best.idx = -2; return; }
+            stack.push_back(payload);
+        }
+    };
+    const TopParams &T = pk.P.top;
+    for (uint32_t k = 0; k < pk.P.lay.bvh2_root; ++k) {
+        const TopPair &tp = T.pair[k >> 1]; const int h = (int)(k & 1u);
+        f4 q0, q1; q0.x = tp.cx[h]; q0.y = tp.cy[h]; q0.z = tp.cz[h]; q0.w = tp.ex[h];
+        q1.x = tp.ey[h]; q1.y = tp.ez[h]; q1.z = 0.0f; q1.w = tp.sphere[h];
+        visit(q0, q1, T.payload[k], (T.prim_mask >> k) & 1u, (T.cube_mask >> k) & 1u);
+    }
+    const float *nodes = reinterpret_cast<const float *>(pk.blob + pk.P.lay.off_nodes2);
+    while (!stack.empty()) {
+        const uint32_t node = stack.back(); stack.pop_back();
+        if (st) st->nodes_visited++;
+        if (node >= pk.P.lay.n_nodes2) { best.idx = -2; return best; }
+        const float *p = nodes + 68 * (size_t)node;
+        uint32_t pm, cm, vm; memcpy(&pm, p + 64, 4); memcpy(&cm, p + 65, 4); memcpy(&vm, p + 66, 4);
+        for (int k = 0; k < 8; ++k) {
+            if (!((vm >> k) & 1u)) continue;
+            const float *q = p + 16 * (k >> 1); const int h = k & 1;
+            f4 q0, q1; q0.x = q[0 + h]; q0.y = q[2 + h]; q0.z = q[4 + h]; q0.w = q[6 + h];
+            q1.x = q[8 + h]; q1.y = q[10 + h]; q1.z = 0.0f; q1.w = q[12 + h];
+            uint32_t payload; memcpy(&payload, q + 14 + h, 4);
+            visit(q0, q1, payload, (pm >> k) & 1u, (cm >> k) & 1u);
+        }
+    }
+    return best;
+}
+
 Hit trace_mode(int use_cull, const Packed &pk, uint32_t *scratch, v3 o, v3 d, TraceStats *st)
 {
+    if (pk.P.lay.mode == 1u && use_cull == 4) return trace_bvh2_scalar(pk, o, d, st);
     if (pk.P.lay.mode == 1u) return trace_any<2>(pk.S, pk.P.cull, scratch, 1, o, d, st);
     if (use_cull == 3) return trace_any<3>(pk.S, pk.P.cull, scratch, 1, o, d, st);
     return use_cull ? trace_any<0>(pk.S, pk.P.cull, scratch, 1, o, d, st) : trace_any<1>(pk.S, pk.P.cull, scratch, 1, o, d, st);
@@ -61,7 +113,7 @@ extern "C" {
 
 int hs_first_hit(const RdrSceneFlat *sc, int use_cull, int32_t *ids, float *ts, TraceStats *stats)
 {
-    Packed pk(sc, use_cull == 2);
+    Packed pk(sc, use_cull == 2 || use_cull == 4);
     if (pk.status != RDR_OK) return pk.status;
     const int64_t n = (int64_t)sc->width * sc->height;
     TraceStats total{};
@@ -86,7 +138,7 @@ int hs_first_hit(const RdrSceneFlat *sc, int use_cull, int32_t *ids, float *ts, 
 
 int hs_trace(const RdrSceneFlat *sc, int use_cull, uint32_t n, const float *rays, int32_t *ids, float *ts, TraceStats *stats)
 {
-    Packed pk(sc, use_cull == 2);
+    Packed pk(sc, use_cull == 2 || use_cull == 4);
     if (pk.status != RDR_OK) return pk.status;
     TraceStats total{};
 #pragma omp parallel
@@ -111,7 +163,7 @@ int hs_trace(const RdrSceneFlat *sc, int use_cull, uint32_t n, const float *rays
 int hs_render(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t sample_begin, uint32_t n_samples,
               uint32_t max_bounces, float *accum, TraceStats *stats)
 {
-    Packed pk(sc, use_cull == 2);
+    Packed pk(sc, use_cull == 2 || use_cull == 4);
     if (pk.status != RDR_OK) return pk.status;
     pk.P.seed_lo = (uint32_t)seed; pk.P.seed_hi = (uint32_t)(seed >> 32);
     pk.P.max_bounces = max_bounces; pk.P.sample_begin = sample_begin; pk.P.sample_count = n_samples;
@@ -140,7 +192,7 @@ int hs_render(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t samp
 int hs_trace_path(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t x, uint32_t y, uint32_t sample,
                   uint32_t max_bounces, RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float rgba[4])
 {
-    Packed pk(sc, use_cull == 2);
+    Packed pk(sc, use_cull == 2 || use_cull == 4);
     if (pk.status != RDR_OK) return pk.status;
     pk.P.seed_lo = (uint32_t)seed; pk.P.seed_hi = (uint32_t)(seed >> 32);
     pk.P.max_bounces = max_bounces;
@@ -221,6 +273,100 @@ int hs_bvh_info(const RdrSceneFlat *sc, uint32_t *n_nodes, uint32_t *mode, uint3
     Packed pk(sc, true);
     if (pk.status != RDR_OK) return pk.status;
     *n_nodes = pk.P.lay.n_nodes; *mode = pk.P.lay.mode; *blob_bytes = pk.P.lay.blob_bytes;
+    return RDR_OK;
+}
+
+// Simulation of the STACK DISCIPLINE of the warp-cooperative traversal (rdr_bvh2.cuh) for groups of 32 primary rays:
+// counts node visits, exact tests and rounds for a given policy, so that the policy can be tuned without a GPU.
+//   flush_at: survivors are exact-tested when a list holds >= flush_at entries (device: 32) or the stack is empty
+//   out[0] = node visits per ray, out[1] = exact tests per ray, out[2] = rounds per warp, out[3] = mean tasks per round
+int hs_bvh2_warp_sim(const RdrSceneFlat *sc, uint32_t flush_at, uint32_t order_children, double *out)
+{
+    Packed pk(sc, true);
+    if (pk.status != RDR_OK) return pk.status;
+    const SceneView &S = pk.S;
+    const int64_t n = (int64_t)sc->width * sc->height;
+    const float *nodes = reinterpret_cast<const float *>(pk.blob + pk.P.lay.off_nodes2);
+    const TopParams &T = pk.P.top;
+    double visits = 0, exacts = 0, rounds = 0, tasks_popped = 0, warps = 0;
+    for (int64_t p0 = 0; p0 < n; p0 += 32) {
+        const int nl = (int)std::min<int64_t>(32, n - p0);
+        v3 o[32], d[32]; RayBvh rb[32]; Hit best[32];
+        for (int l = 0; l < nl; ++l) {
+            o[l] = mk3(pk.P.cam.pos[0], pk.P.cam.pos[1], pk.P.cam.pos[2]);
+            d[l] = camera_ray_dir(pk.P.cam, (uint32_t)((p0 + l) % sc->width), (uint32_t)((p0 + l) / sc->width));
+            rb[l] = make_ray_bvh(o[l], d[l], pk.P.cull); best[l].idx = -1; best[l].t = finf();
+        }
+        struct Task { uint32_t owner, node; };
+        struct Surv { uint32_t owner, payload; };
+        std::vector<Task> stack; std::vector<Surv> surv;
+        auto prune = [&](int l) { return (best[l].idx >= 0 && !isnan_(best[l].t)) ? best[l].t : finf(); };
+        auto flush = [&](bool all) {
+            while (surv.size() >= flush_at || (all && !surv.empty())) {
+                const size_t k = std::min<size_t>(32, surv.size());
+                for (size_t i = surv.size() - k; i < surv.size(); ++i) { bvh_exact_prim(S, surv[i].payload, o[surv[i].owner], d[surv[i].owner], best[surv[i].owner], nullptr); exacts += 1; }
+                surv.resize(surv.size() - k);
+            }
+        };
+        struct Child { float tn; uint32_t payload; bool prim; };
+        auto emit = [&](int l, std::vector<Child> &ch) {
+            if (order_children) std::stable_sort(ch.begin(), ch.end(), [](const Child &a, const Child &b) { return a.tn > b.tn; });   // far first: near on top
+            for (const Child &c : ch) { if (c.prim) surv.push_back({(uint32_t)l, c.payload}); else stack.push_back({(uint32_t)l, c.payload}); }
+        };
+        for (uint32_t c0 = 0; c0 < pk.P.lay.bvh2_root; c0 += 8) {
+            for (int l = 0; l < nl; ++l) {
+                std::vector<Child> ch;
+                for (uint32_t k = c0; k < std::min(c0 + 8, pk.P.lay.bvh2_root); ++k) {
+                    const TopPair &tp = T.pair[k >> 1]; const int h = (int)(k & 1u);
+                    f4 q0, q1; q0.x = tp.cx[h]; q0.y = tp.cy[h]; q0.z = tp.cz[h]; q0.w = tp.ex[h];
+                    q1.x = tp.ey[h]; q1.y = tp.ez[h]; q1.z = 0.0f; q1.w = tp.sphere[h];
+                    float tn;
+                    if (bvh_entry_may_hit(rb[l], q0, q1, finf(), &tn)) ch.push_back({tn, T.payload[k], ((T.prim_mask >> k) & 1u) != 0u});
+                }
+                emit(l, ch);
+            }
+            flush(false);
+        }
+        for (;;) {
+            const bool last = stack.empty();
+            if (!last) {
+                size_t pop = (1024 > stack.size() ? 1024 - stack.size() : 0) / 7; pop = std::max<size_t>(1, std::min<size_t>(32, pop)); pop = std::min(pop, stack.size());
+                std::vector<Task> popped(stack.end() - pop, stack.end());
+                stack.resize(stack.size() - pop);
+                rounds += 1; tasks_popped += (double)pop;
+                for (size_t i = 0; i < pop; ++i) {                  // lane i takes stack[top - i]
+                    const Task t = popped[pop - 1 - i];
+                    visits += 1;
+                    const float *pn = nodes + 68 * (size_t)t.node;
+                    uint32_t pm, vm; memcpy(&pm, pn + 64, 4); memcpy(&vm, pn + 66, 4);
+                    std::vector<Child> ch;
+                    for (int k = 0; k < 8; ++k) {
+                        if (!((vm >> k) & 1u)) continue;
+                        const float *q = pn + 16 * (k >> 1); const int h = k & 1;
+                        f4 q0, q1; q0.x = q[0 + h]; q0.y = q[2 + h]; q0.z = q[4 + h]; q0.w = q[6 + h];
+                        q1.x = q[8 + h]; q1.y = q[10 + h]; q1.z = 0.0f; q1.w = q[12 + h];
+                        uint32_t payload; memcpy(&payload, q + 14 + h, 4);
+                        float tn;
+                        if (bvh_entry_may_hit(rb[t.owner], q0, q1, prune((int)t.owner), &tn)) ch.push_back({tn, payload, ((pm >> k) & 1u) != 0u});
+                    }
+                    emit((int)t.owner, ch);
+                }
+            }
+            flush(last);
+            if (last) break;
+        }
+        warps += 1;
+    }
+    out[0] = visits / (double)n; out[1] = exacts / (double)n; out[2] = rounds / warps; out[3] = tasks_popped / std::max(1.0, rounds);
+    return RDR_OK;
+}
+
+// shape of the pair-packed hierarchy of the cooperative traversal: nodes, root entries
+int hs_bvh2_info(const RdrSceneFlat *sc, uint32_t *n_nodes2, uint32_t *n_root, uint32_t *ok)
+{
+    Packed pk(sc, true);
+    if (pk.status != RDR_OK) return pk.status;
+    *n_nodes2 = pk.P.lay.n_nodes2; *n_root = pk.P.lay.bvh2_root; *ok = pk.P.lay.bvh2_ok;
     return RDR_OK;
 }
 

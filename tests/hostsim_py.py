@@ -55,6 +55,8 @@ def lib():
         L.hs_rng_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
         L.hs_scene_consts.argtypes = [sfp, fp, fp, fp]
         L.hs_bvh_info.argtypes = [sfp, u32p, u32p, u32p]
+        L.hs_bvh2_info.argtypes = [sfp, u32p, u32p, u32p]
+        L.hs_bvh2_warp_sim.argtypes = [sfp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
         L.hs_cluster_info.argtypes = [sfp, u32p, u32p]
         _lib = L
     return _lib
@@ -140,6 +142,7 @@ BVH = 2      # pass as use_cull to select the hierarchy (1/True = scan + cull, 0
 
 
 CLUSTER = 3  # two-level cluster scan
+BVH2 = 4     # scalar walk of the pair-packed hierarchy of the warp-cooperative traversal (builder check)
 
 
 def cluster_info(scene):
@@ -154,6 +157,21 @@ def bvh_info(scene):
     n = C.c_uint32(); mode = C.c_uint32(); nbytes = C.c_uint32()
     _ok(lib().hs_bvh_info(C.byref(f), C.byref(n), C.byref(mode), C.byref(nbytes)))
     return n.value, mode.value, nbytes.value
+
+
+def bvh2_info(scene):
+    f = rb._as_flat(scene)
+    n = C.c_uint32(); root = C.c_uint32(); ok = C.c_uint32()
+    _ok(lib().hs_bvh2_info(C.byref(f), C.byref(n), C.byref(root), C.byref(ok)))
+    return n.value, root.value, ok.value
+
+
+def bvh2_warp_sim(scene, flush_at=32, order_children=0):
+    """(node visits per ray, exact tests per ray, rounds per warp, tasks per round) of the cooperative stack discipline."""
+    f = rb._as_flat(scene)
+    out = (C.c_double * 4)()
+    _ok(lib().hs_bvh2_warp_sim(C.byref(f), flush_at, order_children, out))
+    return tuple(out)
 
 
 def scene_consts(scene):

@@ -23,7 +23,10 @@ def test_hierarchy_shape(hs):
     n_nodes, mode, nbytes = hs.bvh_info(scene)
     assert mode == 1
     assert 5001 / 8 <= n_nodes <= 5001                      # 8-wide: between N/8 and N nodes
-    assert nbytes == 256 * n_nodes + 64 * 5001 + (-(256 * n_nodes + 64 * 5001)) % 16
+    n_nodes2, n_root, ok2 = hs.bvh2_info(scene)               # pair-packed twin: <= 32 root entries, 17 quads per node
+    assert ok2 == 1 and 4 <= n_root <= 32 and 5001 / 8 / 1.5 <= n_nodes2 <= 5001
+    raw = 256 * n_nodes + 64 * 5001 + 272 * n_nodes2
+    assert nbytes == raw + (-raw) % 16
 
 
 @pytest.mark.parametrize("n", [300, 20_000])
@@ -38,6 +41,9 @@ def test_config4_first_hit_matches_linear_scan(hs, orc, n):
     assert len(np.unique(ids_o)) > min(n, 2000) // 4
     assert st.degenerate == 0
     assert (st.sphere_exact + st.cube_exact) / st.traces < 0.01 * n + 12      # a tiny fraction of the N exact tests
+    ids2, ts2, st2 = hs.first_hit(scene, hs.BVH2)             # the pair-packed hierarchy holds the same winner
+    assert np.array_equal(ids2, ids_o) and np.array_equal(u32(ts2), u32(t_o))
+    assert (st2.sphere_exact + st2.cube_exact) / st2.traces < 0.01 * n + 12
 
 
 def test_config4_secondary_rays(hs, orc):
@@ -52,7 +58,7 @@ def test_config5_glass_metal_lattice(hs, orc):
     scene = ss.config5(160, 90)
     assert scene.n_objects == 513
     ids_o, t_o = orc.first_hit(scene)
-    for mode in (True, hs.BVH, hs.CLUSTER):
+    for mode in (True, hs.BVH, hs.CLUSTER, hs.BVH2):
         ids, ts, _ = hs.first_hit(scene, mode)
         assert np.array_equal(ids, ids_o) and np.array_equal(u32(ts), u32(t_o))
     small = scene.with_resolution(64, 36)
@@ -83,6 +89,8 @@ def test_coincident_and_nested_primitives(hs, orc, default_scene):
     assert np.array_equal(a_ids, b_ids) and np.array_equal(u32(a_t), u32(b_t))
     c_ids, c_t, _ = hs.trace(s, rays, hs.CLUSTER)
     assert np.array_equal(a_ids, c_ids) and np.array_equal(u32(a_t), u32(c_t))
+    e_ids, e_t, _ = hs.trace(s, rays, hs.BVH2)
+    assert np.array_equal(a_ids, e_ids) and np.array_equal(u32(a_t), u32(e_t))
     for i in range(0, n, 101):
         idx, t = orc.trace(s, rays[i, :3], rays[i, 3:])
         assert idx == b_ids[i]

@@ -51,7 +51,7 @@ def test_intersection_kat(renderer, orc, sphere):
 
 
 @pytest.mark.parametrize("name,res", [("default", None), ("benchmark", (1920, 1080)), ("benchmark", None)])
-@pytest.mark.parametrize("cull", [True, False, "bvh", "cluster", "coop", "fused"])
+@pytest.mark.parametrize("cull", [True, False, "bvh", "cluster", "coop", "fused", "bvh2"])
 def test_first_hit_ids_bit_exact(rb, renderer, orc, default_scene, benchmark_scene, name, res, cull):
     scene = default_scene if name == "default" else benchmark_scene
     if res:
@@ -60,7 +60,7 @@ def test_first_hit_ids_bit_exact(rb, renderer, orc, default_scene, benchmark_sce
         pytest.skip("exact-everything reference run only up to 1080p")
     ids_o, t_o = orc.first_hit(scene)
     renderer.debug_set_cull(cull is not False)
-    renderer.set_accel({"bvh": rb.ACCEL_BVH, "cluster": rb.ACCEL_CLUSTER, "coop": rb.ACCEL_COOP, "fused": rb.ACCEL_FUSED}.get(cull, rb.ACCEL_BRUTE))
+    renderer.set_accel({"bvh": rb.ACCEL_BVH, "cluster": rb.ACCEL_CLUSTER, "coop": rb.ACCEL_COOP, "fused": rb.ACCEL_FUSED, "bvh2": rb.ACCEL_BVH_COOP}.get(cull, rb.ACCEL_BRUTE))
     try:
         renderer.new_frame(scene)
         ids_g, t_g = renderer.first_hit()
@@ -82,14 +82,14 @@ def test_camera_rays(renderer, orc, default_scene, benchmark_scene):
             assert np.array_equal(u32(o), u32(ray[:3])) and np.array_equal(u32(d), u32(ray[3:]))
 
 
-@pytest.mark.parametrize("accel", ["brute", "bvh", "cluster", "coop", "fused"])
+@pytest.mark.parametrize("accel", ["brute", "bvh", "cluster", "coop", "fused", "bvh2"])
 def test_trace_arbitrary_rays(rb, renderer, orc, benchmark_scene, accel):
     rng = np.random.default_rng(11)
     rays = random_rays(rng, 20_003, scale=8.0)            # not a multiple of 32: partial warps
     rays[:, 1] = np.abs(rays[:, 1])                       # origins above the floor
     rays[::50, 3 + (np.arange(len(rays[::50])) % 3)] = 0.0   # axis-parallel components (division by zero in the slabs)
     rays[::77, :3] *= 1e4                                 # origins far outside the scene bound (no culling)
-    renderer.set_accel({"bvh": rb.ACCEL_BVH, "cluster": rb.ACCEL_CLUSTER, "coop": rb.ACCEL_COOP, "fused": rb.ACCEL_FUSED}.get(accel, rb.ACCEL_BRUTE))
+    renderer.set_accel({"bvh": rb.ACCEL_BVH, "cluster": rb.ACCEL_CLUSTER, "coop": rb.ACCEL_COOP, "fused": rb.ACCEL_FUSED, "bvh2": rb.ACCEL_BVH_COOP}.get(accel, rb.ACCEL_BRUTE))
     try:
         renderer.new_frame(benchmark_scene.with_resolution(64, 36))
         ids_g, t_g = renderer.kat_trace(rays)
@@ -102,14 +102,14 @@ def test_trace_arbitrary_rays(rb, renderer, orc, benchmark_scene, accel):
             assert u32(np.float32(t)) == u32(t_g[i])
 
 
-@pytest.mark.parametrize("accel", ["brute", "bvh", "cluster", "coop", "fused"])
+@pytest.mark.parametrize("accel", ["brute", "bvh", "cluster", "coop", "fused", "bvh2"])
 @pytest.mark.parametrize("name", ["default", "benchmark"])
 def test_single_path_debug_mode(rb, orc, default_scene, benchmark_scene, name, accel):
     scene = (default_scene if name == "default" else benchmark_scene.with_resolution(480, 270))
     seed = 0xC0FFEE
     r = rb.Renderer(rb.RendererConfig(max_sample_count=4, max_bounces=12))
     r.set_seed(seed)
-    r.set_accel({"bvh": rb.ACCEL_BVH, "cluster": rb.ACCEL_CLUSTER, "coop": rb.ACCEL_COOP, "fused": rb.ACCEL_FUSED}.get(accel, rb.ACCEL_BRUTE))
+    r.set_accel({"bvh": rb.ACCEL_BVH, "cluster": rb.ACCEL_CLUSTER, "coop": rb.ACCEL_COOP, "fused": rb.ACCEL_FUSED, "bvh2": rb.ACCEL_BVH_COOP}.get(accel, rb.ACCEL_BRUTE))
     r.new_frame(scene)
     rng = np.random.default_rng(5)
     fields = ["position", "normal", "origin", "direction", "attenuation", "light"]
@@ -131,7 +131,7 @@ def test_single_path_debug_mode(rb, orc, default_scene, benchmark_scene, name, a
     r.close()
 
 
-@pytest.mark.parametrize("accel", ["brute", "bvh", "cluster", "coop", "fused"])
+@pytest.mark.parametrize("accel", ["brute", "bvh", "cluster", "coop", "fused", "bvh2"])
 @pytest.mark.parametrize("name,res,spp", [("default", (427, 240), 16), ("benchmark", (320, 180), 8)])
 def test_accumulator_bit_exact(rb, orc, default_scene, benchmark_scene, name, res, spp, accel):
     scene = (default_scene if name == "default" else benchmark_scene).with_resolution(*res)
@@ -139,7 +139,7 @@ def test_accumulator_bit_exact(rb, orc, default_scene, benchmark_scene, name, re
     acc_o = orc.render(scene, seed, 0, spp, 12, n_threads=orc.max_threads())
     r = rb.Renderer(rb.RendererConfig(max_sample_count=spp, max_bounces=12))
     r.set_seed(seed)
-    r.set_accel({"bvh": rb.ACCEL_BVH, "cluster": rb.ACCEL_CLUSTER, "coop": rb.ACCEL_COOP, "fused": rb.ACCEL_FUSED}.get(accel, rb.ACCEL_BRUTE))
+    r.set_accel({"bvh": rb.ACCEL_BVH, "cluster": rb.ACCEL_CLUSTER, "coop": rb.ACCEL_COOP, "fused": rb.ACCEL_FUSED, "bvh2": rb.ACCEL_BVH_COOP}.get(accel, rb.ACCEL_BRUTE))
     img = r.render_frame(scene)
     acc_g = r.read_accum()
     assert np.array_equal(u32(acc_o), u32(acc_g))
@@ -200,16 +200,18 @@ def test_bvh_config4_100k_objects(rb, orc):
     import synth_scenes as ss
     scene = ss.config4(100_000, 160, 90)
     ids_o, t_o = orc.first_hit(scene)
-    r = rb.Renderer(rb.RendererConfig(2, 12)); r.set_seed(3)          # ACCEL_AUTO -> BVH (n > threshold)
-    r.new_frame(scene)
-    ids_g, t_g = r.first_hit()
-    assert np.array_equal(ids_o, ids_g)
-    assert np.array_equal(u32(t_o), u32(t_g))
-    assert len(np.unique(ids_o)) > 3000
+    r = rb.Renderer(rb.RendererConfig(2, 12)); r.set_seed(3)          # ACCEL_AUTO -> cooperative hierarchy (n > threshold)
     small = scene.with_resolution(48, 27)
     want = orc.render(small, 3, 0, 2, 12, n_threads=orc.max_threads())
-    r.render_frame(small)
-    assert np.array_equal(u32(want), u32(r.read_accum()))
+    assert len(np.unique(ids_o)) > 3000
+    for accel in (rb.ACCEL_AUTO, rb.ACCEL_BVH):                       # warp-cooperative and per-lane traversal
+        r.set_accel(accel)
+        r.new_frame(scene)
+        ids_g, t_g = r.first_hit()
+        assert np.array_equal(ids_o, ids_g), accel
+        assert np.array_equal(u32(t_o), u32(t_g)), accel
+        r.render_frame(small)
+        assert np.array_equal(u32(want), u32(r.read_accum())), accel
     # the brute-force scan cannot hold this scene in shared memory: explicit request is an error, not a fallback
     r.set_accel(rb.ACCEL_BRUTE)
     with pytest.raises(rb.RaydarError) as e:
@@ -223,7 +225,7 @@ def test_bvh_config5_glass_metal_32_bounces(rb, orc):
     import synth_scenes as ss
     scene = ss.config5(192, 108)
     want = orc.render(scene, 9, 0, 2, 32, n_threads=orc.max_threads())
-    for accel in (rb.ACCEL_BRUTE, rb.ACCEL_BVH, rb.ACCEL_CLUSTER, rb.ACCEL_COOP, rb.ACCEL_FUSED):
+    for accel in (rb.ACCEL_BRUTE, rb.ACCEL_BVH, rb.ACCEL_CLUSTER, rb.ACCEL_COOP, rb.ACCEL_FUSED, rb.ACCEL_BVH_COOP):
         r = rb.Renderer(rb.RendererConfig(2, 32)); r.set_seed(9); r.set_accel(accel)
         r.render_frame(scene)
         assert np.array_equal(u32(want), u32(r.read_accum())), accel
