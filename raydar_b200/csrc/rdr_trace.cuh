@@ -443,6 +443,11 @@ RDR_HD void lane_init(LaneState &st, uint32_t *masks)
     st.h0.idx = -1; st.h0.t = 0.0f; st.hit = st.h0;
 }
 
+// The camera ray is set up once per pixel per launch (once per ~2000 trace iterations at 1024 spp) but is 240
+// instructions of exact divisions and square roots: kept out of line so that the hot loop stays compact in the
+// instruction cache.  Returns its result in registers.
+RDR_HD_NOINLINE v3 camera_ray_dir_cold(const Camera &cam, uint32_t x, uint32_t y) { return camera_ray_dir(cam, x, y); }
+
 // take ownership of `pixel` (acc = its current accumulator).  Afterwards either st.alive (the primary ray is
 // waiting to be traced) or the pixel is already finished (no samples / no bounces) and st.acc is final.
 RDR_HD void lane_start_pixel(const FrameParams &P, uint32_t pixel, f4 acc, LaneState &st)
@@ -460,7 +465,7 @@ RDR_HD void lane_start_pixel(const FrameParams &P, uint32_t pixel, f4 acc, LaneS
     }
     st.alive = P.sample_count > 0u;
     st.primary_pending = st.alive;
-    if (st.alive) st.cam_d = st.rd = camera_ray_dir(P.cam, pixel % P.cam.width, pixel / P.cam.width);
+    if (st.alive) st.cam_d = st.rd = camera_ray_dir_cold(P.cam, pixel % P.cam.width, pixel / P.cam.width);
 }
 
 // the traced hit of the lane's current ray arrives
