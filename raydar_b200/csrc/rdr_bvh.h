@@ -163,10 +163,12 @@ private:
 // Same boxes and the same conservative rules as BvhBuilder, different shape and storage:
 //   root   <= 32 entries, returned as 16 TopPair records (FFMA2 operand order) that travel in the kernel parameters,
 //          plus their payloads;
-//   node   8 entries = 4 pairs (A, B) x 4 quads + 1 header quad (17 quads, 272 B):
-//            (cxA, cxB, cyA, cyB) (czA, czB, exA, exB) (eyA, eyB, ezA, ezB) (sphereA, sphereB, payloadA, payloadB)
-//          header: (primitive mask, cube mask, valid mask, 0) over the 8 entries, bit = entry
-//   payload as in BvhBuilder: bit 31 = primitive (else child node index), bit 30 = cube, low 30 bits = index.
+//   node   8 entries = 4 pairs (A, B), 16 quads (256 B, one or two 128-byte lines), QUAD-MAJOR: quad i of pair p is
+//          quad 4 i + p, so that the 4 lanes that share a node read 64 contiguous bytes per load instruction:
+//            i = 0: (cxA, cxB, cyA, cyB)   1: (czA, czB, exA, exB)   2: (eyA, eyB, ezA, ezB)
+//            i = 3: (sphereA, sphereB, payloadA, payloadB)
+//   payload as in BvhBuilder: bit 31 = primitive (else child node index), bit 30 = cube, low 30 bits = index;
+//   0xffffffff = unused entry (its box has e = -1).
 struct Bvh2Root {
     float cx[32], cy[32], cz[32], ex[32], ey[32], ez[32], sphere[32];
     uint32_t payload[32];
@@ -175,7 +177,7 @@ struct Bvh2Root {
 
 class Bvh2Builder {
 public:
-    static constexpr int NODE_FLOATS = 68;
+    static constexpr int NODE_FLOATS = 64;
     std::vector<float> nodes;
     Bvh2Root root;
     int max_depth = 0;
@@ -285,25 +287,21 @@ private:
     void write_node(uint32_t node, const std::vector<Entry> &entries)
     {
         float *p = nodes.data() + (size_t)node * NODE_FLOATS;
-        uint32_t prim_mask = 0u, cube_mask = 0u, valid_mask = 0u;
         for (int k = 0; k < BVH_WIDTH; ++k) {
-            float *q = p + 16 * (k >> 1);
-            const int h = k & 1;
+            const int pair = k >> 1, h = k & 1;
+            auto quad = [&](int i) { return p + 4 * (4 * i + pair); };
             if (k >= (int)entries.size()) {
-                q[6 + h] = q[8 + h] = q[10 + h] = -1.0f;           // unused: e = -1 (and masked out by valid_mask)
-                const uint32_t none = 0xffffffffu; memcpy(&q[14 + h], &none, 4);
+                quad(1)[2 + h] = quad(2)[0 + h] = quad(2)[2 + h] = -1.0f;      // unused: e = -1, payload = 0xffffffff
+                const uint32_t none = 0xffffffffu; memcpy(&quad(3)[2 + h], &none, 4);
                 continue;
             }
             const Entry &e = entries[k];
-            q[0 + h] = e.box.c[0]; q[2 + h] = e.box.c[1]; q[4 + h] = e.box.c[2];
-            q[6 + h] = e.box.e[0]; q[8 + h] = e.box.e[1]; q[10 + h] = e.box.e[2];
-            q[12 + h] = e.box.sphere ? 1.0f : 0.0f;
-            memcpy(&q[14 + h], &e.payload, 4);
-            valid_mask |= 1u << k;
-            if (e.payload & BVH_PRIM_BIT) prim_mask |= 1u << k;
-            if ((e.payload & BVH_PRIM_BIT) && (e.payload & BVH_CUBE_BIT)) cube_mask |= 1u << k;
+            quad(0)[0 + h] = e.box.c[0]; quad(0)[2 + h] = e.box.c[1];
+            quad(1)[0 + h] = e.box.c[2]; quad(1)[2 + h] = e.box.e[0];
+            quad(2)[0 + h] = e.box.e[1]; quad(2)[2 + h] = e.box.e[2];
+            quad(3)[0 + h] = e.box.sphere ? 1.0f : 0.0f;
+            memcpy(&quad(3)[2 + h], &e.payload, 4);
         }
-        memcpy(&p[64], &prim_mask, 4); memcpy(&p[65], &cube_mask, 4); memcpy(&p[66], &valid_mask, 4);
     }
 };
 

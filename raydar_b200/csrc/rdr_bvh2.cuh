@@ -6,17 +6,19 @@
 // Here the WARP owns one stack of (ray, node) tasks in shared memory and all 32 lanes work on it together:
 //   A0   every lane tests ITS ray against the <= 32 root entries (constant bank, FFMA2 pairs: top_scan of rdr_fused.cuh);
 //        the root is then consumed in chunks of 8 entries exactly like a node;
-//   N    pop up to 32 tasks from the top of the stack, one per lane -- usually some OTHER lane's ray, whose slab
-//        constants come by indexed shuffle -- load the node (16 quads + header, LDG.128) and test its 8 entries as
-//        4 FFMA2 pairs, bounded by the ray's best exact t so far (read from its winner key);
-//   P    the 8-bit hit mask is split with the node's masks into child nodes, spheres and cubes; ONE packed shuffle
-//        prefix sum (3 x 10 bits) gives every lane its positions on the stack and in the two survivor lists;
+//   N    pop up to 8 tasks from the top of the stack, FOUR LANES PER TASK -- usually some other lane's ray, whose slab
+//        constants come by indexed shuffle; each lane loads one pair of the node's entries (quad-major node: the 4 lanes
+//        read 64 contiguous bytes per LDG.128) and tests it with FFMA2, bounded by the ray's best exact t so far;
+//   P    the hit entries are split by payload bits into child nodes, spheres and cubes; ONE packed shuffle prefix sum
+//        (3 x 10 bits) gives every lane its positions on the stack and in the two survivor lists;
 //   E    full groups of 32 survivors (and, when the stack is empty, the rest) get the exact, reference-ordered test, one
 //        per lane, folded into the owner's winner with a 64-bit atomicMin on the (t, original index) key.
 // LIFO order makes the warp go depth-first, so hits arrive early and prune the rest (a task whose node cannot beat the
 // ray's best is simply expanded to nothing).  The stack cannot overflow: the root pushes at most 32 x 32 tasks, a round
-// pops P <= 32 tasks and pushes at most 8 P, and P is throttled so that the stack stays below its soft limit; above
+// pops P <= 8 tasks and pushes at most 8 P, and P is throttled so that the stack stays below its soft limit; above
 // it P = 1, i.e. plain depth-first descent of one task, which adds at most 7 entries per level (8 levels).
+// (One node per LANE -- 32 tasks per round, 17 scattered LDG.128 per lane -- was measured first: 77 % L1 data-pipe
+// utilisation, 24 % issue utilisation, profiles/ncu_r01r_config4_bvh2_summary.txt.)
 // The winner is decided by the exact tests and the (t, index) rule only, exactly as in every other search.
 // Device-only; must be entered by all 32 lanes of a warp.  Needs lay.bvh2_ok.
 #pragma once
@@ -66,6 +68,39 @@ __device__ __forceinline__ void bvh2_exact(const f4 *obj_geom, Bvh2Warp ws, uint
     __syncwarp();
 }
 
+// P: the entries this lane found hit (bit k of `bits` = entry pay[k]) go to the warp's stack (child nodes) or survivor
+// lists (spheres, cubes), by payload bits; ONE packed prefix sum (3 x 10 bits) gives every lane its positions.
+// Unrolled and predicated: no dependent loads, no divergent loop.  n_t / n_s / n_c: list lengths, warp-uniform.
+template <int N>
+__device__ __forceinline__ void bvh2_emit(Bvh2Warp ws, uint32_t lane, uint32_t owner, uint32_t bits, const uint32_t (&pay)[N],
+                                          uint32_t &n_t, uint32_t &n_s, uint32_t &n_c)
+{
+    uint32_t nb = 0u, cb = 0u;                                    // child-node bits, cube bits
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        nb |= ((pay[k] >> 31) ^ 1u) << k;
+        cb |= (((pay[k] >> 30) & 1u) & (pay[k] >> 31)) << k;
+    }
+    nb &= bits; cb &= bits;
+    const uint32_t packed = __popc(nb) | (__popc(bits ^ nb ^ cb) << 10) | (__popc(cb) << 20);
+    const uint32_t incl = warp_scan_incl(packed, lane);
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t excl = incl - packed;
+    // the three lists are one array (stack | surv_s | surv_c): a position is all that is selected per entry
+    uint32_t pn = n_t + (excl & 1023u), ps = BVH2_STACK_CAP + n_s + ((excl >> 10) & 1023u), pc = BVH2_STACK_CAP + BVH2_SURV_CAP + n_c + (excl >> 20);
+    const uint32_t tag = owner << 27;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        if ((bits >> k) & 1u) {
+            const bool node = (nb >> k) & 1u, cube = (cb >> k) & 1u;
+            ws.stack[node ? pn : (cube ? pc : ps)] = tag | (pay[k] & 0x07ffffffu);
+            pn += node ? 1u : 0u; pc += (!node && cube) ? 1u : 0u; ps += (!node && !cube) ? 1u : 0u;
+        }
+    }
+    n_t += total & 1023u; n_s += (total >> 10) & 1023u; n_c += total >> 20;
+    __syncwarp();
+}
+
 __device__ __forceinline__ Hit trace_bvh2(const SceneView &S, const FrameParams &P, Bvh2Warp ws, bool alive, v3 o, v3 d)
 {
     const uint32_t FULL = 0xffffffffu;
@@ -78,73 +113,46 @@ __device__ __forceinline__ Hit trace_bvh2(const SceneView &S, const FrameParams 
 
     const f4 *nodes = reinterpret_cast<const f4 *>(P.blob + P.lay.off_nodes2);
     const uint32_t root_chunks = (P.lay.bvh2_root + 7u) >> 3;
+    const uint32_t sub = lane & 3u, grp = lane >> 2;              // node stage: 4 lanes per task, one pair of entries per lane
     uint32_t n_t = 0u, n_s = 0u, n_c = 0u, chunk = 0u;            // stack / survivor list lengths: warp-uniform
 #pragma unroll 1
     for (;;) {
         const bool rooting = chunk < root_chunks;
         const bool last = !rooting && n_t == 0u;
-        if (!last) {
-            uint32_t bits, prim_mask, cube_mask, owner;
-            uint32_t pay[8];                                      // payloads of the 8 entries (registers: the emit loop is unrolled)
-            if (rooting) {
-                // ---- the root, 8 entries at a time: the lane's own ray, masks and payloads from the kernel parameters ----
-                bits = (m >> (8u * chunk)) & 0xffu;
-                prim_mask = (P.top.prim_mask >> (8u * chunk)) & 0xffu;
-                cube_mask = (P.top.cube_mask >> (8u * chunk)) & 0xffu;
-                owner = lane;
+        if (rooting) {
+            // ---- the root, 8 entries at a time: the lane's own ray, payloads from the kernel parameters ----
+            uint32_t pay[8];
 #pragma unroll
-                for (uint32_t k = 0; k < 8u; ++k) pay[k] = P.top.payload[8u * chunk + k];
-                ++chunk;
-            } else {
-                // ---- N: pop up to 32 tasks (throttled near the soft limit), test the node's 8 entries ----
-                uint32_t pop = (BVH2_STACK_SOFT > n_t ? BVH2_STACK_SOFT - n_t : 0u) / 7u;
-                pop = pop < 1u ? 1u : (pop > 32u ? 32u : pop);
-                if (pop > n_t) pop = n_t;
-                const bool has = lane < pop;
-                const uint32_t task = has ? ws.stack[n_t - 1u - lane] : (lane << 27);
-                n_t -= pop;
-                __syncwarp();                                     // the popped slots are overwritten by the pushes below
-                owner = task >> 27;
-                const float qx = __shfl_sync(FULL, R.rx, owner), qy = __shfl_sync(FULL, R.ry, owner), qz = __shfl_sync(FULL, R.rz, owner);
-                const float mx = __shfl_sync(FULL, R.nx, owner), my = __shfl_sync(FULL, R.ny, owner), mz = __shfl_sync(FULL, R.nz, owner);
-                const f32x2 rho2 = bc2(__shfl_sync(FULL, R.rho, owner));
-                // best exact t of the owner so far: high word of its key; ~0 (no hit) and a NaN hit read as NaN = no bound
-                const float best = __uint_as_float(reinterpret_cast<const uint32_t *>(ws.best + owner)[1]);
-                const f4 *nd = nodes + 17u * (size_t)(task & 0x07ffffffu);
-                const f4 hdr = nd[16];
-                bits = 0u;
-#pragma unroll
-                for (uint32_t p = 0; p < 4u; ++p) {
-                    const f4 q0 = nd[4u * p], q1 = nd[4u * p + 1u], q2 = nd[4u * p + 2u], q3 = nd[4u * p + 3u];
-                    const f32x2 sp = pk2(q3.x, q3.y);
-                    const f32x2 ex = fma2(sp, rho2, pk2(q1.z, q1.w)), ey = fma2(sp, rho2, pk2(q2.x, q2.y)), ez = fma2(sp, rho2, pk2(q2.z, q2.w));
-                    bits |= slab_pair<true>(pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), ex, ey, ez, qx, qy, qz, mx, my, mz, best) << (2u * p);
-                    pay[2u * p] = __float_as_uint(q3.z); pay[2u * p + 1u] = __float_as_uint(q3.w);
-                }
-                prim_mask = __float_as_uint(hdr.x); cube_mask = __float_as_uint(hdr.y);
-                bits &= __float_as_uint(hdr.z);
-                if (!has) bits = 0u;
-            }
-            // ---- P: child nodes -> stack, primitives -> survivor lists (one packed prefix sum for the three counts) ----
-            const uint32_t pb = bits & prim_mask, nb = bits ^ pb, cb = pb & cube_mask;
-            const uint32_t packed = __popc(nb) | (__popc(pb ^ cb) << 10) | (__popc(cb) << 20);
-            const uint32_t incl = warp_scan_incl(packed, lane);
-            const uint32_t total = __shfl_sync(FULL, incl, 31);
-            const uint32_t excl = incl - packed;
-            // the three lists are one array (stack | surv_s | surv_c): a position is all that is selected per entry
-            uint32_t pn = n_t + (excl & 1023u), ps = BVH2_STACK_CAP + n_s + ((excl >> 10) & 1023u), pc = BVH2_STACK_CAP + BVH2_SURV_CAP + n_c + (excl >> 20);
-            const uint32_t tag = owner << 27;
-#pragma unroll
-            for (uint32_t k = 0; k < 8u; ++k) {                   // unrolled + predicated: no dependent loads, no divergent loop
-                if ((bits >> k) & 1u) {
-                    const bool node = (nb >> k) & 1u, cube = (cb >> k) & 1u;
-                    const uint32_t pos = node ? pn : (cube ? pc : ps);
-                    ws.stack[pos] = tag | (pay[k] & 0x07ffffffu);
-                    pn += node ? 1u : 0u; pc += (!node && cube) ? 1u : 0u; ps += (!node && !cube) ? 1u : 0u;
-                }
-            }
-            n_t += total & 1023u; n_s += (total >> 10) & 1023u; n_c += total >> 20;
-            __syncwarp();
+            for (uint32_t k = 0; k < 8u; ++k) pay[k] = P.top.payload[8u * chunk + k];
+            bvh2_emit<8>(ws, lane, lane, (m >> (8u * chunk)) & 0xffu, pay, n_t, n_s, n_c);
+            ++chunk;
+        } else if (!last) {
+            // ---- N: pop up to 8 tasks (throttled near the soft limit); the 4 lanes of a group test one pair each.  The
+            //      node is quad-major, so a group reads 64 contiguous bytes per load: 8 wavefronts per LDG.128 instead of the
+            //      32 of one-node-per-lane (the traversal is bound by the L1 data pipe) ----
+            uint32_t pop = (BVH2_STACK_SOFT > n_t ? BVH2_STACK_SOFT - n_t : 0u) / 7u;
+            pop = pop < 1u ? 1u : (pop > 8u ? 8u : pop);
+            if (pop > n_t) pop = n_t;
+            const bool has = grp < pop;
+            const uint32_t task = has ? ws.stack[n_t - 1u - grp] : (lane << 27);
+            n_t -= pop;
+            __syncwarp();                                         // the popped slots are overwritten by the pushes below
+            const uint32_t owner = task >> 27;
+            const float qx = __shfl_sync(FULL, R.rx, owner), qy = __shfl_sync(FULL, R.ry, owner), qz = __shfl_sync(FULL, R.rz, owner);
+            const float mx = __shfl_sync(FULL, R.nx, owner), my = __shfl_sync(FULL, R.ny, owner), mz = __shfl_sync(FULL, R.nz, owner);
+            const f32x2 rho2 = bc2(__shfl_sync(FULL, R.rho, owner));
+            // best exact t of the owner so far: high word of its key; ~0 (no hit) and a NaN hit read as NaN = no bound
+            const float best = __uint_as_float(reinterpret_cast<const uint32_t *>(ws.best + owner)[1]);
+            const f4 *nd = nodes + 16u * (size_t)(task & 0x07ffffffu) + sub;
+            const f4 q0 = nd[0], q1 = nd[4], q2 = nd[8], q3 = nd[12];
+            const f32x2 sp = pk2(q3.x, q3.y);
+            const f32x2 ex = fma2(sp, rho2, pk2(q1.z, q1.w)), ey = fma2(sp, rho2, pk2(q2.x, q2.y)), ez = fma2(sp, rho2, pk2(q2.z, q2.w));
+            uint32_t bits = slab_pair<true>(pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), ex, ey, ez, qx, qy, qz, mx, my, mz, best);
+            uint32_t pay[2] = {__float_as_uint(q3.z), __float_as_uint(q3.w)};
+            if (pay[0] == 0xffffffffu) bits &= ~1u;              // unused entries (a ray that skips the cull passes every box)
+            if (pay[1] == 0xffffffffu) bits &= ~2u;
+            if (!has) bits = 0u;
+            bvh2_emit<2>(ws, lane, owner, bits, pay, n_t, n_s, n_c);
         }
         // ---- E: exact tests on full groups of 32 survivors, and on the rest once the stack is empty ----
 #pragma unroll 1

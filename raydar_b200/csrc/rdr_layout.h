@@ -52,13 +52,13 @@ namespace rdr {
 //   nodes        f4[16*n_nodes]   8 entries x 2 quads per node (rdr_bvh.h), per-lane traversal
 //   obj_geom     f4[n]
 //   material     f4[3*n]
-//   nodes2       f4[17*n_nodes2]  the same primitives as a pair-packed hierarchy for the warp-cooperative traversal
+//   nodes2       f4[16*n_nodes2]  the same primitives as a pair-packed hierarchy for the warp-cooperative traversal
 //                                 (rdr_bvh2.cuh); its <= 32 root entries travel in FrameParams::top
 // and is either staged the same way (small scenes) or read in place from global memory / L2 (large scenes).
 struct SceneLayout {
     uint32_t mode;                       // 0 = brute-force scan lists, 1 = BVH
     uint32_t n_nodes, off_nodes;
-    uint32_t bvh2_ok, bvh2_root, n_nodes2, off_nodes2;   // pair-packed hierarchy of the cooperative traversal (17 quads per node)
+    uint32_t bvh2_ok, bvh2_root, n_nodes2, off_nodes2;   // pair-packed hierarchy of the cooperative traversal (16 quads per node)
     uint32_t n_objects, n_spheres, n_cubes;
     uint32_t ns_pad, nc_pad;
     uint32_t off_sphere_cull, off_cube_cull, off_sphere_geom, off_cube_geom;

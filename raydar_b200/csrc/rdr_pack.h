@@ -95,12 +95,12 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
             L.off_nodes = (uint32_t)off; off += 256ull * L.n_nodes;
             L.off_obj_geom = (uint32_t)off; off += 16ull * n;
             L.off_material = (uint32_t)off; off += 48ull * n;
-            L.off_nodes2 = (uint32_t)off; off += 272ull * L.n_nodes2;
+            L.off_nodes2 = (uint32_t)off; off += 256ull * L.n_nodes2;
             if (off > 0xfffffff0ull) { err = "scene too large"; return RDR_ERR_INVALID; }
             L.blob_bytes = std::max(16u, round_up_u32((uint32_t)off, 16u));
             blob.assign(L.blob_bytes, 0);
             memcpy(blob.data() + L.off_nodes, builder.nodes.data(), 256ull * L.n_nodes);
-            if (L.n_nodes2) memcpy(blob.data() + L.off_nodes2, builder2.nodes.data(), 272ull * L.n_nodes2);
+            if (L.n_nodes2) memcpy(blob.data() + L.off_nodes2, builder2.nodes.data(), 256ull * L.n_nodes2);
             if (ok2) {
                 const Bvh2Root &R = builder2.root;
                 for (uint32_t k = 0; k < FUSED_MAX_TOP; ++k) {

@@ -42,6 +42,16 @@ struct Packed {
     }
 };
 
+// entry k of a quad-major pair-packed node (rdr_bvh.h) in the two-quad entry form of bvh_entry_may_hit
+void node2_entry(const float *p, int k, f4 &q0, f4 &q1, uint32_t &payload)
+{
+    const int pair = k >> 1, h = k & 1;
+    auto quad = [&](int i) { return p + 4 * (4 * i + pair); };
+    q0.x = quad(0)[0 + h]; q0.y = quad(0)[2 + h]; q0.z = quad(1)[0 + h]; q0.w = quad(1)[2 + h];
+    q1.x = quad(2)[0 + h]; q1.y = quad(2)[2 + h]; q1.z = 0.0f; q1.w = quad(3)[0 + h];
+    memcpy(&payload, &quad(3)[2 + h], 4);
+}
+
 // Scalar walk of the pair-packed hierarchy of the warp-cooperative traversal (rdr_bvh2.cuh runs on the device only):
 // checks what the host can check -- the builder's boxes, masks and payloads, and the root in the kernel parameters --
 // with the same conservative entry test and the same exact tests / winner rule.
@@ -78,15 +88,12 @@ Hit trace_bvh2_scalar(const Packed &pk, v3 o, v3 d, TraceStats *st)
         const uint32_t node = stack.back(); stack.pop_back();
         if (st) st->nodes_visited++;
         if (node >= pk.P.lay.n_nodes2) { best.idx = -2; return best; }
-        const float *p = nodes + 68 * (size_t)node;
-        uint32_t pm, cm, vm; memcpy(&pm, p + 64, 4); memcpy(&cm, p + 65, 4); memcpy(&vm, p + 66, 4);
+        const float *p = nodes + 64 * (size_t)node;
         for (int k = 0; k < 8; ++k) {
-            if (!((vm >> k) & 1u)) continue;
-            const float *q = p + 16 * (k >> 1); const int h = k & 1;
-            f4 q0, q1; q0.x = q[0 + h]; q0.y = q[2 + h]; q0.z = q[4 + h]; q0.w = q[6 + h];
-            q1.x = q[8 + h]; q1.y = q[10 + h]; q1.z = 0.0f; q1.w = q[12 + h];
-            uint32_t payload; memcpy(&payload, q + 14 + h, 4);
-            visit(q0, q1, payload, (pm >> k) & 1u, (cm >> k) & 1u);
+            f4 q0, q1; uint32_t payload;
+            node2_entry(p, k, q0, q1, payload);
+            if (payload == 0xffffffffu) continue;
+            visit(q0, q1, payload, (payload & 0x80000000u) != 0u, (payload & 0x40000000u) != 0u);
         }
     }
     return best;
@@ -337,17 +344,14 @@ int hs_bvh2_warp_sim(const RdrSceneFlat *sc, uint32_t flush_at, uint32_t order_c
                 for (size_t i = 0; i < pop; ++i) {                  // lane i takes stack[top - i]
                     const Task t = popped[pop - 1 - i];
                     visits += 1;
-                    const float *pn = nodes + 68 * (size_t)t.node;
-                    uint32_t pm, vm; memcpy(&pm, pn + 64, 4); memcpy(&vm, pn + 66, 4);
+                    const float *pn = nodes + 64 * (size_t)t.node;
                     std::vector<Child> ch;
                     for (int k = 0; k < 8; ++k) {
-                        if (!((vm >> k) & 1u)) continue;
-                        const float *q = pn + 16 * (k >> 1); const int h = k & 1;
-                        f4 q0, q1; q0.x = q[0 + h]; q0.y = q[2 + h]; q0.z = q[4 + h]; q0.w = q[6 + h];
-                        q1.x = q[8 + h]; q1.y = q[10 + h]; q1.z = 0.0f; q1.w = q[12 + h];
-                        uint32_t payload; memcpy(&payload, q + 14 + h, 4);
+                        f4 q0, q1; uint32_t payload;
+                        node2_entry(pn, k, q0, q1, payload);
+                        if (payload == 0xffffffffu) continue;
                         float tn;
-                        if (bvh_entry_may_hit(rb[t.owner], q0, q1, prune((int)t.owner), &tn)) ch.push_back({tn, payload, ((pm >> k) & 1u) != 0u});
+                        if (bvh_entry_may_hit(rb[t.owner], q0, q1, prune((int)t.owner), &tn)) ch.push_back({tn, payload, (payload & 0x80000000u) != 0u});
                     }
                     emit((int)t.owner, ch);
                 }
