@@ -130,7 +130,7 @@ __device__ __forceinline__ Hit trace_bvh2(const SceneView &S, const FrameParams 
             // ---- N: pop up to 8 tasks (throttled near the soft limit); the 4 lanes of a group test one pair each.  The
             //      node is quad-major, so a group reads 64 contiguous bytes per load: 8 wavefronts per LDG.128 instead of the
             //      32 of one-node-per-lane (the traversal is bound by the L1 data pipe) ----
-            uint32_t pop = (BVH2_STACK_SOFT > n_t ? BVH2_STACK_SOFT - n_t : 0u) / 7u;
+            uint32_t pop = (BVH2_STACK_SOFT > n_t ? BVH2_STACK_SOFT - n_t : 0u) >> 3;      // <= room / 7
             pop = pop < 1u ? 1u : (pop > 8u ? 8u : pop);
             if (pop > n_t) pop = n_t;
             const bool has = grp < pop;

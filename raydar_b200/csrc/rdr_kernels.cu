@@ -287,9 +287,18 @@ static int fused_cta_config()
     if (cfg < 0) { const char *e = getenv("RDR_FUSED_CTA"); cfg = e ? atoi(e) : 3; if (cfg < 0 || cfg > 3) cfg = 3; }
     return cfg;
 }
+// CTA shape of the cooperative hierarchy kernel.  Measured on config 4 (profiles/sweep_r01u.txt, Msamples/s): 640 threads
+// @ 94 registers (no spills) 143.7, 768 @ 80 140.7, 512 @ 94 129.5.  RDR_BVH2_CTA (experiments): 0 = 768, 1 = 640, 2 = 512.
+static int bvh2_cta_config()
+{
+    static int cfg = -1;
+    if (cfg < 0) { const char *e = getenv("RDR_BVH2_CTA"); cfg = e ? atoi(e) : 1; if (cfg < 0 || cfg > 2) cfg = 1; }
+    return cfg;
+}
 static uint32_t render_block(int mode)
 {
     if (mode < 5) return RDR_BLOCK;
+    if (mode == 7) return bvh2_cta_config() == 1 ? 640u : (bvh2_cta_config() == 2 ? 512u : 768u);
     if (mode >= 6) return 768u;
     switch (fused_cta_config()) { case 1: return 896u; case 2: return 1024u; case 3: return 768u; default: return RDR_BLOCK; }
 }
@@ -297,7 +306,13 @@ static uint32_t render_block(int mode)
 // calls F(kernel) with the render kernel instantiation for `mode`
 #define RDR_RENDER_DISPATCH(mode, F)                                                                  \
     do {                                                                                              \
-        if ((mode) == 7) { F((render_kernel<7, 768, 1>)); }                                           \
+        if ((mode) == 7) {                                                                            \
+            switch (bvh2_cta_config()) {                                                              \
+            case 1: F((render_kernel<7, 640, 1>)); break;                                             \
+            case 2: F((render_kernel<7, 512, 1>)); break;                                             \
+            default: F((render_kernel<7, 768, 1>)); break;                                            \
+            }                                                                                         \
+        }                                                                                             \
         else if ((mode) == 6) { F((render_kernel<6, 768, 1>)); }                                      \
         else if ((mode) == 5) {                                                                       \
             switch (fused_cta_config()) {                                                             \
