@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0x5EED)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--progressive", action="store_true",
+                    help="time the interactive path instead: render_sample() = one 1-spp launch + resolve + image read-back per call")
     ap.add_argument("--accel", default="auto", choices=["auto", "brute", "bvh", "cluster", "coop", "fused", "bvh2"], help="nearest-hit search of the CUDA backend")
     return ap.parse_args()
 
@@ -88,6 +90,16 @@ def cpu_run(a, target_seconds, threads=None):
     samples = a.width * a.height * spp
     return samples / dt / 1e6, f"{a.width}x{a.height} x {spp} spp ({samples / 1e6:.1f} Msamples, {dt:.1f} s)", \
         st.trace_calls / max(1, st.samples), threads, scene
+
+
+def cpu_single_thread(a):
+    from oracle import orc
+    scene = orc.load_rscn(a.scene).with_resolution(max(1, a.width // 2), max(1, a.height // 2))
+    t0 = time.perf_counter()
+    orc.render(scene, a.seed, 0, 1, a.bounces, n_threads=1)
+    dt = time.perf_counter() - t0
+    n = scene.width * scene.height
+    return {"value": n / dt / 1e6, "unit": UNIT, "cores": 1, "sample": f"{scene.width}x{scene.height} x 1 spp ({dt:.1f} s)"}
 
 
 def run_reference(a):
@@ -232,6 +244,13 @@ def run_b200(a):
         torch.cuda.synchronize()
         return r.resolve(a.spp * world) if rank == 0 else None
 
+    if a.progressive:
+        run_progressive(a, r, flat, rank)
+        if world > 1:
+            dist.destroy_process_group()
+        r.close()
+        return
+
     for _ in range(a.warmup):
         step_resident()
     clocks = ClockSampler(local)
@@ -289,6 +308,8 @@ def run_b200(a):
         if not a.no_cpu_baseline and world == 1:
             v, sample, traces_per_sample, cores, _ = cpu_run(a, a.cpu_seconds)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            # the reference's CPU backend is single-threaded (cpu.rs:198): the same port on ONE core, on a quarter-size frame
+            cpu["single_thread"] = cpu_single_thread(a)
         n_sph = int((np.ctypeslib.as_array(flat.kind, (flat.n_objects,)) == rb.SPHERE).sum())
         n_cub = flat.n_objects - n_sph
         # scenes whose trace count is unknown (no CPU leg in this run) and scenes traversed through the BVH have no
@@ -315,6 +336,31 @@ def run_b200(a):
     if world > 1:
         dist.destroy_process_group()
     r.close()
+
+
+def run_progressive(a, r, flat, rank):
+    """The editor's loop (raydar_editor.rs:95-115): new_frame, then render_sample() until it returns None; every call
+    is one 1-spp kernel launch, the resolve kernel and the RGBA8 read-back.  Reports the mean latency per call."""
+    import torch
+    n_calls = min(a.spp, 256)
+    r.set_max_sample_count(n_calls)
+    img = torch.empty((a.height, a.width, 4), dtype=torch.uint8, pin_memory=True).numpy()     # one pinned image buffer, reused
+    lat = []
+    for rep in range(a.warmup + a.steps):
+        r.new_frame(flat)
+        t0 = time.perf_counter()
+        calls = 0
+        while r.render_sample(flat, out=img) is not None:
+            calls += 1
+        dt = time.perf_counter() - t0
+        if rep >= a.warmup:
+            lat.append(dt / max(1, calls))
+    if rank == 0:
+        ms = float(np.mean(lat)) * 1e3
+        print(json.dumps({"metric": "ms per render_sample() call (1 spp + resolve + read-back)", "value": ms, "unit": "ms",
+                          "higher_is_better": False, "calls_per_frame": n_calls, "steps": a.steps, "warmup": a.warmup,
+                          "Msamples/s": a.width * a.height / (ms * 1e-3) / 1e6,
+                          "config": {"workload": workload_name(a).replace(f"{a.spp} spp", "1 spp per call"), "accel": a.accel}}))
 
 
 def ncu_traffic():

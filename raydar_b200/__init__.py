@@ -268,15 +268,18 @@ class Renderer:
         _check(self._L.rdr_new_frame(self._h, C.byref(f)), self._h)
         self._shape = (f.height, f.width)
 
-    def render_sample(self, scene=None):
+    def render_sample(self, scene=None, out=None):
         """Returns the resolved image after one more sample, or None once sample_count >= max_sample_count.
         Like the reference (cpu.rs:142-158) the scene argument is only used for its resolution: the frame
-        was snapshotted by new_frame."""
+        was snapshotted by new_frame.  out: optional (H, W, 4) uint8 array to receive the image (an interactive
+        caller reuses one buffer, ideally pinned, instead of allocating 8 MB per call)."""
         if self._shape is None:
             if scene is None:
                 raise RaydarError(ERR_INVALID, "render_sample before new_frame")
             self.new_frame(scene)
-        img = np.empty((*self._shape, 4), np.uint8)
+        img = out if out is not None else np.empty((*self._shape, 4), np.uint8)
+        if img.shape != (*self._shape, 4) or img.dtype != np.uint8 or not img.flags["C_CONTIGUOUS"]:
+            raise RaydarError(ERR_INVALID, "out must be a C-contiguous (H, W, 4) uint8 array")
         produced = C.c_int(0)
         _check(self._L.rdr_render_sample(self._h, img.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(produced)), self._h)
         return img if produced.value else None
