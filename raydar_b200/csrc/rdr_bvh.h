@@ -173,6 +173,11 @@ struct Bvh2Root {
     float cx[32], cy[32], cz[32], ex[32], ey[32], ez[32], sphere[32];
     uint32_t payload[32];
     uint32_t n = 0;
+    // Front-to-back order of the root's child nodes.  The root groups come from recursive median splits, so for a ray
+    // direction octant (bit 0/1/2 = d.x/d.y/d.z negative) the near-to-far order is the in-order walk of the split tree
+    // with the near side of every split first -- 8 fixed permutations, no per-ray sorting:
+    uint64_t rank8[32];                  // bits [5 oct, 5 oct + 5): rank of entry k in octant oct's order
+    uint32_t node_by_rank[8][32];        // child node of the entry with that rank (0xffffffff: not a child node)
 };
 
 class Bvh2Builder {
@@ -191,8 +196,24 @@ public:
         for (size_t i = 0; i < order_.size(); ++i) order_[i] = (uint32_t)i;
         if (prims_.empty()) return true;
         std::vector<Entry> entries;
-        make_entries(0u, (uint32_t)order_.size(), 32, 4, 1, entries);
+        std::vector<std::vector<int>> order;
+        make_entries(0u, (uint32_t)order_.size(), 32, 4, 1, entries, &order);
         root.n = (uint32_t)entries.size();
+        for (int k = 0; k < 32; ++k) root.rank8[k] = 0;
+        for (int oct = 0; oct < 8; ++oct) {
+            for (int i = 0; i < 32; ++i) root.node_by_rank[oct][i] = 0xffffffffu;
+            // entries the split order does not cover (direct primitives, or everything when the root holds <= 32
+            // primitives) take the remaining ranks; they are primitives, their order does not matter
+            std::vector<int> seq = order.size() == 8 ? order[(size_t)oct] : std::vector<int>();
+            std::vector<bool> seen(entries.size(), false);
+            for (int k : seq) seen[(size_t)k] = true;
+            for (size_t k = 0; k < entries.size(); ++k) if (!seen[k]) seq.push_back((int)k);
+            for (size_t i = 0; i < seq.size(); ++i) {
+                const int k = seq[i];
+                root.rank8[k] |= (uint64_t)i << (5 * oct);
+                if (!(entries[(size_t)k].payload & BVH_PRIM_BIT)) root.node_by_rank[oct][i] = entries[(size_t)k].payload;
+            }
+        }
         for (uint32_t k = 0; k < root.n; ++k) {
             const Entry &e = entries[k];
             root.cx[k] = e.box.c[0]; root.cy[k] = e.box.c[1]; root.cz[k] = e.box.c[2];
@@ -230,9 +251,12 @@ private:
         return box;
     }
 
-    void split(uint32_t b, uint32_t e, int k, std::vector<std::pair<uint32_t, uint32_t>> &out)
+    struct SplitNode { int axis, left, right; };       // children: >= 0 split node, < 0 group -(g + 1)
+
+    // returns the id of the subtree covering [b, e): a split node, or -(group index + 1)
+    int split(uint32_t b, uint32_t e, int k, std::vector<std::pair<uint32_t, uint32_t>> &out, std::vector<SplitNode> *tree = nullptr)
     {
-        if (k <= 1 || e - b <= 1) { out.emplace_back(b, e); return; }
+        if (k <= 1 || e - b <= 1) { out.emplace_back(b, e); return -(int)out.size(); }
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (uint32_t i = b; i < e; ++i)
             for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], prims_[order_[i]].c[a]); hi[a] = std::max(hi[a], prims_[order_[i]].c[a]); }
@@ -244,15 +268,30 @@ private:
         mid = std::max(b + 1, std::min(e - 1, mid));
         std::nth_element(order_.begin() + b, order_.begin() + mid, order_.begin() + e,
                          [&](uint32_t x, uint32_t y) { return prims_[x].c[axis] < prims_[y].c[axis]; });
-        split(b, mid, kl, out);
-        split(mid, e, kr, out);
+        const int l = split(b, mid, kl, out, tree);
+        const int r = split(mid, e, kr, out, tree);
+        if (!tree) return 0;
+        tree->push_back(SplitNode{axis, l, r});
+        return (int)tree->size() - 1;
+    }
+
+    // near-to-far order of the groups under `id` for direction octant `oct`
+    static void ordered_groups(const std::vector<SplitNode> &tree, int id, int oct, std::vector<int> &out)
+    {
+        if (id < 0) { out.push_back(-id - 1); return; }
+        const SplitNode &n = tree[(size_t)id];
+        const bool neg = (oct >> n.axis) & 1;
+        ordered_groups(tree, neg ? n.right : n.left, oct, out);
+        ordered_groups(tree, neg ? n.left : n.right, oct, out);
     }
 
     static uint32_t prim_payload(const BvhBuildPrim &p) { return BVH_PRIM_BIT | (p.cube ? BVH_CUBE_BIT : 0u) | (p.index & BVH_INDEX_MASK); }
 
     // the <= width entries that cover order_[b, e): primitives when they fit, otherwise up to max_direct large
     // primitives as direct entries and a k-way split of the rest into child nodes (or single primitives)
-    void make_entries(uint32_t b, uint32_t e, int width, int max_direct, int depth, std::vector<Entry> &out)
+    // order: when given (the root), receives for every octant the entry indices of `out` in near-to-far order
+    void make_entries(uint32_t b, uint32_t e, int width, int max_direct, int depth, std::vector<Entry> &out,
+                      std::vector<std::vector<int>> *order = nullptr)
     {
         max_depth = std::max(max_depth, depth);
         if (e - b <= (uint32_t)width) {
@@ -271,9 +310,13 @@ private:
             }
         }
         std::vector<std::pair<uint32_t, uint32_t>> groups;
-        split(rest, e, width - slot, groups);
-        for (const auto &g : groups) {
+        std::vector<SplitNode> tree;
+        const int top = split(rest, e, width - slot, groups, order ? &tree : nullptr);
+        std::vector<int> entry_of_group(groups.size(), -1);
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            const auto &g = groups[gi];
             if (g.second == g.first) continue;
+            entry_of_group[gi] = (int)out.size();
             if (g.second - g.first == 1) { out.push_back(Entry{prim_box(prims_[order_[g.first]]), prim_payload(prims_[order_[g.first]])}); continue; }
             const uint32_t child = n_nodes();
             nodes.resize(nodes.size() + NODE_FLOATS, 0.0f);
@@ -281,6 +324,14 @@ private:
             std::vector<Entry> sub;
             make_entries(g.first, g.second, BVH_WIDTH, 3, depth + 1, sub);
             write_node(child, sub);
+        }
+        if (order) {
+            order->assign(8, std::vector<int>());
+            for (int oct = 0; oct < 8; ++oct) {
+                std::vector<int> gs;
+                ordered_groups(tree, top, oct, gs);
+                for (int gi : gs) if (entry_of_group[(size_t)gi] >= 0) (*order)[(size_t)oct].push_back(entry_of_group[(size_t)gi]);
+            }
         }
     }
 

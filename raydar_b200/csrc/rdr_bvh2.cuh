@@ -3,22 +3,25 @@
 //
 // The per-lane traversal (trace_bvh, rdr_trace.cuh) keeps a 64-entry stack per lane in local memory and walks one ray
 // per lane: lanes finish at different times (12 of 32 active on config 4) and every node costs 8 scalar box tests.
-// Here the WARP owns one stack of (ray, node) tasks in shared memory and all 32 lanes work on it together:
+// Here the rays keep ONE STACK EACH in shared memory, but the WARP serves them together:
 //   A0   every lane tests ITS ray against the <= 32 root entries (constant bank, FFMA2 pairs: top_scan of rdr_fused.cuh);
-//        the root is then consumed in chunks of 8 entries exactly like a node;
-//   N    pop up to 8 tasks from the top of the stack, FOUR LANES PER TASK -- usually some other lane's ray, whose slab
-//        constants come by indexed shuffle; each lane loads one pair of the node's entries (quad-major node: the 4 lanes
-//        read 64 contiguous bytes per LDG.128) and tests it with FFMA2, bounded by the ray's best exact t so far;
-//   P    the hit entries are split by payload bits into child nodes, spheres and cubes; ONE packed shuffle prefix sum
-//        (3 x 10 bits) gives every lane its positions on the stack and in the two survivor lists;
-//   E    full groups of 32 survivors (and, when the stack is empty, the rest) get the exact, reference-ordered test, one
+//        root primitives go to the survivor lists; the root's child nodes the ray touches are kept as a bit mask in
+//        FRONT-TO-BACK order for the ray's direction octant (the builder's split tree gives 8 fixed permutations);
+//   S    each round the first 8 rays that still have work contribute their next node: the top of the ray's stack, else
+//        the nearest untouched child of the root;
+//   N    FOUR LANES PER TASK: each lane loads one pair of the node's entries (quad-major node: the 4 lanes read 64
+//        contiguous bytes per LDG.128) and tests it with FFMA2, bounded by the ray's best exact t so far; the ray's slab
+//        constants come by indexed shuffle;
+//   P    child nodes go onto the owner's stack, primitives to the warp's sphere / cube survivor lists; every position is
+//        a popcount of a ballot (no shuffle scan, no atomics);
+//   E    full groups of 32 survivors (and, when no ray has work left, the rest) get the exact, reference-ordered test, one
 //        per lane, folded into the owner's winner with a 64-bit atomicMin on the (t, original index) key.
-// LIFO order makes the warp go depth-first, so hits arrive early and prune the rest (a task whose node cannot beat the
-// ray's best is simply expanded to nothing).  The stack cannot overflow: the root pushes at most 32 x 32 tasks, a round
-// pops P <= 8 tasks and pushes at most 8 P, and P is throttled so that the stack stays below its soft limit; above
-// it P = 1, i.e. plain depth-first descent of one task, which adds at most 7 entries per level (8 levels).
-// (One node per LANE -- 32 tasks per round, 17 scattered LDG.128 per lane -- was measured first: 77 % L1 data-pipe
-// utilisation, 24 % issue utilisation, profiles/ncu_r01r_config4_bvh2_summary.txt.)
+// Per-ray depth-first order is what makes the hierarchy pay: a ray descends its nearest subtree first, finds its hit and
+// prunes the rest.  Measured with the host simulation of the disciplines (tests/hostsim, config 4, primary rays): one
+// shared LIFO stack for the warp 77 node visits and 22 exact tests per ray; per-ray stacks with the root in front-to-
+// back order 24 and 6.7 (19 and 4.4 with the children of every node ordered too).  The shared-stack version was built
+// first (91 -> 144 Msamples/s after the 4-lanes-per-node change) and replaced.
+// A ray's stack holds at most 8 + 7 x 5 entries (node levels 2..8, BVH_MAX_DEPTH).
 // The winner is decided by the exact tests and the (t, index) rule only, exactly as in every other search.
 // Device-only; must be entered by all 32 lanes of a warp.  Needs lay.bvh2_ok.
 #pragma once
@@ -27,15 +30,16 @@
 
 namespace rdr {
 
-constexpr uint32_t BVH2_STACK_SOFT = 1024u;
-constexpr uint32_t BVH2_STACK_CAP = BVH2_STACK_SOFT + 7u * 8u + 8u;
-constexpr uint32_t BVH2_SURV_CAP = 31u + 256u + 1u;
-constexpr uint32_t BVH2_WARP_BYTES = 32u * 8u + 4u * BVH2_STACK_CAP + 2u * 4u * BVH2_SURV_CAP;
+constexpr uint32_t BVH2_RAY_STACK = 56u;                      // per ray: 8 + 7 x 5 pending siblings (node levels 2..8) and slack
+constexpr uint32_t BVH2_SURV_CAP = 31u + 256u + 1u;           // carried remainder + one root chunk of 32 x 8 primitives
+constexpr uint32_t BVH2_WARP_BYTES = 32u * 8u + 4u * 32u * BVH2_RAY_STACK + 4u * 32u + 8u * 8u + 2u * 4u * BVH2_SURV_CAP;
 
 struct Bvh2Warp {
-    unsigned long long *best;     // [32] winner key per lane
-    uint32_t *stack;              // [BVH2_STACK_CAP]  owner lane << 27 | node
-    uint32_t *surv_s, *surv_c;    // [BVH2_SURV_CAP]   owner lane << 27 | object
+    unsigned long long *best;     // [32] winner key per ray (lane)
+    uint32_t *stack;              // [32][BVH2_RAY_STACK] pending child nodes per ray, top = next
+    uint32_t *depth;              // [32] entries on each ray's stack
+    uint2 *slot;                  // [8]  this round's tasks: (owner lane, node)
+    uint32_t *surv_s, *surv_c;    // [BVH2_SURV_CAP] owner lane << 27 | object; surv_c = surv_s + BVH2_SURV_CAP
 };
 
 __device__ __forceinline__ Bvh2Warp bvh2_warp(unsigned char *base, uint32_t warp)
@@ -43,8 +47,10 @@ __device__ __forceinline__ Bvh2Warp bvh2_warp(unsigned char *base, uint32_t warp
     unsigned char *p = base + (size_t)warp * BVH2_WARP_BYTES;
     Bvh2Warp w;
     w.best = reinterpret_cast<unsigned long long *>(p);
-    w.stack = reinterpret_cast<uint32_t *>(p + 256u);
-    w.surv_s = w.stack + BVH2_STACK_CAP;
+    w.slot = reinterpret_cast<uint2 *>(p + 256u);
+    w.depth = reinterpret_cast<uint32_t *>(p + 256u + 64u);
+    w.stack = w.depth + 32u;
+    w.surv_s = w.stack + 32u * BVH2_RAY_STACK;
     w.surv_c = w.surv_s + BVH2_SURV_CAP;
     return w;
 }
@@ -68,36 +74,30 @@ __device__ __forceinline__ void bvh2_exact(const f4 *obj_geom, Bvh2Warp ws, uint
     __syncwarp();
 }
 
-// P: the entries this lane found hit (bit k of `bits` = entry pay[k]) go to the warp's stack (child nodes) or survivor
-// lists (spheres, cubes), by payload bits; ONE packed prefix sum (3 x 10 bits) gives every lane its positions.
-// Unrolled and predicated: no dependent loads, no divergent loop.  n_t / n_s / n_c: list lengths, warp-uniform.
+// Root primitives: the entries this lane's ray hit (bit k of `bits` = primitive pay[k]) go to the warp's survivor lists;
+// one packed prefix sum gives every lane its positions.  n_s / n_c: list lengths, warp-uniform.
 template <int N>
-__device__ __forceinline__ void bvh2_emit(Bvh2Warp ws, uint32_t lane, uint32_t owner, uint32_t bits, const uint32_t (&pay)[N],
-                                          uint32_t &n_t, uint32_t &n_s, uint32_t &n_c)
+__device__ __forceinline__ void bvh2_emit_prims(Bvh2Warp ws, uint32_t lane, uint32_t bits, const uint32_t (&pay)[N], uint32_t &n_s, uint32_t &n_c)
 {
-    uint32_t nb = 0u, cb = 0u;                                    // child-node bits, cube bits
+    uint32_t cb = 0u;
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-        nb |= ((pay[k] >> 31) ^ 1u) << k;
-        cb |= (((pay[k] >> 30) & 1u) & (pay[k] >> 31)) << k;
-    }
-    nb &= bits; cb &= bits;
-    const uint32_t packed = __popc(nb) | (__popc(bits ^ nb ^ cb) << 10) | (__popc(cb) << 20);
+    for (int k = 0; k < N; ++k) cb |= ((pay[k] >> 30) & 1u) << k;
+    cb &= bits;
+    const uint32_t packed = __popc(bits ^ cb) | (__popc(cb) << 16);
     const uint32_t incl = warp_scan_incl(packed, lane);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     const uint32_t excl = incl - packed;
-    // the three lists are one array (stack | surv_s | surv_c): a position is all that is selected per entry
-    uint32_t pn = n_t + (excl & 1023u), ps = BVH2_STACK_CAP + n_s + ((excl >> 10) & 1023u), pc = BVH2_STACK_CAP + BVH2_SURV_CAP + n_c + (excl >> 20);
-    const uint32_t tag = owner << 27;
+    uint32_t ps = n_s + (excl & 0xffffu), pc = BVH2_SURV_CAP + n_c + (excl >> 16);     // surv_c = surv_s + BVH2_SURV_CAP
+    const uint32_t tag = lane << 27;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         if ((bits >> k) & 1u) {
-            const bool node = (nb >> k) & 1u, cube = (cb >> k) & 1u;
-            ws.stack[node ? pn : (cube ? pc : ps)] = tag | (pay[k] & 0x07ffffffu);
-            pn += node ? 1u : 0u; pc += (!node && cube) ? 1u : 0u; ps += (!node && !cube) ? 1u : 0u;
+            const bool cube = (cb >> k) & 1u;
+            ws.surv_s[cube ? pc : ps] = tag | (pay[k] & 0x07ffffffu);
+            pc += cube ? 1u : 0u; ps += cube ? 0u : 1u;
         }
     }
-    n_t += total & 1023u; n_s += (total >> 10) & 1023u; n_c += total >> 20;
+    n_s += total & 0xffffu; n_c += total >> 16;
     __syncwarp();
 }
 
@@ -107,54 +107,95 @@ __device__ __forceinline__ Hit trace_bvh2(const SceneView &S, const FrameParams 
     const uint32_t lane = threadIdx.x & 31u;
     const SlabRay R = slab_ray_setup(P.cull, o, d);
     ws.best[lane] = ~0ull;
+    ws.depth[lane] = 0u;
     uint32_t m = top_scan(P.top, P.lay.bvh2_root, R);
     if (!alive) m = 0u;
+    // the root's child nodes this ray touches, as bits in FRONT-TO-BACK order for its direction octant (rdr_bvh.h)
+    const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    uint32_t mr = 0u;
+    for (uint32_t mm = m & ~P.top.prim_mask; mm != 0u; mm &= mm - 1u) {
+        const uint32_t k = (uint32_t)__ffs((int)mm) - 1u;
+        mr |= 1u << ((uint32_t)(P.top.rank8[k] >> (5u * oct)) & 31u);
+    }
+    m &= P.top.prim_mask;                                         // what is left in entry order: the root's primitives
     __syncwarp();
 
     const f4 *nodes = reinterpret_cast<const f4 *>(P.blob + P.lay.off_nodes2);
     const uint32_t root_chunks = (P.lay.bvh2_root + 7u) >> 3;
     const uint32_t sub = lane & 3u, grp = lane >> 2;              // node stage: 4 lanes per task, one pair of entries per lane
-    uint32_t n_t = 0u, n_s = 0u, n_c = 0u, chunk = 0u;            // stack / survivor list lengths: warp-uniform
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t n_s = 0u, n_c = 0u, chunk = 0u;                      // survivor list lengths: warp-uniform
 #pragma unroll 1
     for (;;) {
-        const bool rooting = chunk < root_chunks;
-        const bool last = !rooting && n_t == 0u;
-        if (rooting) {
-            // ---- the root, 8 entries at a time: the lane's own ray, payloads from the kernel parameters ----
+        bool last = false;
+        if (chunk < root_chunks) {
+            // ---- the root's primitives, 8 entries at a time, to the survivor lists ----
             uint32_t pay[8];
 #pragma unroll
             for (uint32_t k = 0; k < 8u; ++k) pay[k] = P.top.payload[8u * chunk + k];
-            bvh2_emit<8>(ws, lane, lane, (m >> (8u * chunk)) & 0xffu, pay, n_t, n_s, n_c);
+            bvh2_emit_prims<8>(ws, lane, (m >> (8u * chunk)) & 0xffu, pay, n_s, n_c);
             ++chunk;
-        } else if (!last) {
-            // ---- N: pop up to 8 tasks (throttled near the soft limit); the 4 lanes of a group test one pair each.  The
-            //      node is quad-major, so a group reads 64 contiguous bytes per load: 8 wavefronts per LDG.128 instead of the
-            //      32 of one-node-per-lane (the traversal is bound by the L1 data pipe) ----
-            uint32_t pop = (BVH2_STACK_SOFT > n_t ? BVH2_STACK_SOFT - n_t : 0u) >> 3;      // <= room / 7
-            pop = pop < 1u ? 1u : (pop > 8u ? 8u : pop);
-            if (pop > n_t) pop = n_t;
-            const bool has = grp < pop;
-            const uint32_t task = has ? ws.stack[n_t - 1u - grp] : (lane << 27);
-            n_t -= pop;
-            __syncwarp();                                         // the popped slots are overwritten by the pushes below
-            const uint32_t owner = task >> 27;
-            const float qx = __shfl_sync(FULL, R.rx, owner), qy = __shfl_sync(FULL, R.ry, owner), qz = __shfl_sync(FULL, R.rz, owner);
-            const float mx = __shfl_sync(FULL, R.nx, owner), my = __shfl_sync(FULL, R.ny, owner), mz = __shfl_sync(FULL, R.nz, owner);
-            const f32x2 rho2 = bc2(__shfl_sync(FULL, R.rho, owner));
-            // best exact t of the owner so far: high word of its key; ~0 (no hit) and a NaN hit read as NaN = no bound
-            const float best = __uint_as_float(reinterpret_cast<const uint32_t *>(ws.best + owner)[1]);
-            const f4 *nd = nodes + 16u * (size_t)(task & 0x07ffffffu) + sub;
-            const f4 q0 = nd[0], q1 = nd[4], q2 = nd[8], q3 = nd[12];
-            const f32x2 sp = pk2(q3.x, q3.y);
-            const f32x2 ex = fma2(sp, rho2, pk2(q1.z, q1.w)), ey = fma2(sp, rho2, pk2(q2.x, q2.y)), ez = fma2(sp, rho2, pk2(q2.z, q2.w));
-            uint32_t bits = slab_pair<true>(pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), ex, ey, ez, qx, qy, qz, mx, my, mz, best);
-            uint32_t pay[2] = {__float_as_uint(q3.z), __float_as_uint(q3.w)};
-            if (pay[0] == 0xffffffffu) bits &= ~1u;              // unused entries (a ray that skips the cull passes every box)
-            if (pay[1] == 0xffffffffu) bits &= ~2u;
-            if (!has) bits = 0u;
-            bvh2_emit<2>(ws, lane, owner, bits, pay, n_t, n_s, n_c);
+        } else {
+            // ---- select: the first 8 rays that still have work contribute their NEXT node each (top of the ray's stack,
+            //      else the nearest untouched child of the root) ----
+            const uint32_t dep = ws.depth[lane];
+            const bool work = dep != 0u || mr != 0u;
+            const uint32_t active = __ballot_sync(FULL, work);
+            last = active == 0u;
+            if (!last) {
+                const uint32_t idx = __popc(active & lt);
+                if (work && idx < 8u) {
+                    uint32_t node;
+                    if (dep != 0u) { node = ws.stack[lane * BVH2_RAY_STACK + dep - 1u]; ws.depth[lane] = dep - 1u; }
+                    else { const uint32_t r = (uint32_t)__ffs((int)mr) - 1u; mr &= mr - 1u; node = P.top.node_by_rank[oct][r]; }
+                    ws.slot[idx] = make_uint2(lane, node);
+                }
+                const uint32_t n_act = __popc(active), n_tasks = n_act < 8u ? n_act : 8u;
+                __syncwarp();
+                // ---- N: 4 lanes per task, one pair of the node's entries per lane (quad-major node: the 4 lanes read 64
+                //      contiguous bytes per LDG.128), bounded by the owner's best exact t so far ----
+                const bool has = grp < n_tasks;
+                const uint2 task = has ? ws.slot[grp] : make_uint2(lane, 0u);
+                const uint32_t owner = task.x;
+                const float qx = __shfl_sync(FULL, R.rx, owner), qy = __shfl_sync(FULL, R.ry, owner), qz = __shfl_sync(FULL, R.rz, owner);
+                const float mx = __shfl_sync(FULL, R.nx, owner), my = __shfl_sync(FULL, R.ny, owner), mz = __shfl_sync(FULL, R.nz, owner);
+                const f32x2 rho2 = bc2(__shfl_sync(FULL, R.rho, owner));
+                // best exact t of the owner so far: high word of its key; ~0 (no hit) and a NaN hit read as NaN = no bound
+                const float best = __uint_as_float(reinterpret_cast<const uint32_t *>(ws.best + owner)[1]);
+                const uint32_t dbase = ws.depth[owner];           // after the pop above
+                const f4 *nd = nodes + 16u * (size_t)task.y + sub;
+                const f4 q0 = nd[0], q1 = nd[4], q2 = nd[8], q3 = nd[12];
+                const f32x2 sp = pk2(q3.x, q3.y);
+                const f32x2 ex = fma2(sp, rho2, pk2(q1.z, q1.w)), ey = fma2(sp, rho2, pk2(q2.x, q2.y)), ez = fma2(sp, rho2, pk2(q2.z, q2.w));
+                uint32_t bits = slab_pair<true>(pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), ex, ey, ez, qx, qy, qz, mx, my, mz, best);
+                const uint32_t pa = __float_as_uint(q3.z), pb = __float_as_uint(q3.w);
+                if (!has) bits = 0u;
+                // unused entries (payload ~0: a ray that skips the cull passes every box) are dropped here
+                const bool ha = (bits & 1u) && pa != 0xffffffffu, hb = (bits & 2u) && pb != 0xffffffffu;
+                const bool na = ha && !(pa >> 31), nb = hb && !(pb >> 31);                       // child nodes
+                const bool ca = ha && (pa >> 30) == 3u, cb = hb && (pb >> 30) == 3u;              // cubes
+                const bool sa = ha && (pa >> 30) == 2u, sb = hb && (pb >> 30) == 2u;              // spheres
+                // ---- P: child nodes onto the owner's stack (positions from two ballots within the group), primitives to the
+                //      warp's survivor lists (positions from four ballots); no shuffle scan, no atomics ----
+                const uint32_t bna = __ballot_sync(FULL, na), bnb = __ballot_sync(FULL, nb);
+                const uint32_t ga = (bna >> (4u * grp)) & 0xfu, gb = (bnb >> (4u * grp)) & 0xfu, low = (1u << sub) - 1u;
+                const uint32_t pos = owner * BVH2_RAY_STACK + dbase + __popc(ga & low) + __popc(gb & low);
+                if (na) ws.stack[pos] = pa;
+                if (nb) ws.stack[pos + (na ? 1u : 0u)] = pb;
+                if (has && sub == 0u) ws.depth[owner] = dbase + __popc(ga) + __popc(gb);
+                const uint32_t bsa = __ballot_sync(FULL, sa), bsb = __ballot_sync(FULL, sb);
+                const uint32_t bca = __ballot_sync(FULL, ca), bcb = __ballot_sync(FULL, cb);
+                const uint32_t tag = owner << 27;
+                const uint32_t ps = n_s + __popc(bsa & lt) + __popc(bsb & lt), pc = n_c + __popc(bca & lt) + __popc(bcb & lt);
+                if (sa) ws.surv_s[ps] = tag | (pa & 0x07ffffffu);
+                if (sb) ws.surv_s[ps + (sa ? 1u : 0u)] = tag | (pb & 0x07ffffffu);
+                if (ca) ws.surv_c[pc] = tag | (pa & 0x07ffffffu);
+                if (cb) ws.surv_c[pc + (ca ? 1u : 0u)] = tag | (pb & 0x07ffffffu);
+                n_s += __popc(bsa) + __popc(bsb); n_c += __popc(bca) + __popc(bcb);
+                __syncwarp();
+            }
         }
-        // ---- E: exact tests on full groups of 32 survivors, and on the rest once the stack is empty ----
+        // ---- E: exact tests on full groups of 32 survivors, and on the rest once no ray has work left ----
 #pragma unroll 1
         while (n_s >= 32u || (last && n_s != 0u)) {
             const uint32_t n = n_s < 32u ? n_s : 32u;

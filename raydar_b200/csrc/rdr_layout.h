@@ -83,8 +83,11 @@ constexpr uint32_t FUSED_MAX_TOP = 32u;
 struct alignas(8) TopPair { float cx[2], cy[2], cz[2], ex[2], ey[2], ez[2], sphere[2]; };
 struct TopParams {
     TopPair pair[FUSED_MAX_TOP / 2];
-    uint32_t payload[FUSED_MAX_TOP];     // cooperative BVH: payload of the root entries (rdr_bvh.h)
-    uint32_t prim_mask, cube_mask;       // cooperative BVH: which root entries are primitives / cubes
+    // cooperative hierarchy only (rdr_bvh.h, Bvh2Root): root payloads and the front-to-back order tables
+    uint64_t rank8[FUSED_MAX_TOP];       // bits [5 oct, 5 oct + 5): rank of root entry k for direction octant oct
+    uint32_t payload[FUSED_MAX_TOP];
+    uint32_t node_by_rank[8][FUSED_MAX_TOP];   // child node of the root entry with that rank (0xffffffff: none)
+    uint32_t prim_mask, cube_mask;       // which root entries are primitives / cubes
 };
 
 struct FrameParams {

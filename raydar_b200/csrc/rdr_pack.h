@@ -110,6 +110,8 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
                     tp.ex[h] = R.ex[k]; tp.ey[h] = R.ey[k]; tp.ez[h] = R.ez[k];
                     tp.sphere[h] = R.sphere[k];
                     P.top.payload[k] = R.payload[k];
+                    P.top.rank8[k] = R.rank8[k];
+                    for (int oct = 0; oct < 8; ++oct) P.top.node_by_rank[oct][k] = R.node_by_rank[oct][k];
                     if (k < R.n && (R.payload[k] & BVH_PRIM_BIT)) {
                         P.top.prim_mask |= 1u << k;
                         if (R.payload[k] & BVH_CUBE_BIT) P.top.cube_mask |= 1u << k;

@@ -365,6 +365,96 @@ int hs_bvh2_warp_sim(const RdrSceneFlat *sc, uint32_t flush_at, uint32_t order_c
     return RDR_OK;
 }
 
+// Alternative discipline for comparison: ONE STACK PER RAY (near child on top), each round serves up to `per_round`
+// rays (round-robin over the rays that still have tasks), one task each; survivors are exact-tested when >= flush_at
+// have accumulated.  out as in hs_bvh2_warp_sim.
+int hs_bvh2_perray_sim(const RdrSceneFlat *sc, uint32_t flush_at, uint32_t per_round, double *out)
+{
+    Packed pk(sc, true);
+    if (pk.status != RDR_OK) return pk.status;
+    const SceneView &S = pk.S;
+    const int64_t n = (int64_t)sc->width * sc->height;
+    const float *nodes = reinterpret_cast<const float *>(pk.blob + pk.P.lay.off_nodes2);
+    const TopParams &T = pk.P.top;
+    double visits = 0, exacts = 0, rounds = 0, tasks_popped = 0, warps = 0, max_depth = 0;
+    for (int64_t p0 = 0; p0 < n; p0 += 32) {
+        const int nl = (int)std::min<int64_t>(32, n - p0);
+        v3 o[32], d[32]; RayBvh rb[32]; Hit best[32];
+        struct Child { float tn; uint32_t payload; bool prim; };
+        std::vector<Child> stack[32];
+        struct Surv { uint32_t owner, payload; };
+        std::vector<Surv> surv;
+        auto prune = [&](int l) { return (best[l].idx >= 0 && !isnan_(best[l].t)) ? best[l].t : finf(); };
+        auto flush = [&](bool all) {
+            while (surv.size() >= (flush_at & 0xffffu) || (all && !surv.empty())) {
+                const size_t k = std::min<size_t>(32, surv.size());
+                for (size_t i = surv.size() - k; i < surv.size(); ++i) { bvh_exact_prim(S, surv[i].payload, o[surv[i].owner], d[surv[i].owner], best[surv[i].owner], nullptr); exacts += 1; }
+                surv.resize(surv.size() - k);
+            }
+        };
+        bool sort_children = true;
+        auto emit = [&](int l, std::vector<Child> &ch) {
+            if (sort_children) std::stable_sort(ch.begin(), ch.end(), [](const Child &a, const Child &b) { return a.tn > b.tn; });   // far first
+            for (const Child &c : ch) { if (c.prim) surv.push_back({(uint32_t)l, c.payload}); else stack[l].push_back(c); }
+            max_depth = std::max(max_depth, (double)stack[l].size());
+        };
+        sort_children = (flush_at & 0x20000u) == 0u;                 // bit 17 of flush_at: root hits pushed in entry order
+        for (int l = 0; l < nl; ++l) {
+            o[l] = mk3(pk.P.cam.pos[0], pk.P.cam.pos[1], pk.P.cam.pos[2]);
+            d[l] = camera_ray_dir(pk.P.cam, (uint32_t)((p0 + l) % sc->width), (uint32_t)((p0 + l) / sc->width));
+            rb[l] = make_ray_bvh(o[l], d[l], pk.P.cull); best[l].idx = -1; best[l].t = finf();
+            std::vector<Child> ch;
+            for (uint32_t k = 0; k < pk.P.lay.bvh2_root; ++k) {
+                const TopPair &tp = T.pair[k >> 1]; const int h = (int)(k & 1u);
+                f4 q0, q1; q0.x = tp.cx[h]; q0.y = tp.cy[h]; q0.z = tp.cz[h]; q0.w = tp.ex[h];
+                q1.x = tp.ey[h]; q1.y = tp.ez[h]; q1.z = 0.0f; q1.w = tp.sphere[h];
+                float tn;
+                if (bvh_entry_may_hit(rb[l], q0, q1, finf(), &tn)) {
+                    if (flush_at & 0x80000u) {                      // bit 19: order the root by the builder's octant ranks, not by tn
+                        const int oct = (d[l].x < 0.0f ? 1 : 0) | (d[l].y < 0.0f ? 2 : 0) | (d[l].z < 0.0f ? 4 : 0);
+                        tn = (float)((T.rank8[k] >> (5 * oct)) & 31u);
+                    }
+                    ch.push_back({tn, T.payload[k], ((T.prim_mask >> k) & 1u) != 0u});
+                }
+            }
+            emit(l, ch);
+        }
+        sort_children = (flush_at & 0x40000u) == 0u;                 // bit 18: node children pushed in entry order too
+        flush(false);
+        int next = 0;
+        for (;;) {
+            int served = 0;
+            for (int step = 0; step < nl && served < (int)per_round; ++step) {
+                const int l = (next + step) % nl;
+                if (stack[l].empty()) continue;
+                const Child t = stack[l].back(); stack[l].pop_back();
+                ++served;
+                if ((flush_at & 0x10000u) == 0u && t.tn > prune(l)) continue;   // stale entry (skipped when the stack keeps tn; bit 16 of flush_at: no tn kept)
+                visits += 1;
+                const float *pn = nodes + 64 * (size_t)t.payload;
+                std::vector<Child> ch;
+                for (int k = 0; k < 8; ++k) {
+                    f4 q0, q1; uint32_t payload;
+                    node2_entry(pn, k, q0, q1, payload);
+                    if (payload == 0xffffffffu) continue;
+                    float tn;
+                    if (bvh_entry_may_hit(rb[l], q0, q1, prune(l), &tn)) ch.push_back({tn, payload, (payload & 0x80000000u) != 0u});
+                }
+                emit(l, ch);
+                if (served == (int)per_round) next = (l + 1) % nl;
+            }
+            const bool last = served == 0;
+            if (!last) { rounds += 1; tasks_popped += served; }
+            flush(last);
+            if (last) break;
+        }
+        warps += 1;
+    }
+    out[0] = visits / (double)n; out[1] = exacts / (double)n; out[2] = rounds / warps; out[3] = tasks_popped / std::max(1.0, rounds);
+    out[4] = max_depth;
+    return RDR_OK;
+}
+
 // shape of the pair-packed hierarchy of the cooperative traversal: nodes, root entries
 int hs_bvh2_info(const RdrSceneFlat *sc, uint32_t *n_nodes2, uint32_t *n_root, uint32_t *ok)
 {

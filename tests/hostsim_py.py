@@ -57,6 +57,7 @@ def lib():
         L.hs_bvh_info.argtypes = [sfp, u32p, u32p, u32p]
         L.hs_bvh2_info.argtypes = [sfp, u32p, u32p, u32p]
         L.hs_bvh2_warp_sim.argtypes = [sfp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
+        L.hs_bvh2_perray_sim.argtypes = [sfp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
         L.hs_cluster_info.argtypes = [sfp, u32p, u32p]
         _lib = L
     return _lib
@@ -171,6 +172,15 @@ def bvh2_warp_sim(scene, flush_at=32, order_children=0):
     f = rb._as_flat(scene)
     out = (C.c_double * 4)()
     _ok(lib().hs_bvh2_warp_sim(C.byref(f), flush_at, order_children, out))
+    return tuple(out)
+
+
+def bvh2_perray_sim(scene, flush_at=32, per_round=8):
+    """(node visits per ray, exact tests per ray, rounds per warp, tasks per round, deepest per-ray stack) with one
+    near-first stack per ray and `per_round` rays served per round."""
+    f = rb._as_flat(scene)
+    out = (C.c_double * 5)()
+    _ok(lib().hs_bvh2_perray_sim(C.byref(f), flush_at, per_round, out))
     return tuple(out)
 
 
