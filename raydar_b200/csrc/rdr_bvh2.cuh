@@ -180,6 +180,7 @@ __device__ __forceinline__ Hit trace_bvh2(const SceneView &S, const FrameParams 
                 const uint32_t bna = __ballot_sync(FULL, na), bnb = __ballot_sync(FULL, nb);
                 const uint32_t ga = (bna >> (4u * grp)) & 0xfu, gb = (bnb >> (4u * grp)) & 0xfu, low = (1u << sub) - 1u;
                 const uint32_t pos = owner * BVH2_RAY_STACK + dbase + __popc(ga & low) + __popc(gb & low);
+                __syncwarp();                                     // every lane of the group has read depth[owner] before lane 0 rewrites it
                 if (na) ws.stack[pos] = pa;
                 if (nb) ws.stack[pos + (na ? 1u : 0u)] = pb;
                 if (has && sub == 0u) ws.depth[owner] = dbase + __popc(ga) + __popc(gb);
