@@ -1,6 +1,6 @@
 #!/bin/bash
-# compute-sanitizer (memcheck, racecheck, synccheck) over small renders with the fused scan, the generic fused scan and
-# the cooperative hierarchy.  Usage: bash scripts/gpu_sanitize.sh <tag>
+# TEST TOOL (checks against the oracle, hence under tests/).  compute-sanitizer (memcheck, racecheck, synccheck) over small renders with the fused scan, the generic fused scan and
+# the cooperative hierarchy.  Usage: bash tests/tools/gpu_sanitize.sh <tag>
 TAG=${1:-s}; OUT=gpurun_out; mkdir -p $OUT
 cat > /tmp/san.py <<'PY'
 import sys, os

@@ -1,11 +1,12 @@
 #!/usr/bin/env python
-"""Writes the seeded synthetic scenes of BASELINE.json configs 4 and 5 as .rscn files, so that
+"""TEST / BENCH INPUT TOOL (lives under tests/: it uses the test-side scene generator, which borrows the oracle's Scene
+container).  Writes the seeded synthetic scenes of BASELINE.json configs 4 and 5 as .rscn files, so that
 bench.py / raydar-cuda load them through the product's own scene loader.
-Usage: python scripts/make_synth_scenes.py <out_dir> [config4 [n]] [config5]"""
+Usage: python tests/tools/make_synth_scenes.py <out_dir> [config4 [n]] [config5]"""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import synth_scenes as ss  # noqa: E402
 
