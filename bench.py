@@ -323,7 +323,10 @@ def run_b200(a):
             "bound": "fp32", "kernel": "render_kernel (fused two-level scan)" if a.accel in ("auto", "fused") else f"render_kernel ({a.accel})",
             "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": achieved / fp32_peak if have_roofline else None, "traffic": traffic if headline and (a.width, a.height) == (1920, 1080) else None,
-            "traffic_source": traffic_src,
+            "traffic_source": traffic_src.get("source"),
+            # the same capture's utilisation figures for the dominant kernel (north-star: FP32 pipe, warp execution efficiency, issue slots)
+            "ncu": {k: traffic_src.get(k) for k in ("fp32_pipe_active_pct", "fma_pipe_inst_pct", "alu_pipe_inst_pct", "issue_slots_busy_pct",
+                                                   "warp_execution_efficiency_lanes", "achieved_occupancy_pct")} if headline else None,
             "kernel_ms": kernel_ms, "flops_per_sample": f_sample, "traces_per_sample": traces_per_sample,
             "peak_source": f"{sm_count} SMs x 128 lanes x 2 flop x sm_max_mhz from {peak_src}",
             "note": "FP32-pipe bound (no dense contraction, HBM traffic is 32 B/pixel/launch); achieved = algorithmic "
@@ -369,10 +372,10 @@ def ncu_traffic():
     figure does not depend on spp."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
-        return None, None
+        return None, {}
     with open(p) as f:
         d = json.load(f)
-    return d.get("dram_bytes_per_launch"), d.get("source")
+    return d.get("dram_bytes_per_launch"), d
 
 
 if __name__ == "__main__":

@@ -25,8 +25,15 @@ if len(sys.argv) > 3 and sys.argv[2] == "--traffic-json":
     import json
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot = sum(float(rows[2][hdr.index(k)]) * scale[rows[1][hdr.index(k)]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    val = lambda k: float(rows[2][hdr.index(k)]) if k in hdr else None
     with open(sys.argv[3], "w") as f:
         json.dump({"dram_bytes_per_launch": tot, "kernel": rows[2][hdr.index("Kernel Name")],
+                   "fp32_pipe_active_pct": val("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                   "fma_pipe_inst_pct": val("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                   "alu_pipe_inst_pct": val("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                   "issue_slots_busy_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                   "warp_execution_efficiency_lanes": val("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                   "achieved_occupancy_pct": val("sm__warps_active.avg.pct_of_peak_sustained_active"),
                    "source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch, " + rep.split("/")[-1]
                              + " (1920x1080, 64 spp; per-launch traffic does not depend on spp)"}, f, indent=1)
 for i, h in enumerate(hdr):
