@@ -30,6 +30,8 @@ namespace rdr {
 constexpr uint32_t BVH_PRIM_BIT = 0x80000000u;
 constexpr uint32_t BVH_CUBE_BIT = 0x40000000u;
 constexpr uint32_t BVH_INDEX_MASK = 0x3fffffffu;
+constexpr uint32_t BVH2_RHO_BIT = 0x20000000u;      // pair-packed nodes only
+constexpr uint32_t BVH2_INDEX_MASK = 0x07ffffffu;
 constexpr int BVH_WIDTH = 8;
 constexpr int BVH_MAX_DEPTH = 8;            // the traversal stack (64 entries) holds 7 * depth + 8
 
@@ -166,9 +168,11 @@ private:
 //   node   8 entries = 4 pairs (A, B), 16 quads (256 B, one or two 128-byte lines), QUAD-MAJOR: quad i of pair p is
 //          quad 4 i + p, so that the 4 lanes that share a node read 64 contiguous bytes per load instruction:
 //            i = 0: (cxA, cxB, cyA, cyB)   1: (czA, czB, exA, exB)   2: (eyA, eyB, ezA, ezB)
-//            i = 3: (sphereA, sphereB, payloadA, payloadB)
-//   payload as in BvhBuilder: bit 31 = primitive (else child node index), bit 30 = cube, low 30 bits = index;
-//   0xffffffff = unused entry (its box has e = -1).
+//            i = 3: (orderA, orderB, payloadA, payloadB)
+//   payload: bit 31 = primitive (else child node index), bit 30 = cube, bit 29 = the box grows by the per-ray rho (a
+//   sphere, or a node that contains one), low 27 bits = index; 0xffffffff = unused entry (its box has e = -1).
+//   order: bits [3 oct, 3 oct + 3) = rank of the entry in the node's near-to-far order for direction octant oct
+//   (same construction as the root's, from the node's own split tree).
 struct Bvh2Root {
     float cx[32], cy[32], cz[32], ex[32], ey[32], ez[32], sphere[32];
     uint32_t payload[32];
@@ -202,12 +206,7 @@ public:
         for (int k = 0; k < 32; ++k) root.rank8[k] = 0;
         for (int oct = 0; oct < 8; ++oct) {
             for (int i = 0; i < 32; ++i) root.node_by_rank[oct][i] = 0xffffffffu;
-            // entries the split order does not cover (direct primitives, or everything when the root holds <= 32
-            // primitives) take the remaining ranks; they are primitives, their order does not matter
-            std::vector<int> seq = order.size() == 8 ? order[(size_t)oct] : std::vector<int>();
-            std::vector<bool> seen(entries.size(), false);
-            for (int k : seq) seen[(size_t)k] = true;
-            for (size_t k = 0; k < entries.size(); ++k) if (!seen[k]) seq.push_back((int)k);
+            const std::vector<int> seq = full_sequence(order, oct, entries.size());
             for (size_t i = 0; i < seq.size(); ++i) {
                 const int k = seq[i];
                 root.rank8[k] |= (uint64_t)i << (5 * oct);
@@ -311,7 +310,7 @@ private:
         }
         std::vector<std::pair<uint32_t, uint32_t>> groups;
         std::vector<SplitNode> tree;
-        const int top = split(rest, e, width - slot, groups, order ? &tree : nullptr);
+        const int top = split(rest, e, width - slot, groups, &tree);
         std::vector<int> entry_of_group(groups.size(), -1);
         for (size_t gi = 0; gi < groups.size(); ++gi) {
             const auto &g = groups[gi];
@@ -322,8 +321,9 @@ private:
             nodes.resize(nodes.size() + NODE_FLOATS, 0.0f);
             out.push_back(Entry{range_box(g.first, g.second), child});
             std::vector<Entry> sub;
-            make_entries(g.first, g.second, BVH_WIDTH, 3, depth + 1, sub);
-            write_node(child, sub);
+            std::vector<std::vector<int>> sub_order;
+            make_entries(g.first, g.second, BVH_WIDTH, 3, depth + 1, sub, &sub_order);
+            write_node(child, sub, sub_order);
         }
         if (order) {
             order->assign(8, std::vector<int>());
@@ -335,9 +335,25 @@ private:
         }
     }
 
-    void write_node(uint32_t node, const std::vector<Entry> &entries)
+    // near-to-far sequence of all entries for an octant: the split order first, then the entries it does not cover
+    // (direct primitives; everything when the entries are plain primitives) -- their order does not matter
+    static std::vector<int> full_sequence(const std::vector<std::vector<int>> &order, int oct, size_t n_entries)
+    {
+        std::vector<int> seq = order.size() == 8 ? order[(size_t)oct] : std::vector<int>();
+        std::vector<bool> seen(n_entries, false);
+        for (int k : seq) seen[(size_t)k] = true;
+        for (size_t k = 0; k < n_entries; ++k) if (!seen[k]) seq.push_back((int)k);
+        return seq;
+    }
+
+    void write_node(uint32_t node, const std::vector<Entry> &entries, const std::vector<std::vector<int>> &order)
     {
         float *p = nodes.data() + (size_t)node * NODE_FLOATS;
+        uint32_t ranks[BVH_WIDTH] = {0};
+        for (int oct = 0; oct < 8; ++oct) {
+            const std::vector<int> seq = full_sequence(order, oct, entries.size());
+            for (size_t i = 0; i < seq.size(); ++i) ranks[seq[i]] |= (uint32_t)i << (3 * oct);
+        }
         for (int k = 0; k < BVH_WIDTH; ++k) {
             const int pair = k >> 1, h = k & 1;
             auto quad = [&](int i) { return p + 4 * (4 * i + pair); };
@@ -350,8 +366,9 @@ private:
             quad(0)[0 + h] = e.box.c[0]; quad(0)[2 + h] = e.box.c[1];
             quad(1)[0 + h] = e.box.c[2]; quad(1)[2 + h] = e.box.e[0];
             quad(2)[0 + h] = e.box.e[1]; quad(2)[2 + h] = e.box.e[2];
-            quad(3)[0 + h] = e.box.sphere ? 1.0f : 0.0f;
-            memcpy(&quad(3)[2 + h], &e.payload, 4);
+            memcpy(&quad(3)[0 + h], &ranks[k], 4);
+            const uint32_t payload = e.payload | (e.box.sphere ? BVH2_RHO_BIT : 0u);
+            memcpy(&quad(3)[2 + h], &payload, 4);
         }
     }
 };

@@ -12,8 +12,9 @@
 //   N    FOUR LANES PER TASK: each lane loads one pair of the node's entries (quad-major node: the 4 lanes read 64
 //        contiguous bytes per LDG.128) and tests it with FFMA2, bounded by the ray's best exact t so far; the ray's slab
 //        constants come by indexed shuffle;
-//   P    child nodes go onto the owner's stack, primitives to the warp's sphere / cube survivor lists; every position is
-//        a popcount of a ballot (no shuffle scan, no atomics);
+//   P    child nodes go onto the owner's stack far first (every node carries its entries' near-to-far ranks per octant,
+//        like the root), primitives to the warp's sphere / cube survivor lists; every position is a popcount of a
+//        ballot or of the group's rank mask (no shuffle scan, no atomics);
 //   E    full groups of 32 survivors (and, when no ray has work left, the rest) get the exact, reference-ordered test, one
 //        per lane, folded into the owner's winner with a 64-bit atomicMin on the (t, original index) key.
 // Per-ray depth-first order is what makes the hierarchy pay: a ray descends its nearest subtree first, finds its hit and
@@ -165,25 +166,31 @@ __device__ __forceinline__ Hit trace_bvh2(const SceneView &S, const FrameParams 
                 const uint32_t dbase = ws.depth[owner];           // after the pop above
                 const f4 *nd = nodes + 16u * (size_t)task.y + sub;
                 const f4 q0 = nd[0], q1 = nd[4], q2 = nd[8], q3 = nd[12];
-                const f32x2 sp = pk2(q3.x, q3.y);
+                const uint32_t pa = __float_as_uint(q3.z), pb = __float_as_uint(q3.w);
+                // payload bit 29: the box grows by the ray's rho (a sphere, or a node that contains one)
+                const f32x2 sp = pk2((pa & 0x20000000u) ? 1.0f : 0.0f, (pb & 0x20000000u) ? 1.0f : 0.0f);
                 const f32x2 ex = fma2(sp, rho2, pk2(q1.z, q1.w)), ey = fma2(sp, rho2, pk2(q2.x, q2.y)), ez = fma2(sp, rho2, pk2(q2.z, q2.w));
                 uint32_t bits = slab_pair<true>(pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), ex, ey, ez, qx, qy, qz, mx, my, mz, best);
-                const uint32_t pa = __float_as_uint(q3.z), pb = __float_as_uint(q3.w);
                 if (!has) bits = 0u;
                 // unused entries (payload ~0: a ray that skips the cull passes every box) are dropped here
                 const bool ha = (bits & 1u) && pa != 0xffffffffu, hb = (bits & 2u) && pb != 0xffffffffu;
                 const bool na = ha && !(pa >> 31), nb = hb && !(pb >> 31);                       // child nodes
                 const bool ca = ha && (pa >> 30) == 3u, cb = hb && (pb >> 30) == 3u;              // cubes
                 const bool sa = ha && (pa >> 30) == 2u, sb = hb && (pb >> 30) == 2u;              // spheres
-                // ---- P: child nodes onto the owner's stack (positions from two ballots within the group), primitives to the
-                //      warp's survivor lists (positions from four ballots); no shuffle scan, no atomics ----
-                const uint32_t bna = __ballot_sync(FULL, na), bnb = __ballot_sync(FULL, nb);
-                const uint32_t ga = (bna >> (4u * grp)) & 0xfu, gb = (bnb >> (4u * grp)) & 0xfu, low = (1u << sub) - 1u;
-                const uint32_t pos = owner * BVH2_RAY_STACK + dbase + __popc(ga & low) + __popc(gb & low);
+                // ---- P: child nodes onto the owner's stack FAR FIRST (the nearest ends on top): the node carries, for each
+                //      direction octant, the rank of every entry in its near-to-far order (rdr_bvh.h); the group ORs its hit
+                //      children into a mask in rank space (two butterfly shuffles) and an entry's slot is the number of hit
+                //      children behind it.  Primitives go to the warp's survivor lists (positions from four ballots). ----
+                const uint32_t octq = (qx < 0.0f ? 3u : 0u) + (qy < 0.0f ? 6u : 0u) + (qz < 0.0f ? 12u : 0u);     // 3 x octant of the owner
+                const uint32_t ra = (__float_as_uint(q3.x) >> octq) & 7u, rb = (__float_as_uint(q3.y) >> octq) & 7u;
+                uint32_t gm = (na ? 1u << ra : 0u) | (nb ? 1u << rb : 0u);
+                gm |= __shfl_xor_sync(FULL, gm, 1);
+                gm |= __shfl_xor_sync(FULL, gm, 2);
+                const uint32_t sbase = owner * BVH2_RAY_STACK + dbase;
                 __syncwarp();                                     // every lane of the group has read depth[owner] before lane 0 rewrites it
-                if (na) ws.stack[pos] = pa;
-                if (nb) ws.stack[pos + (na ? 1u : 0u)] = pb;
-                if (has && sub == 0u) ws.depth[owner] = dbase + __popc(ga) + __popc(gb);
+                if (na) ws.stack[sbase + __popc(gm >> (ra + 1u))] = pa & 0x07ffffffu;
+                if (nb) ws.stack[sbase + __popc(gm >> (rb + 1u))] = pb & 0x07ffffffu;
+                if (has && sub == 0u) ws.depth[owner] = dbase + __popc(gm);
                 const uint32_t bsa = __ballot_sync(FULL, sa), bsb = __ballot_sync(FULL, sb);
                 const uint32_t bca = __ballot_sync(FULL, ca), bcb = __ballot_sync(FULL, cb);
                 const uint32_t tag = owner << 27;

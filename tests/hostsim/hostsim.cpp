@@ -48,8 +48,17 @@ void node2_entry(const float *p, int k, f4 &q0, f4 &q1, uint32_t &payload)
     const int pair = k >> 1, h = k & 1;
     auto quad = [&](int i) { return p + 4 * (4 * i + pair); };
     q0.x = quad(0)[0 + h]; q0.y = quad(0)[2 + h]; q0.z = quad(1)[0 + h]; q0.w = quad(1)[2 + h];
-    q1.x = quad(2)[0 + h]; q1.y = quad(2)[2 + h]; q1.z = 0.0f; q1.w = quad(3)[0 + h];
+    q1.x = quad(2)[0 + h]; q1.y = quad(2)[2 + h]; q1.z = 0.0f;
     memcpy(&payload, &quad(3)[2 + h], 4);
+    q1.w = (payload != 0xffffffffu && (payload & BVH2_RHO_BIT)) ? 1.0f : 0.0f;
+    if (payload != 0xffffffffu) payload &= ~BVH2_RHO_BIT;
+}
+
+// rank of entry k in the node's near-to-far order for direction octant oct
+uint32_t node2_rank(const float *p, int k, int oct)
+{
+    uint32_t r; memcpy(&r, p + 4 * (4 * 3 + (k >> 1)) + (k & 1), 4);
+    return (r >> (3 * oct)) & 7u;
 }
 
 // Scalar walk of the pair-packed hierarchy of the warp-cooperative traversal (rdr_bvh2.cuh runs on the device only):
@@ -438,7 +447,13 @@ int hs_bvh2_perray_sim(const RdrSceneFlat *sc, uint32_t flush_at, uint32_t per_r
                     node2_entry(pn, k, q0, q1, payload);
                     if (payload == 0xffffffffu) continue;
                     float tn;
-                    if (bvh_entry_may_hit(rb[l], q0, q1, prune(l), &tn)) ch.push_back({tn, payload, (payload & 0x80000000u) != 0u});
+                    if (bvh_entry_may_hit(rb[l], q0, q1, prune(l), &tn)) {
+                        if (flush_at & 0x100000u) {                 // bit 20: order the children by the builder's octant ranks
+                            const int oct = (d[l].x < 0.0f ? 1 : 0) | (d[l].y < 0.0f ? 2 : 0) | (d[l].z < 0.0f ? 4 : 0);
+                            tn = (float)node2_rank(pn, k, oct);
+                        }
+                        ch.push_back({tn, payload, (payload & 0x80000000u) != 0u});
+                    }
                 }
                 emit(l, ch);
                 if (served == (int)per_round) next = (l + 1) % nl;

@@ -261,6 +261,44 @@ def test_fused_scan_cluster_sizes(rb, orc, n):
     r.close()
 
 
+def test_renderer_trait_session(rb, orc, default_scene, benchmark_scene):
+    """The trait's session semantics on one handle (renderer/mod.rs:25-35): timers, getters, a resolution and scene change
+    between frames (frame_buffer() reallocation, cpu.rs:404-411), setters in mid-frame (inspector.rs:178-204), the
+    SolidColor world, and a non-16:9 frame through an orthographic-style matrix pair (the path has no special case)."""
+    import copy
+    r = rb.Renderer(rb.RendererConfig(4, 12)); r.set_seed(11)
+    a = default_scene.with_resolution(160, 90)
+    r.render_frame(a)
+    p = r.profiler()                                            # main.rs:61-107 fails if any of the four timers is unset
+    assert p.has_frame and p.has_prepare and p.has_render and p.has_sample and p.device_render_ms > 0
+    assert (r.sample_count(), r.max_sample_count(), r.max_bounces()) == (4, 4, 12)
+    assert np.array_equal(u32(orc.render(a, 11, 0, 4, 12)), u32(r.read_accum()))
+    b = benchmark_scene.with_resolution(200, 112)
+    r.set_max_sample_count(2); r.set_max_bounces(5)
+    img = r.render_frame(b)
+    assert img.shape == (112, 200, 4) and img[..., 3].min() == 255
+    assert np.array_equal(u32(orc.render(b, 11, 0, 2, 5)), u32(r.read_accum()))
+    r.set_max_sample_count(5)                                   # raising the budget continues the same accumulation
+    n = 0
+    while r.render_sample(b) is not None:
+        n += 1
+    assert n == 3 and r.sample_count() == 5
+    want = orc.render(b, 11, 0, 5, 5)
+    assert np.array_equal(u32(want), u32(r.read_accum()))
+    assert np.array_equal(orc.resolve(want, 5), r.resolve())
+    c = copy.copy(a); c.world_kind = rb.WORLD_SOLID; c.world_a = np.array([0.25, 0.5, 0.75], np.float32)
+    r.set_max_sample_count(3); r.set_max_bounces(12)
+    r.render_frame(c)
+    assert np.array_equal(u32(orc.render(c, 11, 0, 3, 12)), u32(r.read_accum()))
+    e = copy.copy(default_scene).with_resolution(97, 131)       # odd, portrait frame: partial warps, matrices used as stored
+    e.inv_proj = np.diag([3.0, 4.0, 1.0, 1.0]).astype(np.float32).T.reshape(-1)     # an orthographic-style inverse projection
+    r.render_frame(e)
+    assert np.array_equal(u32(orc.render(e, 11, 0, 3, 12)), u32(r.read_accum()))
+    ids_o, t_o = orc.first_hit(e); ids_g, t_g = r.first_hit()
+    assert np.array_equal(ids_o, ids_g) and np.array_equal(u32(t_o), u32(t_g))
+    r.close()
+
+
 def test_edge_cases(rb, orc, default_scene):
     # zero objects: every sample is the sky
     empty = default_scene.with_resolution(32, 16)
