@@ -43,6 +43,12 @@ def test_library_has_sm100a_code_and_tma(rb):
     sass = subprocess.run(["cuobjdump", "-sass", rb.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass            # cp.async.bulk staging of the scene blob
     assert "render_kernel" in sass
+    # the fused scan: packed FP32 pair tests with broadcast-scalar |x| operands, top-level boxes through uniform
+    # constant loads, shared-memory (not generic) scene accesses
+    fused = sass[sass.index("render_kernelILi5ELi768ELi1E"):]
+    fused = fused[:fused.index("Function :", 10)] if "Function :" in fused[10:] else fused
+    assert fused.count("FFMA2") > 200 and "|.F32" in fused and "LDCU.128" in fused and "LDS.128" in fused
+    assert fused.count("LD.E.128") == 0
 
 
 def test_no_cpu_fallback(rb):
