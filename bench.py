@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--progressive", action="store_true",
                     help="time the interactive path instead: render_sample() = one 1-spp launch + resolve + image read-back per call")
+    ap.add_argument("--partition", default="samples", choices=["samples", "stripes"],
+                    help="N > 1: shard by sample range (default) or by round-robin 16-row stripes (bit-identical to 1 GPU); "
+                         "both keep the per-GPU load fixed: the frame has N*spp samples per pixel")
     ap.add_argument("--accel", default="auto", choices=["auto", "brute", "bvh", "cluster", "coop", "fused", "bvh2"], help="nearest-hit search of the CUDA backend")
     return ap.parse_args()
 
@@ -201,10 +204,17 @@ def run_b200(a):
     scene = rb.Scene.load(a.scene).override_resolution(a.width, a.height)
     flat = scene.flat()
     n_pixels = a.width * a.height
-    r = rb.Renderer(rb.RendererConfig(a.spp, a.bounces), device=local)
+    from raydar_b200 import dist as rdist
+    stripes = a.partition == "stripes" and world > 1
+    # samples: rank g renders spp samples of every pixel; stripes: rank g renders all N*spp samples of 1/N of the rows
+    rank_spp = a.spp * world if stripes else a.spp
+    r = rb.Renderer(rb.RendererConfig(rank_spp, a.bounces), device=local)
     r.set_seed(a.seed)
     r.set_accel({"auto": rb.ACCEL_AUTO, "brute": rb.ACCEL_BRUTE, "bvh": rb.ACCEL_BVH, "cluster": rb.ACCEL_CLUSTER, "coop": rb.ACCEL_COOP, "fused": rb.ACCEL_FUSED, "bvh2": rb.ACCEL_BVH_COOP}[a.accel])
-    r.set_sample_offset(rank * a.spp)                    # weak scaling: every rank renders spp samples of its own range
+    if stripes:
+        r.set_row_stripes(rdist.STRIPE_ROWS, rank, world)
+    else:
+        r.set_sample_offset(rank * a.spp)                # weak scaling: every rank renders spp samples of its own range
     r.new_frame(flat)
     ptr, nbytes = r.accum_device_ptr()
 
@@ -225,7 +235,7 @@ def run_b200(a):
         flush.zero_()                                    # L2 flush between timed iterations
         torch.cuda.synchronize()
         r.reset_frame()
-        r.render_samples(a.spp)                          # returns after the kernel's stop event
+        r.render_samples(rank_spp)                       # returns after the kernel's stop event
         device_ms.append(r.profiler().device_render_ms)
         if world > 1:
             dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)     # NCCL over NVLink, per-GPU accumulators -> rank 0
@@ -239,7 +249,7 @@ def run_b200(a):
         if world == 1:
             return r.render_frame(flat)                  # host scene in -> host RGBA8 out
         r.new_frame(flat)
-        r.render_samples(a.spp)
+        r.render_samples(rank_spp)
         dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
         return r.resolve(a.spp * world) if rank == 0 else None
@@ -293,7 +303,7 @@ def run_b200(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "parallelism": f"sample-range x{world}", "accel": a.accel,
+            "config": {"workload": workload_name(a), "parallelism": (f"row-stripes({rdist.STRIPE_ROWS}) x{world}" if stripes else f"sample-range x{world}"), "accel": a.accel,
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
                        "step": "fresh accumulator + spp samples/pixel in one kernel launch"
                                + (" + NCCL reduce to rank 0" if world > 1 else "") + " + resolve to RGBA8"},

@@ -131,6 +131,11 @@ int rdr_set_seed(RdrRenderer *r, uint64_t seed);
 /* This instance renders global sample indices [first, first + max_sample_count): sample-range
  * sharding across GPUs (one instance per GPU, accumulators summed afterwards). */
 int rdr_set_sample_offset(RdrRenderer *r, uint32_t first_sample);
+/* This instance renders only the row stripes s (stripe_rows image rows each, top stripe = 0) with
+ * s % count == index: image-tile sharding across GPUs.  The stripes of different instances are disjoint, so the
+ * sum of their accumulators (x + 0 = x) is BIT-IDENTICAL to the one-instance image.  count <= 1 or
+ * stripe_rows == 0: the whole image.  Takes effect at the next launch; the accumulator stays W*H. */
+int rdr_set_row_stripes(RdrRenderer *r, uint32_t stripe_rows, uint32_t index, uint32_t count);
 int rdr_set_accel(RdrRenderer *r, int accel);                 /* RDR_ACCEL_* */
 /* Zero the accumulator and sample_count but keep the scene already resident on the device
  * (new_frame without the scene upload; the editor calls new_frame for every change, the
@@ -155,6 +160,13 @@ uint64_t rdr_scene_device_bytes(const RdrRenderer *r);
 /* single-process multi-GPU: one sub-renderer per device, sample ranges split evenly, accumulators
  * combined with one ncclReduce(sum, f32) onto devices[0] before resolve. */
 int rdr_create_multi(const RdrConfig *config, int n_devices, const int *devices, RdrRenderer **out);
+/* how a multi-GPU handle splits the frame (takes effect at the next new_frame):
+ *   SAMPLES  every device renders the whole image for its share of the sample indices (default; perfect balance,
+ *            result equal to one GPU up to f32 summation order)
+ *   STRIPES  every device renders all samples of its round-robin row stripes (stripe_rows rows each, 0 = 16):
+ *            the reduce adds zeros, so the result is bit-identical to one GPU */
+enum { RDR_PARTITION_SAMPLES = 0, RDR_PARTITION_STRIPES = 1 };
+int rdr_set_partition(RdrRenderer *r, int partition, uint32_t stripe_rows);
 
 /* ---- parity / debug modes ------------------------------------------------------------------------ */
 /* first-hit object id (-1 = miss) and t per pixel for the current frame's primary rays */

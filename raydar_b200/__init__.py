@@ -25,6 +25,7 @@ LIB_PATH = os.path.join(_HERE, "libraydar_cuda.so")
 SPHERE, CUBE = 0, 1
 WORLD_SKY, WORLD_SOLID, WORLD_TRANSPARENT = 0, 1, 2
 ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH, ACCEL_CLUSTER, ACCEL_COOP, ACCEL_FUSED, ACCEL_BVH_COOP = 0, 1, 2, 3, 4, 5, 6
+PARTITION_SAMPLES, PARTITION_STRIPES = 0, 1
 MAT_STRIDE = 11
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_IO, ERR_PARSE, ERR_NCCL, ERR_NOMEM = range(8)
 
@@ -32,7 +33,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_IO, ERR_PARSE, ERR_NCCL, ERR_NOM
 EXPORTS = [
     "rdr_create", "rdr_destroy", "rdr_last_error", "rdr_new_frame", "rdr_render_sample", "rdr_render_frame",
     "rdr_profiler", "rdr_sample_count", "rdr_max_sample_count", "rdr_max_bounces", "rdr_set_max_sample_count",
-    "rdr_set_max_bounces", "rdr_reset_frame", "rdr_set_seed", "rdr_set_sample_offset", "rdr_set_accel", "rdr_render_samples",
+    "rdr_set_max_bounces", "rdr_reset_frame", "rdr_set_seed", "rdr_set_sample_offset", "rdr_set_row_stripes", "rdr_set_partition", "rdr_set_accel", "rdr_render_samples",
     "rdr_resolve", "rdr_read_accum", "rdr_accum_device_ptr", "rdr_stream", "rdr_synchronize", "rdr_launch_count",
     "rdr_scene_device_bytes",
     "rdr_create_multi", "rdr_first_hit", "rdr_trace_path", "rdr_kat_hit_sphere", "rdr_kat_hit_cube",
@@ -114,6 +115,8 @@ def load_library():
     L.rdr_set_seed.argtypes = [vp, C.c_uint64]
     L.rdr_set_sample_offset.argtypes = [vp, C.c_uint32]
     L.rdr_set_accel.argtypes = [vp, C.c_int]
+    L.rdr_set_row_stripes.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.rdr_set_partition.argtypes = [vp, C.c_int, C.c_uint32]
     L.rdr_debug_set_cull.argtypes = [vp, C.c_int]
     L.rdr_render_samples.argtypes = [vp, C.c_uint32]
     L.rdr_reset_frame.argtypes = [vp]
@@ -306,6 +309,14 @@ class Renderer:
     def set_seed(self, seed: int) -> None: _check(self._L.rdr_set_seed(self._h, seed), self._h)
     def set_sample_offset(self, first: int) -> None: _check(self._L.rdr_set_sample_offset(self._h, first), self._h)
     def set_accel(self, accel: int) -> None: _check(self._L.rdr_set_accel(self._h, accel), self._h)
+
+    def set_row_stripes(self, stripe_rows: int, index: int, count: int) -> None:
+        """Render only the row stripes s with s % count == index (image-tile sharding; count <= 1: whole image)."""
+        _check(self._L.rdr_set_row_stripes(self._h, stripe_rows, index, count), self._h)
+
+    def set_partition(self, partition: int, stripe_rows: int = 0) -> None:
+        """Multi-GPU handle only: PARTITION_SAMPLES (sample ranges) or PARTITION_STRIPES (round-robin row stripes)."""
+        _check(self._L.rdr_set_partition(self._h, partition, stripe_rows), self._h)
     def debug_set_cull(self, enabled: bool) -> None: _check(self._L.rdr_debug_set_cull(self._h, int(enabled)), self._h)
     def reset_frame(self) -> None: _check(self._L.rdr_reset_frame(self._h), self._h)
     def render_samples(self, n: int) -> None: _check(self._L.rdr_render_samples(self._h, n), self._h)

@@ -51,6 +51,7 @@ struct RdrRenderer {
     RdrConfig config{1024u, 12u};
     uint64_t seed = 0x5EEDull;
     uint32_t sample_offset = 0;
+    uint32_t stripe_rows = 0, stripe_index = 0, stripe_count = 1;   // rdr_set_row_stripes (count <= 1: whole image)
     int accel = RDR_ACCEL_AUTO;
     bool use_cull = true;
 
@@ -134,6 +135,8 @@ int render_launch(RdrRenderer *r, uint32_t n)
     P.sample_begin = r->sample_offset + r->sample_count;
     P.sample_count = n;
     P.max_bounces = r->config.max_bounces;
+    P.stripe_rows = r->stripe_rows; P.stripe_index = r->stripe_index; P.stripe_count = r->stripe_count;
+    P.owned_pixels = rdr::stripe_owned_pixels(P.cam.width, P.cam.height, P.stripe_rows, P.stripe_index, P.stripe_count);
     RDR_CUDA(r, cudaEventRecord(r->ev_start, r->stream));
     if (r->resident_ctas <= 0) RDR_CUDA(r, rdr::render_resident_ctas(P, scan_variant(r), &r->resident_ctas));
     RDR_CUDA(r, rdr::launch_render(P, scan_variant(r), r->resident_ctas, r->stream));
@@ -448,6 +451,25 @@ int rdr_set_sample_offset(RdrRenderer *r, uint32_t first_sample)
     if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
     if (r->multi) return fail(r, RDR_ERR_INVALID, "a multi-GPU handle assigns sample ranges itself");
     r->sample_offset = first_sample;
+    return RDR_OK;
+}
+
+int rdr_set_row_stripes(RdrRenderer *r, uint32_t stripe_rows, uint32_t index, uint32_t count)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    if (r->multi) return fail(r, RDR_ERR_INVALID, "a multi-GPU handle assigns stripes itself (rdr_set_partition)");
+    if (count <= 1u || stripe_rows == 0u) { r->stripe_rows = 0u; r->stripe_index = 0u; r->stripe_count = 1u; return RDR_OK; }
+    if (index >= count) return fail(r, RDR_ERR_INVALID, "stripe index %u out of range (count %u)", index, count);
+    r->stripe_rows = stripe_rows; r->stripe_index = index; r->stripe_count = count;
+    return RDR_OK;
+}
+
+int rdr_set_partition(RdrRenderer *r, int partition, uint32_t stripe_rows)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    if (partition != RDR_PARTITION_SAMPLES && partition != RDR_PARTITION_STRIPES) return fail(r, RDR_ERR_INVALID, "unknown partition %d", partition);
+    if (!r->multi) return fail(r, RDR_ERR_INVALID, "rdr_set_partition needs a handle made by rdr_create_multi");
+    rdr::multi_set_partition(r->multi, partition, stripe_rows ? stripe_rows : 16u);
     return RDR_OK;
 }
 

@@ -77,15 +77,16 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) render_kernel(const __grid_co
     extern __shared__ __align__(128) unsigned char smem[];
     const SceneView S = scene_view(stage_scene<MODE>(smem, P), P.lay);
     uint32_t *scratch0 = scratch_base<MODE>(smem, P);
-    const uint32_t n_pixels = P.cam.width * P.cam.height;
+    const uint32_t n_owned = P.owned_pixels;        // the whole image, or this shard's row stripes (rdr_set_row_stripes)
 
     LaneState st;
     lane_init(st, scratch0 + threadIdx.x);
     bool exhausted = false;
     for (;;) {
         while (!st.alive && !exhausted) {
-            const uint32_t pixel = atomicAdd(P.pixel_counter, 1u);
-            if (pixel >= n_pixels) { exhausted = true; break; }
+            const uint32_t k = atomicAdd(P.pixel_counter, 1u);
+            if (k >= n_owned) { exhausted = true; break; }
+            const uint32_t pixel = stripe_pixel(P.cam.width, P.stripe_rows, P.stripe_index, P.stripe_count, k);
             lane_start_pixel(P, pixel, P.accum[pixel], st);
             if (!st.alive) P.accum[pixel] = st.acc;      // nothing to trace (no samples or no bounces)
         }
@@ -333,7 +334,7 @@ size_t fused_smem_bytes(const SceneLayout &L) { return mode_smem_bytes(L, true, 
 
 cudaError_t launch_render(const FrameParams &P, int variant, int resident_ctas, cudaStream_t stream)
 {
-    const uint32_t n_pixels = P.cam.width * P.cam.height;
+    const uint32_t n_pixels = P.owned_pixels;       // pixels this launch hands out (all of them, or the shard's stripes)
     if (n_pixels == 0u) return cudaSuccess;
     const int mode = mode_of(P, variant);
     const uint32_t block = render_block(mode);

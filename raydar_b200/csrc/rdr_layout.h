@@ -103,8 +103,38 @@ struct FrameParams {
     uint32_t max_bounces;
     uint32_t sample_begin;               // global index of the first sample of this launch
     uint32_t sample_count;               // samples per pixel in this launch
+    // row-stripe sharding (rdr_set_row_stripes): this launch renders only the stripes s of stripe_rows image rows with
+    // s % stripe_count == stripe_index.  stripe_count <= 1: the whole image.  owned_pixels = pixels handed out.
+    uint32_t stripe_rows, stripe_index, stripe_count;
+    uint32_t owned_pixels;
     TopParams top;                       // fused scan only (lay.fused_ok)
 };
+
+// ---- row-stripe ownership (image-tile sharding across GPUs, SURVEY.md 8e "alternative") --------------------
+// Stripe s covers image rows [s * rows, min((s + 1) * rows, H)); shard `index` of `count` owns the stripes with
+// s % count == index (round-robin, so an unevenly lit image still balances).  Pixels are row-major, so a stripe
+// is one contiguous range of pixel indices and the k-th owned pixel is found with one division.
+RDR_HD uint32_t stripe_owned_pixels(uint32_t width, uint32_t height, uint32_t rows, uint32_t index, uint32_t count)
+{
+    if (count <= 1u || rows == 0u) return width * height;
+    const uint32_t n_stripes = (height + rows - 1u) / rows;
+    uint32_t owned_rows = 0u;
+    for (uint32_t s = index; s < n_stripes; s += count) {
+        const uint32_t r0 = s * rows;
+        owned_rows += (height - r0 < rows) ? height - r0 : rows;
+    }
+    return owned_rows * width;
+}
+
+// global pixel index (y * W + x) of the k-th pixel this shard owns, k < owned_pixels.  Only the last stripe of the
+// image can be short, and a shard that owns it owns it last, so every earlier owned stripe is full.
+RDR_HD uint32_t stripe_pixel(uint32_t width, uint32_t rows, uint32_t index, uint32_t count, uint32_t k)
+{
+    if (count <= 1u || rows == 0u) return k;
+    const uint32_t per = rows * width;
+    const uint32_t s = k / per;
+    return (s * count + index) * per + (k - s * per);
+}
 
 struct Hit { int idx; float t; };
 

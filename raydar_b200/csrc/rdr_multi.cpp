@@ -55,6 +55,8 @@ struct MultiGpu {
     size_t root_capacity = 0;
     bool reduced = false;                    // root_sum holds the sum of the current accumulators
     uint32_t sample_count = 0;
+    int partition = RDR_PARTITION_SAMPLES, frame_partition = RDR_PARTITION_SAMPLES;   // requested / of the current frame
+    uint32_t stripe_rows = 16;
 };
 
 static int child_fail(RdrRenderer *owner, RdrRenderer *c, int st)
@@ -100,20 +102,26 @@ void multi_destroy(MultiGpu *m)
 
 void multi_set_config(MultiGpu *m, const RdrConfig &config) { m->config = config; for (RdrRenderer *c : m->child) rdr_set_max_bounces(c, config.max_bounces); }
 void multi_set_seed(MultiGpu *m, uint64_t seed) { m->seed = seed; }
+void multi_set_partition(MultiGpu *m, int partition, uint32_t stripe_rows) { m->partition = partition; m->stripe_rows = stripe_rows; }
 
 int multi_new_frame(RdrRenderer *owner, MultiGpu *m, const RdrSceneFlat *scene)
 {
     const uint32_t G = (uint32_t)m->child.size();
     const uint64_t S = m->config.max_sample_count;
     m->begin.assign(G, 0); m->count.assign(G, 0);
+    m->frame_partition = m->partition;
+    const bool stripes = m->frame_partition == RDR_PARTITION_STRIPES;
     for (uint32_t g = 0; g < G; ++g) {
-        const uint32_t b = (uint32_t)(S * g / G), e = (uint32_t)(S * (g + 1) / G);
+        // SAMPLES: device g renders sample indices [S g / G, S (g + 1) / G) of every pixel;
+        // STRIPES: device g renders every sample of its round-robin row stripes
+        const uint32_t b = stripes ? 0u : (uint32_t)(S * g / G), e = stripes ? (uint32_t)S : (uint32_t)(S * (g + 1) / G);
         m->begin[g] = b; m->count[g] = e - b;
         RdrRenderer *c = m->child[g];
         rdr_set_max_sample_count(c, e - b);
         rdr_set_max_bounces(c, m->config.max_bounces);
         rdr_set_seed(c, m->seed);
         rdr_set_sample_offset(c, b);
+        rdr_set_row_stripes(c, stripes ? m->stripe_rows : 0u, g, stripes ? G : 1u);
         int st = rdr_new_frame(c, scene);
         if (st != RDR_OK) return child_fail(owner, c, st);
     }
@@ -141,7 +149,7 @@ static int render_shares(RdrRenderer *owner, MultiGpu *m, const std::vector<uint
     for (uint32_t g = 0; g < G; ++g) {
         int st = api_render_finish(m->child[g], share[g]);
         if (st != RDR_OK) return child_fail(owner, m->child[g], st);
-        m->sample_count += share[g];
+        if (m->frame_partition != RDR_PARTITION_STRIPES || g == 0u) m->sample_count += share[g];   // stripes: every device renders the same sample indices
     }
     m->reduced = false;
     return RDR_OK;
@@ -151,7 +159,8 @@ int multi_render_samples(RdrRenderer *owner, MultiGpu *m, uint32_t n)
 {
     const uint32_t G = (uint32_t)m->child.size();
     std::vector<uint32_t> share(G, 0);
-    for (uint32_t g = 0; g < G; ++g) share[g] = std::min(n / G + (g < n % G ? 1u : 0u), api_samples_left(m->child[g]));
+    const bool stripes = m->frame_partition == RDR_PARTITION_STRIPES;
+    for (uint32_t g = 0; g < G; ++g) share[g] = std::min(stripes ? n : n / G + (g < n % G ? 1u : 0u), api_samples_left(m->child[g]));
     return render_shares(owner, m, share);
 }
 

@@ -1,5 +1,5 @@
 // rdr_multi.h -- single-process multi-GPU renderer: one sub-renderer per device, sample-range
-// sharding, one ncclReduce(sum, f32) of the per-GPU accumulators onto devices[0].
+// sharding (or round-robin row stripes, rdr_set_partition), one ncclReduce(sum, f32) of the per-GPU accumulators onto devices[0].
 // The reference has no multi-device path; this is the B200 extension behind rdr_create_multi.
 #pragma once
 
@@ -28,6 +28,7 @@ uint32_t multi_sample_count(const MultiGpu *m);
 int multi_profiler(const MultiGpu *m, RdrProfiler *out);
 void multi_set_config(MultiGpu *m, const RdrConfig &config);
 void multi_set_seed(MultiGpu *m, uint64_t seed);
+void multi_set_partition(MultiGpu *m, int partition, uint32_t stripe_rows);
 
 // hooks implemented in rdr_api.cpp
 int api_fail(RdrRenderer *r, int status, const char *msg);

@@ -16,6 +16,18 @@ def strong_sample_range(rank: int, world: int, total_spp: int) -> tuple[int, int
     return b, e - b
 
 
+STRIPE_ROWS = 16
+
+
+def stripe_rows_owned(rank: int, world: int, height: int, stripe_rows: int = STRIPE_ROWS) -> list[int]:
+    """Image rows rank `rank` renders under row-stripe sharding: stripe s = rows [s*stripe_rows, (s+1)*stripe_rows)
+    belongs to rank s % world (the rule of rdr_set_row_stripes / stripe_pixel in rdr_layout.h).  The stripes of the
+    ranks are disjoint and cover the image, so reducing the accumulators adds zeros: bit-identical to one GPU."""
+    if world <= 1 or stripe_rows <= 0:
+        return list(range(height))
+    return [y for y in range(height) if (y // stripe_rows) % world == rank]
+
+
 def reduce_accum(accum, dst: int = 0):
     """Sums the per-rank float RGBA accumulators onto rank `dst` (in place on dst)."""
     import torch.distributed as dist

@@ -1,7 +1,7 @@
 // raydar-cuda -- headless driver over the C ABI, mirroring the reference's `raydar` binary
 // (src/main.rs:10-107, flags of src/cli/mod.rs:12-27,66-68):
 //
-//   raydar-cuda [--max-sample-count N] [--max-bounces B] [-o out.png] [--gpus G] [--resolution WxH]
+//   raydar-cuda [--max-sample-count N] [--max-bounces B] [-o out.png] [--gpus G] [--partition samples|stripes] [--resolution WxH]
 //               [--seed S] [scene.rscn]
 //
 // Same info / profiling printout as the reference plus a samples/s line.  No scene file = Scene::default()
@@ -26,7 +26,7 @@ int main(int argc, char **argv)
 {
     RdrConfig config{1024u, 12u};                         // RendererConfig::default(), renderer/mod.rs:16-23
     std::string output = "output.png", scene_file;
-    int gpus = 1;
+    int gpus = 1, partition = RDR_PARTITION_SAMPLES;
     uint32_t width = 0, height = 0;
     unsigned long long seed = 0x5EED;
     for (int i = 1; i < argc; ++i) {
@@ -39,13 +39,19 @@ int main(int argc, char **argv)
         else if (a == "--max-bounces") config.max_bounces = (uint32_t)strtoul(value("--max-bounces"), nullptr, 10);
         else if (a == "-o" || a == "--output") output = value("--output");
         else if (a == "--gpus") gpus = atoi(value("--gpus"));
+        else if (a == "--partition") {
+            const std::string v = value("--partition");
+            if (v == "samples") partition = RDR_PARTITION_SAMPLES;
+            else if (v == "stripes") partition = RDR_PARTITION_STRIPES;
+            else { fprintf(stderr, "error: --partition expects samples|stripes\n"); return 2; }
+        }
         else if (a == "--seed") seed = strtoull(value("--seed"), nullptr, 0);
         else if (a == "--resolution") {
             if (sscanf(value("--resolution"), "%ux%u", &width, &height) != 2) { fprintf(stderr, "error: --resolution expects WxH\n"); return 2; }
         } else if (a == "--cuda" || a == "--cpu") {
             if (a == "--cpu") { fprintf(stderr, "error: this binary only has the CUDA backend (no CPU fallback)\n"); return 2; }
         } else if (a == "-h" || a == "--help") {
-            printf("Usage: raydar-cuda [--max-sample-count N] [--max-bounces B] [-o out.png] [--gpus G] [--resolution WxH] [--seed S] [scene.rscn]\n");
+            printf("Usage: raydar-cuda [--max-sample-count N] [--max-bounces B] [-o out.png] [--gpus G] [--partition samples|stripes] [--resolution WxH] [--seed S] [scene.rscn]\n");
             return 0;
         } else if (!a.empty() && a[0] == '-') { fprintf(stderr, "error: unexpected argument '%s'\n", a.c_str()); return 2; }
         else scene_file = a;
@@ -62,6 +68,7 @@ int main(int argc, char **argv)
     for (int g = 0; g < gpus; ++g) devices.push_back(g);
     if ((gpus > 1 ? rdr_create_multi(&config, gpus, devices.data(), &r) : rdr_create(&config, 0, &r)) != RDR_OK) return die("renderer", nullptr);
     rdr_set_seed(r, seed);
+    if (gpus > 1 && rdr_set_partition(r, partition, 0) != RDR_OK) return die("partition", r);
 
     // print_info, main.rs:26-59
     printf("=== Raydar (CUDA backend) %s ===\n", rdr_version());

@@ -45,4 +45,6 @@ extern "C" {
     pub fn rdr_set_max_sample_count(r: *mut RdrRenderer, count: u32) -> c_int;
     pub fn rdr_set_max_bounces(r: *mut RdrRenderer, bounces: u32) -> c_int;
     pub fn rdr_set_seed(r: *mut RdrRenderer, seed: u64) -> c_int;
+    /// multi-GPU handle: 0 = sample ranges (default), 1 = round-robin row stripes (bit-identical to one GPU)
+    pub fn rdr_set_partition(r: *mut RdrRenderer, partition: c_int, stripe_rows: u32) -> c_int;
 }

@@ -205,6 +205,38 @@ int hs_render(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t samp
     return RDR_OK;
 }
 
+// the render kernel's pixel hand-out for one row-stripe shard (rdr_set_row_stripes): k = 0 .. owned_pixels - 1 in the
+// order the atomic counter deals them, mapped by the product's stripe_pixel().  Returns owned_pixels.
+uint32_t hs_stripe_pixels(uint32_t width, uint32_t height, uint32_t rows, uint32_t index, uint32_t count, uint32_t *pixels)
+{
+    const uint32_t n = stripe_owned_pixels(width, height, rows, index, count);
+    if (pixels) for (uint32_t k = 0; k < n; ++k) pixels[k] = stripe_pixel(width, rows, index, count, k);
+    return n;
+}
+
+// hs_render restricted to one row-stripe shard: only the owned pixels of `accum` are touched
+int hs_render_stripes(const RdrSceneFlat *sc, uint64_t seed, uint32_t sample_begin, uint32_t n_samples, uint32_t max_bounces,
+                      uint32_t rows, uint32_t index, uint32_t count, float *accum)
+{
+    Packed pk(sc, false);
+    if (pk.status != RDR_OK) return pk.status;
+    pk.P.seed_lo = (uint32_t)seed; pk.P.seed_hi = (uint32_t)(seed >> 32);
+    pk.P.max_bounces = max_bounces; pk.P.sample_begin = sample_begin; pk.P.sample_count = n_samples;
+    const int64_t n = (int64_t)stripe_owned_pixels(sc->width, sc->height, rows, index, count);
+#pragma omp parallel
+    {
+        std::vector<uint32_t> masks(pk.masks.size());
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t k = 0; k < n; ++k) {
+            const uint32_t p = stripe_pixel(sc->width, rows, index, count, (uint32_t)k);
+            f4 acc; acc.x = accum[4 * p]; acc.y = accum[4 * p + 1]; acc.z = accum[4 * p + 2]; acc.w = accum[4 * p + 3];
+            acc = render_pixel<0>(pk.P, pk.S, masks.data(), 1, p, acc, nullptr);
+            accum[4 * p] = acc.x; accum[4 * p + 1] = acc.y; accum[4 * p + 2] = acc.z; accum[4 * p + 3] = acc.w;
+        }
+    }
+    return RDR_OK;
+}
+
 int hs_trace_path(const RdrSceneFlat *sc, int use_cull, uint64_t seed, uint32_t x, uint32_t y, uint32_t sample,
                   uint32_t max_bounces, RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float rgba[4])
 {

@@ -59,6 +59,9 @@ def lib():
         L.hs_bvh2_warp_sim.argtypes = [sfp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
         L.hs_bvh2_perray_sim.argtypes = [sfp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
         L.hs_cluster_info.argtypes = [sfp, u32p, u32p]
+        L.hs_stripe_pixels.argtypes = [C.c_uint32] * 5 + [u32p]
+        L.hs_stripe_pixels.restype = C.c_uint32
+        L.hs_render_stripes.argtypes = [sfp, C.c_uint64] + [C.c_uint32] * 6 + [fp]
         _lib = L
     return _lib
 
@@ -95,6 +98,24 @@ def render(scene, seed, sample_begin, n_samples, max_bounces, accum=None, use_cu
     st = TraceStats()
     _ok(lib().hs_render(C.byref(f), int(use_cull), seed, sample_begin, n_samples, max_bounces, _fp(accum), C.byref(st)))
     return accum, st
+
+
+def stripe_pixels(width, height, rows, index, count):
+    """Pixel indices one row-stripe shard renders, in hand-out order (the product's stripe_pixel())."""
+    L = lib()
+    args = (width, height, rows, index, count)
+    n = L.hs_stripe_pixels(*args, None)
+    out = np.zeros(n, np.uint32)
+    L.hs_stripe_pixels(*args, out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return out
+
+
+def render_stripes(scene, seed, sample_begin, n_samples, max_bounces, rows, index, count, accum=None):
+    f = rb._as_flat(scene)
+    if accum is None:
+        accum = np.zeros((f.height, f.width, 4), np.float32)
+    _ok(lib().hs_render_stripes(C.byref(f), seed, sample_begin, n_samples, max_bounces, rows, index, count, _fp(accum)))
+    return accum
 
 
 def trace_path(scene, x, y, sample, seed, max_bounces, use_cull=True, capacity=128):

@@ -174,6 +174,48 @@ def test_progressive_equals_one_shot_and_sharding(rb, benchmark_scene):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("count,rows", [(2, 16), (3, 7), (8, 16)])
+def test_row_stripe_shards_sum_bit_identical(rb, orc, default_scene, count, rows):
+    """Image-tile sharding (rdr_set_row_stripes): every shard renders all samples of its round-robin row stripes into
+    a zeroed W x H accumulator; the shards are disjoint, so their sum is bit-identical to the whole-image render
+    and to the oracle (107 x 61: the last stripe is short)."""
+    scene = default_scene.with_resolution(107, 61)
+    spp, seed = 5, 99
+    want = orc.render(scene, seed, 0, spp, 12, n_threads=orc.max_threads())
+    total = np.zeros_like(want)
+    for index in range(count):
+        r = rb.Renderer(rb.RendererConfig(spp, 12)); r.set_seed(seed); r.set_row_stripes(rows, index, count)
+        r.new_frame(scene); r.render_samples(spp)
+        acc = r.read_accum()
+        mine = np.zeros(61, bool); mine[[y for y in range(61) if (y // rows) % count == index]] = True
+        assert np.all(u32(acc[~mine]) == 0)
+        assert np.array_equal(u32(acc[mine]), u32(want[mine]))
+        total += acc
+        r.close()
+    assert np.array_equal(u32(total), u32(want))
+
+
+def test_row_stripes_1080p_fused_and_reset(rb, benchmark_scene):
+    """The same property at the bench resolution on the fused scan, and rdr_set_row_stripes(…, count = 1) restores the
+    whole image on the same handle."""
+    scene = benchmark_scene.with_resolution(1920, 1080)
+    spp = 2
+    a = rb.Renderer(rb.RendererConfig(spp, 12)); a.set_seed(5)
+    a.render_frame(scene); whole = a.read_accum()
+    total = np.zeros_like(whole)
+    for index in range(2):
+        a.set_row_stripes(16, index, 2)
+        a.new_frame(scene); a.render_samples(spp)
+        total += a.read_accum()
+    assert np.array_equal(u32(total), u32(whole))
+    a.set_row_stripes(0, 0, 1)
+    a.new_frame(scene); a.render_samples(spp)
+    assert np.array_equal(u32(a.read_accum()), u32(whole))
+    with pytest.raises(rb.RaydarError):
+        a.set_row_stripes(16, 2, 2)
+    a.close()
+
+
 def test_converged_psnr_independent_streams(rb, orc, default_scene):
     """North-star gate: at high spp the converged GPU image reaches PSNR >= 40 dB against the CPU backend's
     converged image, with bounded per-channel mean error.  The two sides use DIFFERENT RNG seeds (independent
