@@ -20,7 +20,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libraydar_cuda.so")
+# RAYDAR_CUDA_LIB: another build of the same library (kernel experiments: scripts/gpu_variants.sh); still no fallback
+LIB_PATH = os.environ.get("RAYDAR_CUDA_LIB") or os.path.join(_HERE, "libraydar_cuda.so")
 
 SPHERE, CUBE = 0, 1
 WORLD_SKY, WORLD_SOLID, WORLD_TRANSPARENT = 0, 1, 2

@@ -31,6 +31,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Kernel experiments: libraydar_cuda_<name>.so with extra -D flags, next to the product library (git-ignored;
+    selected with RAYDAR_CUDA_LIB).  Not part of build()."""
+    out = os.path.join(HERE, f"libraydar_cuda_{name}.so")
+    cmd = [
+        nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+        "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
+        "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall", "-shared",
+        "-I", os.path.join(ROOT, "include"), "-I", CSRC, *[f"-D{d}" for d in defines],
+        *[os.path.join(CSRC, s) for s in SOURCES], "-o", out, "-ldl",
+    ]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
     if not force and not needs_build():
         return LIB

@@ -162,18 +162,38 @@ __device__ __forceinline__ SlabRay slab_ray_setup(const CullConsts &cc, v3 o, v3
 }
 
 // the ray against the first n_top (<= 32) top-level boxes of the kernel parameters: bit k = box k may be hit.
-// Fully unrolled so that every operand is a compile-time constant-bank address (LDCU.128 into uniform registers).
+// The operands are constant-bank addresses (LDCU.128 into uniform registers).  RDR_TOP_GROUP pairs are tested per
+// iteration of a warp-uniform loop (the constant bank is indexed with a uniform register): the fully unrolled form
+// (RDR_TOP_GROUP = 16) is 8 KB of code for 32 boxes, a quarter of the instruction cache the sample loop lives in.
+#ifndef RDR_TOP_GROUP
+#define RDR_TOP_GROUP 16u
+#endif
+__device__ __forceinline__ uint32_t top_pair_test(const TopPair &t, f32x2 rho2, const SlabRay &R)
+{
+    const f32x2 sp = pk2(t.sphere[0], t.sphere[1]);
+    const f32x2 ex = fma2(sp, rho2, pk2(t.ex[0], t.ex[1])), ey = fma2(sp, rho2, pk2(t.ey[0], t.ey[1])), ez = fma2(sp, rho2, pk2(t.ez[0], t.ez[1]));
+    return slab_pair(pk2(t.cx[0], t.cx[1]), pk2(t.cy[0], t.cy[1]), pk2(t.cz[0], t.cz[1]), ex, ey, ez, R.rx, R.ry, R.rz, R.nx, R.ny, R.nz);
+}
+
 __device__ __forceinline__ uint32_t top_scan(const TopParams &T, uint32_t n_top, const SlabRay &R)
 {
     uint32_t m = 0u;
     const f32x2 rho2 = bc2(R.rho);
+    if (RDR_TOP_GROUP >= FUSED_MAX_TOP / 2u) {
 #pragma unroll
-    for (uint32_t k = 0; k < FUSED_MAX_TOP / 2u; ++k) {
-        if ((k & 3u) == 0u && 2u * k >= n_top) break;
-        const TopPair &t = T.pair[k];
-        const f32x2 sp = pk2(t.sphere[0], t.sphere[1]);
-        const f32x2 ex = fma2(sp, rho2, pk2(t.ex[0], t.ex[1])), ey = fma2(sp, rho2, pk2(t.ey[0], t.ey[1])), ez = fma2(sp, rho2, pk2(t.ez[0], t.ez[1]));
-        m |= slab_pair(pk2(t.cx[0], t.cx[1]), pk2(t.cy[0], t.cy[1]), pk2(t.cz[0], t.cz[1]), ex, ey, ez, R.rx, R.ry, R.rz, R.nx, R.ny, R.nz) << (2u * k);
+        for (uint32_t k = 0; k < FUSED_MAX_TOP / 2u; ++k) {
+            if ((k & 3u) == 0u && 2u * k >= n_top) break;
+            m |= top_pair_test(T.pair[k], rho2, R) << (2u * k);
+        }
+    } else {
+        const uint32_t n_groups = (n_top + 2u * RDR_TOP_GROUP - 1u) / (2u * RDR_TOP_GROUP);
+#pragma unroll 1
+        for (uint32_t g = 0; g < n_groups; ++g) {
+            uint32_t bits = 0u;
+#pragma unroll
+            for (uint32_t j = 0; j < RDR_TOP_GROUP; ++j) bits |= top_pair_test(T.pair[g * RDR_TOP_GROUP + j], rho2, R) << (2u * j);
+            m |= bits << (2u * RDR_TOP_GROUP * g);
+        }
     }
     if (n_top < 32u) m &= (1u << n_top) - 1u;
     return m;

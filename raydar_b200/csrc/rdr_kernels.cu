@@ -26,17 +26,26 @@ namespace rdr {
 // global memory / L2 and only the scratch words live in shared memory.
 // MODE 5 (fused scan) always runs on a staged blob: returning `smem` itself (not a select between two pointers)
 // lets the compiler prove the address space, so every scene access becomes an LDS with a 32-bit address.
-template <int MODE>
+// The fused kernels (MODE 5 / 6) need only the blob's prefix (obj_geom, material and the fused scan's sections:
+// SceneLayout::fused_stage_bytes) unless they also run the per-lane twin of the scan (FULL: trace_path_kernel).
+template <int MODE, bool FULL>
+__device__ __forceinline__ uint32_t staged_bytes(const FrameParams &P)
+{
+    return ((MODE == 5 || MODE == 6) && !FULL) ? P.lay.fused_stage_bytes : P.lay.blob_bytes;
+}
+template <int MODE, bool FULL = false>
 __device__ __forceinline__ const unsigned char *stage_scene(unsigned char *smem, const FrameParams &P)
 {
     if (MODE == 7 || (MODE < 5 && !P.staged)) return P.blob;       // MODE 7 reads the scene in place (global memory / L2)
-    stage_blob(smem, P.blob, P.lay.blob_bytes, bar_ptr(smem, P.lay));
+    const uint32_t bytes = staged_bytes<MODE, FULL>(P);
+    stage_blob(smem, P.blob, bytes, reinterpret_cast<uint64_t *>(smem + bytes));
     return smem;
 }
-template <int MODE>
+template <int MODE, bool FULL = false>
 __device__ __forceinline__ uint32_t *scratch_base(unsigned char *smem, const FrameParams &P)
 {
-    return (MODE != 7 && (MODE >= 5 || P.staged)) ? mask_base(smem, P.lay) : reinterpret_cast<uint32_t *>(smem);
+    return (MODE != 7 && (MODE >= 5 || P.staged)) ? reinterpret_cast<uint32_t *>(smem + staged_bytes<MODE, FULL>(P) + 16u)
+                                                   : reinterpret_cast<uint32_t *>(smem);
 }
 
 // nearest hit for every lane of the warp (alive = the lane has a ray).  MODE 4 regroups the work across the warp
@@ -60,6 +69,37 @@ __device__ __forceinline__ Hit trace_warp(const SceneView &S, const FrameParams 
     return h;
 }
 
+// Cold per-lane state (accumulator, primary direction, primary hit: LaneStateT in rdr_trace.cuh) in shared memory:
+// word i of the lane at base[i * BLOCK + threadIdx.x] (conflict-free columns).  The COLD variants of the warp-cooperative
+// kernels run their hot loop with 9 registers fewer, and with 18 fewer inside the nearest-hit search (lane_park), which is
+// what lets a 896-thread CTA (28 warps per SM at 72 registers) run without spills.
+template <int BLOCK>
+struct ColdShared {
+    float *col;             // &base[threadIdx.x]
+    __device__ __forceinline__ float get(int i) const { return col[i * BLOCK]; }
+    __device__ __forceinline__ void set(int i, float v) { col[i * BLOCK] = v; }
+};
+template <int BLOCK, bool COLD> struct lane_state_of { typedef LaneState type; };
+template <int BLOCK> struct lane_state_of<BLOCK, true> { typedef LaneStateT<ColdShared<BLOCK> > type; };
+// the path state the scan does not need (throughput, light, RNG counters: 9 words) waits in the lane's shared-memory
+// columns while the warp is inside the nearest-hit search
+template <class ST> __device__ __forceinline__ void lane_park(ST &) {}
+template <class ST> __device__ __forceinline__ void lane_unpark(ST &) {}
+template <int BLOCK> __device__ __forceinline__ void lane_park(LaneStateT<ColdShared<BLOCK> > &st)
+{
+    st.cold.set(COLD_PARK + 0, st.light.x); st.cold.set(COLD_PARK + 1, st.light.y); st.cold.set(COLD_PARK + 2, st.light.z);
+    st.cold.set(COLD_PARK + 3, st.atten.x); st.cold.set(COLD_PARK + 4, st.atten.y); st.cold.set(COLD_PARK + 5, st.atten.z);
+    st.cold.set(COLD_PARK + 6, u2f(st.pixel)); st.cold.set(COLD_PARK + 7, u2f(st.s)); st.cold.set(COLD_PARK + 8, u2f(st.bounce));
+}
+template <int BLOCK> __device__ __forceinline__ void lane_unpark(LaneStateT<ColdShared<BLOCK> > &st)
+{
+    st.light = mk3(st.cold.get(COLD_PARK + 0), st.cold.get(COLD_PARK + 1), st.cold.get(COLD_PARK + 2));
+    st.atten = mk3(st.cold.get(COLD_PARK + 3), st.cold.get(COLD_PARK + 4), st.cold.get(COLD_PARK + 5));
+    st.pixel = f2u(st.cold.get(COLD_PARK + 6)); st.s = f2u(st.cold.get(COLD_PARK + 7)); st.bounce = f2u(st.cold.get(COLD_PARK + 8));
+}
+__device__ __forceinline__ void cold_bind(ColdRegs &, unsigned char *) {}
+template <int BLOCK> __device__ __forceinline__ void cold_bind(ColdShared<BLOCK> &c, unsigned char *base) { c.col = reinterpret_cast<float *>(base) + threadIdx.x; }
+
 // ---- the sample loop (LaneState / lane_shade / trace_brute in rdr_trace.cuh) ------------------------------
 // Persistent lanes in warp lock-step.  The grid is sized to the machine (SMs x resident CTAs), not to the
 // image.  Each iteration:
@@ -71,7 +111,7 @@ __device__ __forceinline__ Hit trace_warp(const SceneView &S, const FrameParams 
 //      accumulator (one 16-byte store per pixel per launch, after one 16-byte load when it claimed it).
 // A pixel is always processed by exactly one lane with its samples in ascending order, so results do not
 // depend on the schedule (bit-identical to the per-pixel host loop).
-template <int MODE, int BLOCK, int MIN_CTAS>
+template <int MODE, int BLOCK, int MIN_CTAS, bool COLD>
 __global__ void __launch_bounds__(BLOCK, MIN_CTAS) render_kernel(const __grid_constant__ FrameParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -79,7 +119,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) render_kernel(const __grid_co
     uint32_t *scratch0 = scratch_base<MODE>(smem, P);
     const uint32_t n_owned = P.owned_pixels;        // the whole image, or this shard's row stripes (rdr_set_row_stripes)
 
-    LaneState st;
+    typename lane_state_of<BLOCK, COLD>::type st;
+    // the cold columns follow the per-warp scratch of the cooperative search (mode_smem_bytes)
+    cold_bind(st.cold, reinterpret_cast<unsigned char *>(scratch0 + BLOCK) + (BLOCK / 32) * (MODE == 7 ? BVH2_WARP_BYTES : FUSED_WARP_BYTES));
     lane_init(st, scratch0 + threadIdx.x);
     bool exhausted = false;
     for (;;) {
@@ -88,13 +130,15 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) render_kernel(const __grid_co
             if (k >= n_owned) { exhausted = true; break; }
             const uint32_t pixel = stripe_pixel(P.cam.width, P.stripe_rows, P.stripe_index, P.stripe_count, k);
             lane_start_pixel(P, pixel, P.accum[pixel], st);
-            if (!st.alive) P.accum[pixel] = st.acc;      // nothing to trace (no samples or no bounces)
+            if (!st.alive) P.accum[pixel] = st.acc();      // nothing to trace (no samples or no bounces)
         }
         if (!__any_sync(0xffffffffu, st.alive)) break;
         // every lane passes through the same top-level statements each iteration, so the full-mask
         // __syncwarp()s are safe; they pin the reconvergence points between the phases
         const bool tracing = st.alive;
+        lane_park(st);
         const Hit h = trace_warp<MODE>(S, P, scratch0, tracing, st.ro, st.rd);
+        lane_unpark(st);
         if (tracing) lane_accept_hit(st, h);
         __syncwarp();
         if (tracing && st.hit.idx < 0) lane_miss(P, st);
@@ -103,7 +147,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) render_kernel(const __grid_co
         while (__any_sync(0xffffffffu, shade)) {             // one pass; a second only after a bounce-limit restart
             if (shade) shade = !lane_shade_hit(P, S, st) && st.alive;
         }
-        if (tracing && !st.alive) P.accum[st.pixel] = st.acc;
+        if (tracing && !st.alive) P.accum[st.pixel] = st.acc();
     }
 }
 
@@ -164,8 +208,8 @@ __global__ void __launch_bounds__(RDR_BLOCK, 2) trace_path_kernel(const __grid_c
                                                                  float *__restrict__ rgba)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const SceneView S = scene_view(stage_scene<MODE>(smem, P), P.lay);
-    uint32_t *masks = scratch_base<MODE>(smem, P) + threadIdx.x;          // (MODE 4 walks the path with its per-lane twin)
+    const SceneView S = scene_view(stage_scene<MODE, true>(smem, P), P.lay);      // the per-lane twins read the whole blob
+    uint32_t *masks = scratch_base<MODE, true>(smem, P) + threadIdx.x;    // (MODE 4 - 7 walk the path with their per-lane twin)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     *n_steps = trace_path_lane<MODE>(P, S, masks, blockDim.x, x, y, sample, steps, capacity, rgba);
 }
@@ -221,16 +265,20 @@ static inline uint32_t scratch_words(const SceneLayout &L)
     return chunks > CL_SCRATCH ? chunks : CL_SCRATCH;       // flat-scan masks or cluster masks + queue
 }
 
-// dynamic shared memory of one CTA running kernel variant `mode` (the MODE template argument)
-static size_t mode_smem_bytes(const SceneLayout &L, bool staged, uint32_t block, int mode)
+// dynamic shared memory of one CTA running kernel variant `mode` (the MODE template argument).
+//   cold: the kernel keeps the cold / parked lane state in shared-memory columns (render_kernel<.., COLD = true>)
+//   full: a fused kernel that stages the whole blob, not only its prefix (trace_path_kernel)
+static size_t mode_smem_bytes(const SceneLayout &L, bool staged, uint32_t block, int mode, bool cold = false, bool full = false)
 {
     const size_t warps = (block + 31u) / 32u;
+    const size_t cold_bytes = cold ? (size_t)block * (COLD_WORDS + COLD_PARK_WORDS) * sizeof(float) : 0u;
     size_t scratch;
-    if (mode == 7) return (size_t)block * sizeof(uint32_t) + warps * BVH2_WARP_BYTES;              // never staged
-    if (mode >= 5) scratch = (size_t)block * sizeof(uint32_t) + warps * FUSED_WARP_BYTES;        // one word per lane + per-warp regions
+    if (mode == 7) return (size_t)block * sizeof(uint32_t) + warps * BVH2_WARP_BYTES + cold_bytes;     // never staged
+    if (mode >= 5) scratch = (size_t)block * sizeof(uint32_t) + warps * FUSED_WARP_BYTES + cold_bytes; // one word per lane + per-warp regions
     else if (mode == 4) scratch = (size_t)block * sizeof(uint32_t) + warps * COOP_WARP_BYTES;
-    else scratch = (size_t)scratch_words(L) * block * sizeof(uint32_t);                           // per-lane words
-    return (staged ? (size_t)L.blob_bytes + 16u : 0u) + scratch;
+    else scratch = (size_t)scratch_words(L) * block * sizeof(uint32_t);                                // per-lane words
+    const size_t blob = (mode >= 5 && !full) ? L.fused_stage_bytes : L.blob_bytes;
+    return (staged ? blob + 16u : 0u) + scratch;
 }
 
 // the largest footprint any variant of this layout needs (feasibility check in rdr_api.cpp)
@@ -276,69 +324,89 @@ static cudaError_t set_smem(K kernel, size_t bytes)
         else { KERNEL(0, __VA_ARGS__); }                                  \
     } while (0)
 
-// CTA shape of the render kernel.  The scans that keep per-lane state only (MODE 0-4) run 3 CTAs of 256 threads per
-// SM (80 registers).  The fused scan (MODE 5) is latency-bound on its shuffle / shared-memory chains and wants more
-// resident warps: ONE large CTA per SM shares a single staged copy of the scene, which leaves the shared memory for
-// the warps' scratch.  Measured (profiles/sweep_r01n.txt, Msamples/s): 1 x 768 threads @ 80 registers 5276, 3 x 256 @ 80
-// 5221, 1 x 896 @ 72 5250, 1 x 1024 @ 64 4917 (spills) -> 1 x 768.  RDR_FUSED_CTA (experiments) = 0: 3 x 256,
-// 1: 1 x 896, 2: 1 x 1024, 3: 1 x 768 (default).
-static int fused_cta_config()
+// ---- CTA shape of the render kernel ----------------------------------------------------------------------------
+// The scans that keep per-lane state only (MODE 0-4) run 3 CTAs of 256 threads per SM (80 registers).  The warp-
+// cooperative kernels are latency-bound on their shuffle / shared-memory chains and want as many resident warps as the
+// register file allows: ONE large CTA per SM shares a single staged copy of the scene, and the COLD variants keep the
+// lane state the search does not touch in shared memory.  Measured on benchmark.rscn (Msamples/s, profiles/variants_r02*):
+//   768 threads @ 80 registers, state in registers   5370     (42 B of spills)
+//   768 @ 80, cold + parked state in shared memory   5680
+//   896 @ 72, cold + parked                          5780     <- default when the footprint fits
+//  1024 @ 64, cold                                   5410     (138 B of spills)
+// The shape is chosen per frame: the largest that fits the device's opt-in shared memory.
+struct RenderShape { uint32_t block; bool cold; };
+
+static size_t smem_optin_limit()
 {
-    static int cfg = -1;
-    if (cfg < 0) { const char *e = getenv("RDR_FUSED_CTA"); cfg = e ? atoi(e) : 3; if (cfg < 0 || cfg > 3) cfg = 3; }
-    return cfg;
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 48u << 10;
+    return (size_t)v;
 }
-// CTA shape of the cooperative hierarchy kernel.  Measured on config 4 (profiles/sweep_r01u.txt, Msamples/s): 640 threads
-// @ 94 registers (no spills) 143.7, 768 @ 80 140.7, 512 @ 94 129.5.  RDR_BVH2_CTA (experiments): 0 = 768, 1 = 640, 2 = 512.
-static int bvh2_cta_config()
+static int env_int(const char *name, int dflt)
 {
-    static int cfg = -1;
-    if (cfg < 0) { const char *e = getenv("RDR_BVH2_CTA"); cfg = e ? atoi(e) : 1; if (cfg < 0 || cfg > 2) cfg = 1; }
-    return cfg;
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
-static uint32_t render_block(int mode)
+// RDR_FUSED_CTA / RDR_BVH2_CTA (experiments) force a shape: fused 1 = 896 cold, 3 = 768 cold, 4 = 768 registers,
+// 0 = 3 x 256 registers; hierarchy 0 = 768, 1 = 640, 2 = 512 (registers).
+static RenderShape render_shape(const FrameParams &P, int mode)
 {
-    if (mode < 5) return RDR_BLOCK;
-    if (mode == 7) return bvh2_cta_config() == 1 ? 640u : (bvh2_cta_config() == 2 ? 512u : 768u);
-    if (mode >= 6) return 768u;
-    switch (fused_cta_config()) { case 1: return 896u; case 2: return 1024u; case 3: return 768u; default: return RDR_BLOCK; }
+    if (mode < 5) return RenderShape{RDR_BLOCK, false};
+    const size_t limit = smem_optin_limit();
+    if (mode == 7) {
+        static const int cfg = env_int("RDR_BVH2_CTA", -1);
+        switch (cfg) {
+        case 0: return RenderShape{768u, false};
+        case 2: return RenderShape{512u, false};
+        default: return RenderShape{640u, false};      // its per-ray stacks (9.9 KB per warp) leave no room for cold columns
+        }
+    }
+    static const int cfg = env_int("RDR_FUSED_CTA", -1);
+    if (cfg == 0) return RenderShape{RDR_BLOCK, false};
+    if (cfg == 1) return RenderShape{896u, true};
+    if (cfg == 3) return RenderShape{768u, true};
+    if (cfg == 4) return RenderShape{768u, false};
+    if (mode_smem_bytes(P.lay, true, 896u, mode, true) <= limit) return RenderShape{896u, true};
+    if (mode_smem_bytes(P.lay, true, 768u, mode, true) <= limit) return RenderShape{768u, true};
+    return RenderShape{768u, false};
 }
 
-// calls F(kernel) with the render kernel instantiation for `mode`
-#define RDR_RENDER_DISPATCH(mode, F)                                                                  \
+// calls F(kernel) with the render kernel instantiation for `mode` and `shape`
+#define RDR_RENDER_DISPATCH(mode, shape, F)                                                           \
     do {                                                                                              \
         if ((mode) == 7) {                                                                            \
-            switch (bvh2_cta_config()) {                                                              \
-            case 1: F((render_kernel<7, 640, 1>)); break;                                             \
-            case 2: F((render_kernel<7, 512, 1>)); break;                                             \
-            default: F((render_kernel<7, 768, 1>)); break;                                            \
-            }                                                                                         \
+            if ((shape).block == 768u) F((render_kernel<7, 768, 1, false>));                          \
+            else if ((shape).block == 512u) F((render_kernel<7, 512, 1, false>));                     \
+            else F((render_kernel<7, 640, 1, false>));                                                \
         }                                                                                             \
-        else if ((mode) == 6) { F((render_kernel<6, 768, 1>)); }                                      \
+        else if ((mode) == 6) {                                                                       \
+            if ((shape).cold) { if ((shape).block == 896u) F((render_kernel<6, 896, 1, true>)); else F((render_kernel<6, 768, 1, true>)); } \
+            else if ((shape).block == 768u) F((render_kernel<6, 768, 1, false>));                     \
+            else F((render_kernel<6, RDR_BLOCK, 3, false>));                                          \
+        }                                                                                             \
         else if ((mode) == 5) {                                                                       \
-            switch (fused_cta_config()) {                                                             \
-            case 1: F((render_kernel<5, 896, 1>)); break;                                             \
-            case 2: F((render_kernel<5, 1024, 1>)); break;                                            \
-            case 3: F((render_kernel<5, 768, 1>)); break;                                             \
-            default: F((render_kernel<5, RDR_BLOCK, 3>)); break;                                      \
-            }                                                                                         \
+            if ((shape).cold) { if ((shape).block == 896u) F((render_kernel<5, 896, 1, true>)); else F((render_kernel<5, 768, 1, true>)); } \
+            else if ((shape).block == 768u) F((render_kernel<5, 768, 1, false>));                     \
+            else F((render_kernel<5, RDR_BLOCK, 3, false>));                                          \
         }                                                                                             \
-        else if ((mode) == 4) { F((render_kernel<4, RDR_BLOCK, 3>)); }                                \
-        else if ((mode) == 3) { F((render_kernel<3, RDR_BLOCK, 3>)); }                                \
-        else if ((mode) == 2) { F((render_kernel<2, RDR_BLOCK, 3>)); }                                \
-        else if ((mode) == 1) { F((render_kernel<1, RDR_BLOCK, 3>)); }                                \
-        else { F((render_kernel<0, RDR_BLOCK, 3>)); }                                                 \
+        else if ((mode) == 4) { F((render_kernel<4, RDR_BLOCK, 3, false>)); }                         \
+        else if ((mode) == 3) { F((render_kernel<3, RDR_BLOCK, 3, false>)); }                         \
+        else if ((mode) == 2) { F((render_kernel<2, RDR_BLOCK, 3, false>)); }                         \
+        else if ((mode) == 1) { F((render_kernel<1, RDR_BLOCK, 3, false>)); }                         \
+        else { F((render_kernel<0, RDR_BLOCK, 3, false>)); }                                          \
     } while (0)
 
-size_t fused_smem_bytes(const SceneLayout &L) { return mode_smem_bytes(L, true, render_block(5), 5); }
+// the smallest footprint of the fused render kernel (rdr_api.cpp: does the fused scan fit at all?)
+size_t fused_smem_bytes(const SceneLayout &L) { return mode_smem_bytes(L, true, 768u, 5, false); }
 
 cudaError_t launch_render(const FrameParams &P, int variant, int resident_ctas, cudaStream_t stream)
 {
     const uint32_t n_pixels = P.owned_pixels;       // pixels this launch hands out (all of them, or the shard's stripes)
     if (n_pixels == 0u) return cudaSuccess;
     const int mode = mode_of(P, variant);
-    const uint32_t block = render_block(mode);
-    const size_t smem = mode_smem_bytes(P.lay, P.staged != 0u, block, mode);
+    const RenderShape shape = render_shape(P, mode);
+    const uint32_t block = shape.block;
+    const size_t smem = mode_smem_bytes(P.lay, P.staged != 0u, block, mode, shape.cold);
     // persistent grid: every resident CTA slot of the device, but no more CTAs than there are pixels to hand out
     uint32_t grid = (uint32_t)(resident_ctas > 0 ? resident_ctas : 1);
     const uint32_t needed = (n_pixels + block - 1u) / block;
@@ -346,7 +414,7 @@ cudaError_t launch_render(const FrameParams &P, int variant, int resident_ctas, 
     cudaError_t e = cudaMemsetAsync(P.pixel_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
 #define RDR_F(K) do { if ((e = set_smem(K, smem)) != cudaSuccess) return e; K<<<grid, block, smem, stream>>>(P); } while (0)
-    RDR_RENDER_DISPATCH(mode, RDR_F);
+    RDR_RENDER_DISPATCH(mode, shape, RDR_F);
 #undef RDR_F
     return cudaGetLastError();
 }
@@ -355,15 +423,16 @@ cudaError_t launch_render(const FrameParams &P, int variant, int resident_ctas, 
 cudaError_t render_resident_ctas(const FrameParams &P, int variant, int *out)
 {
     const int mode = mode_of(P, variant);
-    const uint32_t block = render_block(mode);
-    const size_t smem = mode_smem_bytes(P.lay, P.staged != 0u, block, mode);
+    const RenderShape shape = render_shape(P, mode);
+    const uint32_t block = shape.block;
+    const size_t smem = mode_smem_bytes(P.lay, P.staged != 0u, block, mode, shape.cold);
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
 #define RDR_F(K) do { if ((e = set_smem(K, smem)) != cudaSuccess) return e; \
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, K, (int)block, smem); } while (0)
-    RDR_RENDER_DISPATCH(mode, RDR_F);
+    RDR_RENDER_DISPATCH(mode, shape, RDR_F);
 #undef RDR_F
     if (e != cudaSuccess) return e;
     *out = sms * (per_sm > 0 ? per_sm : 1);
@@ -406,7 +475,7 @@ cudaError_t launch_kat_trace(const FrameParams &P, int variant, uint32_t n, cons
 cudaError_t launch_trace_path(const FrameParams &P, int variant, uint32_t x, uint32_t y, uint32_t sample,
                               RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float *rgba, cudaStream_t stream)
 {
-    const size_t smem = mode_smem_bytes(P.lay, P.staged != 0u, 32, mode_of(P, variant));
+    const size_t smem = mode_smem_bytes(P.lay, P.staged != 0u, 32, mode_of(P, variant), false, true);
     cudaError_t e;
 #define RDR_K(M, ...) do { if ((e = set_smem(trace_path_kernel<M>, smem)) != cudaSuccess) return e; trace_path_kernel<M><<<1, 32, smem, stream>>>(P, x, y, sample, steps, capacity, n_steps, rgba); } while (0)
     RDR_DISPATCH(mode_of(P, variant), RDR_K, 0);

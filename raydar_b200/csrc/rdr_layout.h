@@ -39,6 +39,10 @@
 //   The top-level boxes of the fused scan travel in the kernel parameters (FrameParams::top, constant bank); the
 //   leading single-primitive entries (<= 4, spheres first) skip the member stage.
 //
+// Order in the blob: obj_geom, material and the fused scan's three sections come FIRST (SceneLayout::fused_stage_bytes):
+// the fused render kernel stages only that prefix (benchmark.rscn: 20.5 KB of 37.4 KB), which leaves the shared memory
+// for more resident warps; the flat-scan lists and the cluster scan's sections follow.
+//
 // ns_pad / nc_pad are the list lengths rounded up to 32 (one candidate-mask word per chunk).
 // Every lane of a warp reads the same primitive at the same time, so all shared-memory reads in
 // the scan are single-wavefront broadcasts.
@@ -73,6 +77,7 @@ struct SceneLayout {
     uint32_t fused_stride;               // quads per cluster in pair_block (3 * C/2 rounded up to odd)
     uint32_t fused_direct, fused_ns_direct;   // leading single-primitive entries (<= 4) and the spheres among them
     uint32_t off_pair_block, off_fused_geom, off_fused_idx;
+    uint32_t fused_stage_bytes;          // the blob's prefix [obj_geom, material, pair_block, fused_geom, fused_idx]: all the fused kernels stage
     uint32_t blob_bytes;                 // multiple of 16
 };
 

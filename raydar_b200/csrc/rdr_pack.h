@@ -126,16 +126,6 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
     if (!bvh_done) {
         L.mode = 0u;
         L.ns_pad = round_up_u32(L.n_spheres, 32u); L.nc_pad = round_up_u32(L.n_cubes, 32u);
-        uint32_t off = 0;
-        L.off_sphere_cull = off; off += 16u * L.ns_pad;
-        L.off_cube_cull = off;   off += 16u * L.nc_pad;
-        L.off_sphere_geom = off; off += 16u * L.ns_pad;
-        L.off_cube_geom = off;   off += 16u * L.nc_pad;
-        L.off_obj_geom = off;    off += 16u * n;
-        L.off_material = off;    off += 48u * n;
-        L.off_sphere_idx = off;  off += 4u * L.ns_pad;
-        L.off_cube_idx = off;    off += 4u * L.nc_pad;
-        off = round_up_u32(off, 16u);
         // two-level cluster scan (rdr_layout.h)
         std::vector<BvhBuildPrim> cprims(n);
         for (uint32_t i = 0; i < n; ++i) {
@@ -161,11 +151,6 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
         L.n_top = (uint32_t)cs.clusters.size(); L.nt_pad = round_up_u32(L.n_top, 32u);
         if (L.nt_pad > 128u) { err = "too many objects for the shared-memory scan (limit 128 clusters): use RDR_ACCEL_BVH or AUTO"; return RDR_ERR_UNSUPPORTED; }
         L.n_members = 9u * L.n_top;           // 8 members + 1 pad quad per cluster: 144-byte stride spreads the banks
-        L.off_top = off;         off += 32u * L.nt_pad;
-        L.off_member_box = off;  off += 16u * L.n_members;
-        L.off_member_geom = off; off += 16u * L.n_members;
-        L.off_member_idx = off;  off += 4u * L.n_members;
-        off = round_up_u32(off, 16u);
         // the fused scan's own clustering: the smallest cluster size (8, 16, 24, 32) that leaves <= 32 top entries
         ClusterSet fs;
         for (uint32_t cap = 8u; cap <= 32u; cap += 8u) {
@@ -189,10 +174,31 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
             }
             L.fused_stride = 3u * (L.fused_cap / 2u);
             if ((L.fused_stride & 1u) == 0u) ++L.fused_stride;
+        }
+        // Section order: what the shading code and the fused scan read comes first, so that the fused kernels stage
+        // only that prefix (fused_stage_bytes) into shared memory; the flat-scan lists and the cluster scan's sections
+        // follow (staged by the other kernels, which copy the whole blob).
+        uint32_t off = 0;
+        L.off_obj_geom = off;    off += 16u * n;
+        L.off_material = off;    off += 48u * n;
+        if (L.fused_ok) {
             L.off_pair_block = off; off += 16u * L.fused_stride * L.fused_top;
             L.off_fused_geom = off; off += 16u * L.fused_cap * L.fused_top;
             L.off_fused_idx = off;  off += 4u * L.fused_cap * L.fused_top;
         }
+        off = round_up_u32(off, 16u);
+        L.fused_stage_bytes = std::max(16u, off);
+        L.off_sphere_cull = off; off += 16u * L.ns_pad;
+        L.off_cube_cull = off;   off += 16u * L.nc_pad;
+        L.off_sphere_geom = off; off += 16u * L.ns_pad;
+        L.off_cube_geom = off;   off += 16u * L.nc_pad;
+        L.off_sphere_idx = off;  off += 4u * L.ns_pad;
+        L.off_cube_idx = off;    off += 4u * L.nc_pad;
+        off = round_up_u32(off, 16u);
+        L.off_top = off;         off += 32u * L.nt_pad;
+        L.off_member_box = off;  off += 16u * L.n_members;
+        L.off_member_geom = off; off += 16u * L.n_members;
+        L.off_member_idx = off;  off += 4u * L.n_members;
         L.blob_bytes = std::max(16u, round_up_u32(off, 16u));
 
         blob.assign(L.blob_bytes, 0);

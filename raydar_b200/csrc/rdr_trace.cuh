@@ -417,30 +417,59 @@ RDR_HD uint32_t lane_varying_zero(uint32_t *scratch)
 //
 // Per-pixel accumulation order is sample-ascending, as in the reference, so a launch over samples
 // [s0, s0+n) on top of an accumulator that already holds [0, s0) is bit-identical to one launch.
-struct LaneState {
-    f4 acc;                 // running accumulator of the pixel (registers)
-    v3 cam_d;               // primary ray direction
-    Hit h0;                 // cached primary hit
+// The per-lane state that is touched only when a sample ends or starts -- the pixel's accumulator (4 words), the
+// primary ray direction (3) and the cached primary hit (2) -- sits behind a storage policy: registers (ColdRegs: the
+// host simulation and the per-lane kernels) or the lane's column of a shared-memory array (ColdShared, rdr_kernels.cu:
+// 9 registers fewer in the hot loop of the fused kernel, paid with 9 LDS / 4 STS per finished sample).
+enum { COLD_ACC = 0, COLD_CAM_D = 4, COLD_H0_IDX = 7, COLD_H0_T = 8, COLD_WORDS = 9,
+       COLD_PARK = 9, COLD_PARK_WORDS = 9 };     // + the path state parked across a trace (ColdShared only)
+struct ColdRegs {
+    float w[COLD_WORDS];
+    RDR_HD float get(int i) const { return w[i]; }
+    RDR_HD void set(int i, float v) { w[i] = v; }
+};
+
+template <class COLD>
+struct LaneStateT {
+    COLD cold;              // accumulator, primary ray direction, cached primary hit
     Hit hit;                // hit to shade next
     v3 ro, rd, light, atten;
     uint32_t pixel, s, bounce, lane_zero;
     bool alive;             // the lane holds a ray to trace
     bool primary_pending;   // that ray is the pixel's primary ray
+
+    RDR_HD f4 acc() const { f4 a; a.x = cold.get(COLD_ACC); a.y = cold.get(COLD_ACC + 1); a.z = cold.get(COLD_ACC + 2); a.w = cold.get(COLD_ACC + 3); return a; }
+    RDR_HD void set_acc(f4 a) { cold.set(COLD_ACC, a.x); cold.set(COLD_ACC + 1, a.y); cold.set(COLD_ACC + 2, a.z); cold.set(COLD_ACC + 3, a.w); }
+    RDR_HD v3 cam_d() const { return mk3(cold.get(COLD_CAM_D), cold.get(COLD_CAM_D + 1), cold.get(COLD_CAM_D + 2)); }
+    RDR_HD void set_cam_d(v3 d) { cold.set(COLD_CAM_D, d.x); cold.set(COLD_CAM_D + 1, d.y); cold.set(COLD_CAM_D + 2, d.z); }
+    RDR_HD Hit h0() const { Hit h; h.idx = (int)f2u(cold.get(COLD_H0_IDX)); h.t = cold.get(COLD_H0_T); return h; }
+    RDR_HD void set_h0(Hit h) { cold.set(COLD_H0_IDX, u2f((uint32_t)h.idx)); cold.set(COLD_H0_T, h.t); }
+    // the sample's light joins the accumulator (render_next_sample, cpu.rs:203-212: sum += sample, alpha += 1)
+    RDR_HD void accumulate(v3 l)
+    {
+        f4 a = acc();
+        a.x = fadd(a.x, l.x); a.y = fadd(a.y, l.y); a.z = fadd(a.z, l.z); a.w = fadd(a.w, 1.0f);
+        set_acc(a);
+    }
 };
+typedef LaneStateT<ColdRegs> LaneState;
 
 // ptxas 12.9 (sm_100a) promotes a counter that starts from a constant and is stepped by a constant to a
 // UNIFORM register even when lanes step it at different times (observed: the sample counter in UR4 with
 // UIADD3/UISETP/BRA.U, all lanes of a warp sharing it -> too few samples per pixel).  Starting the per-lane
 // counters from a value the compiler must treat as lane-varying (a volatile read-back of the lane's scratch
 // word) keeps them in vector registers.  tests/test_gpu_parity.py::test_accumulator_bit_exact guards this.
-RDR_HD void lane_init(LaneState &st, uint32_t *masks)
+template <class ST>
+RDR_HD void lane_init(ST &st, uint32_t *masks)
 {
     st.lane_zero = lane_varying_zero(masks);
     st.alive = false; st.primary_pending = false;
     st.pixel = 0u; st.s = st.lane_zero; st.bounce = st.lane_zero;
-    st.acc.x = st.acc.y = st.acc.z = st.acc.w = 0.0f;
-    st.cam_d = st.ro = st.rd = st.light = st.atten = mk3(0.0f, 0.0f, 0.0f);
-    st.h0.idx = -1; st.h0.t = 0.0f; st.hit = st.h0;
+    f4 z; z.x = z.y = z.z = z.w = 0.0f;
+    st.set_acc(z);
+    st.ro = st.rd = st.light = st.atten = mk3(0.0f, 0.0f, 0.0f);
+    st.set_cam_d(st.ro);
+    st.hit.idx = -1; st.hit.t = 0.0f; st.set_h0(st.hit);
 }
 
 // The camera ray is set up once per pixel per launch (once per ~2000 trace iterations at 1024 spp) but is 240
@@ -449,45 +478,58 @@ RDR_HD void lane_init(LaneState &st, uint32_t *masks)
 RDR_HD_NOINLINE v3 camera_ray_dir_cold(const Camera &cam, uint32_t x, uint32_t y) { return camera_ray_dir(cam, x, y); }
 
 // take ownership of `pixel` (acc = its current accumulator).  Afterwards either st.alive (the primary ray is
-// waiting to be traced) or the pixel is already finished (no samples / no bounces) and st.acc is final.
-RDR_HD void lane_start_pixel(const FrameParams &P, uint32_t pixel, f4 acc, LaneState &st)
+// waiting to be traced) or the pixel is already finished (no samples / no bounces) and st.acc() is final.
+template <class ST>
+RDR_HD void lane_start_pixel(const FrameParams &P, uint32_t pixel, f4 acc, ST &st)
 {
-    st.pixel = pixel; st.acc = acc;
+    st.pixel = pixel;
     st.s = st.lane_zero; st.bounce = st.lane_zero;
     st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
     st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
     if (P.max_bounces == 0u) {                // `for _ in 0..0`: light stays zero, alpha still accumulates
         for (uint32_t s = 0; s < P.sample_count; ++s) {
-            st.acc.x = fadd(st.acc.x, 0.0f); st.acc.y = fadd(st.acc.y, 0.0f); st.acc.z = fadd(st.acc.z, 0.0f); st.acc.w = fadd(st.acc.w, 1.0f);
+            acc.x = fadd(acc.x, 0.0f); acc.y = fadd(acc.y, 0.0f); acc.z = fadd(acc.z, 0.0f); acc.w = fadd(acc.w, 1.0f);
         }
+        st.set_acc(acc);
         st.alive = false;
         return;
     }
+    st.set_acc(acc);
     st.alive = P.sample_count > 0u;
     st.primary_pending = st.alive;
-    if (st.alive) st.cam_d = st.rd = camera_ray_dir_cold(P.cam, pixel % P.cam.width, pixel / P.cam.width);
+    if (st.alive) { st.rd = camera_ray_dir_cold(P.cam, pixel % P.cam.width, pixel / P.cam.width); st.set_cam_d(st.rd); }
 }
 
 // the traced hit of the lane's current ray arrives
-RDR_HD void lane_accept_hit(LaneState &st, Hit h)
+template <class ST>
+RDR_HD void lane_accept_hit(ST &st, Hit h)
 {
-    if (st.primary_pending) { st.h0 = h; st.primary_pending = false; }
+    if (st.primary_pending) { st.set_h0(h); st.primary_pending = false; }
     st.hit = h;
+}
+
+// the finished sample's light is in the accumulator: start the pixel's next sample from the cached primary hit
+// (false: the pixel has no samples left)
+template <class ST>
+RDR_HD bool lane_next_sample(const FrameParams &P, ST &st)
+{
+    if (++st.s >= P.sample_count) { st.alive = false; return false; }
+    st.bounce = st.lane_zero; st.hit = st.h0();
+    st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]); st.rd = st.cam_d();
+    st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
+    return true;
 }
 
 // The traced ray missed (cpu.rs:334-338): light += sky * attenuation, the sample is complete, and the lane
 // restarts from the cached primary hit.  When the primary ray itself misses, every sample of the pixel is the
 // sky and the pixel is finished here.  Afterwards either !st.alive (pixel done) or st.hit.idx >= 0 (to shade).
-RDR_HD void lane_miss(const FrameParams &P, LaneState &st)
+template <class ST>
+RDR_HD void lane_miss(const FrameParams &P, ST &st)
 {
     for (;;) {
         st.light = add3(st.light, mul3(world_sample(P.world, st.rd), st.atten));
-        st.acc.x = fadd(st.acc.x, st.light.x); st.acc.y = fadd(st.acc.y, st.light.y);
-        st.acc.z = fadd(st.acc.z, st.light.z); st.acc.w = fadd(st.acc.w, 1.0f);
-        if (++st.s >= P.sample_count) { st.alive = false; return; }
-        st.bounce = st.lane_zero; st.hit = st.h0;
-        st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]); st.rd = st.cam_d;
-        st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
+        st.accumulate(st.light);
+        if (!lane_next_sample(P, st)) return;
         if (st.hit.idx >= 0) return;
     }
 }
@@ -496,7 +538,8 @@ RDR_HD void lane_miss(const FrameParams &P, LaneState &st)
 // lane now holds a ray that needs tracing; false when the bounce budget is used up (cpu.rs:256,341: the sample keeps
 // its emission, no sky term) -- then the sample is finished and either the pixel is done (!st.alive) or the lane
 // has restarted from the primary hit, which needs shading again (rare: call once more).
-RDR_HD bool lane_shade_hit(const FrameParams &P, const SceneView &S, LaneState &st)
+template <class ST>
+RDR_HD bool lane_shade_hit(const FrameParams &P, const SceneView &S, ST &st)
 {
     bool is_sphere;
     const Material m = load_material(S, st.hit.idx, &is_sphere);
@@ -508,12 +551,8 @@ RDR_HD bool lane_shade_hit(const FrameParams &P, const SceneView &S, LaneState &
     st.light = add3(st.light, scale3(m.emission, m.emission_strength));
     ++st.bounce;
     if (st.bounce < P.max_bounces) return true;
-    st.acc.x = fadd(st.acc.x, st.light.x); st.acc.y = fadd(st.acc.y, st.light.y);
-    st.acc.z = fadd(st.acc.z, st.light.z); st.acc.w = fadd(st.acc.w, 1.0f);
-    if (++st.s >= P.sample_count) { st.alive = false; return false; }
-    st.bounce = st.lane_zero; st.hit = st.h0;
-    st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]); st.rd = st.cam_d;
-    st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
+    st.accumulate(st.light);
+    lane_next_sample(P, st);
     return false;
 }
 
@@ -530,7 +569,7 @@ RDR_HD f4 render_pixel(const FrameParams &P, const SceneView &S, uint32_t *masks
         if (st.hit.idx < 0) lane_miss(P, st);
         while (st.alive && !lane_shade_hit(P, S, st)) {}
     }
-    return st.acc;
+    return st.acc();
 }
 
 // one path with every bounce recorded (debug / parity); returns the number of steps taken
