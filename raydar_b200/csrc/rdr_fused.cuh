@@ -119,9 +119,20 @@ __device__ __forceinline__ void fused_exact(const FusedView &V, FusedWarp ws, ui
 
 // two boxes (A, B) against one ray: bit 0 / bit 1 of the result = box A / B may be hit.
 //   c*: centres, e*: half-extents (already inflated), r*: the ray's 1/d, n*: -(o/d)
+// slab_pair_acc ORs the two bits into `m` at compile-time position SHIFT.  RDR_PRED_OR: one compare and one predicated
+// OR per box (FSETP + @!P LOP3) instead of the select / add / shift / or chain the compiler builds from the C form.
+#ifndef RDR_PRED_OR
+#define RDR_PRED_OR 1
+#endif
+__device__ __forceinline__ void or_unless_gt(uint32_t &m, float tn, float tf, uint32_t bit)
+{
+    // tn > tf is false for a NaN operand: the bit is set, as in `(tn > tf ? 0 : bit)`
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@!p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(tn), "f"(tf), "r"(bit));
+}
 template <bool BOUNDED = false>
-__device__ __forceinline__ uint32_t slab_pair(f32x2 cx, f32x2 cy, f32x2 cz, f32x2 ex, f32x2 ey, f32x2 ez,
-                                              float rx, float ry, float rz, float nx, float ny, float nz, float best = 0.0f)
+__device__ __forceinline__ void slab_pair_tn_tf(f32x2 cx, f32x2 cy, f32x2 cz, f32x2 ex, f32x2 ey, f32x2 ez,
+                                                float rx, float ry, float rz, float nx, float ny, float nz, float best,
+                                                float &tna, float &tfa, float &tnb, float &tfb)
 {
     const f32x2 tcx = fma2(cx, bc2(rx), bc2(nx)), tcy = fma2(cy, bc2(ry), bc2(ny)), tcz = fma2(cz, bc2(rz), bc2(nz));
     float nxa, nxb, nya, nyb, nza, nzb, fxa, fxb, fya, fyb, fza, fzb;
@@ -129,9 +140,29 @@ __device__ __forceinline__ uint32_t slab_pair(f32x2 cx, f32x2 cy, f32x2 cz, f32x
     un2(fma2(ex, bc2(fabsf(rx)), tcx), fxa, fxb); un2(fma2(ey, bc2(fabsf(ry)), tcy), fya, fyb); un2(fma2(ez, bc2(fabsf(rz)), tcz), fza, fzb);
     // BOUNDED: a box whose entry distance exceeds the ray's best exact t so far cannot hold the winner (ties kept);
     // min.f32 ignores a NaN operand, so "no hit yet" is passed as NaN
-    const float tna = fmaxf(fmaxf(nxa, nya), fmaxf(nza, 0.0f)), tfa = BOUNDED ? fminf(fminf(fxa, fya), fminf(fza, best)) : fminf(fminf(fxa, fya), fza);
-    const float tnb = fmaxf(fmaxf(nxb, nyb), fmaxf(nzb, 0.0f)), tfb = BOUNDED ? fminf(fminf(fxb, fyb), fminf(fzb, best)) : fminf(fminf(fxb, fyb), fzb);
+    tna = fmaxf(fmaxf(nxa, nya), fmaxf(nza, 0.0f)); tfa = BOUNDED ? fminf(fminf(fxa, fya), fminf(fza, best)) : fminf(fminf(fxa, fya), fza);
+    tnb = fmaxf(fmaxf(nxb, nyb), fmaxf(nzb, 0.0f)); tfb = BOUNDED ? fminf(fminf(fxb, fyb), fminf(fzb, best)) : fminf(fminf(fxb, fyb), fzb);
+}
+template <bool BOUNDED = false>
+__device__ __forceinline__ uint32_t slab_pair(f32x2 cx, f32x2 cy, f32x2 cz, f32x2 ex, f32x2 ey, f32x2 ez,
+                                              float rx, float ry, float rz, float nx, float ny, float nz, float best = 0.0f)
+{
+    float tna, tfa, tnb, tfb;
+    slab_pair_tn_tf<BOUNDED>(cx, cy, cz, ex, ey, ez, rx, ry, rz, nx, ny, nz, best, tna, tfa, tnb, tfb);
     return (tna > tfa ? 0u : 1u) | (tnb > tfb ? 0u : 2u);
+}
+template <uint32_t SHIFT>
+__device__ __forceinline__ void slab_pair_acc(uint32_t &m, f32x2 cx, f32x2 cy, f32x2 cz, f32x2 ex, f32x2 ey, f32x2 ez,
+                                              float rx, float ry, float rz, float nx, float ny, float nz)
+{
+    if (RDR_PRED_OR) {
+        float tna, tfa, tnb, tfb;
+        slab_pair_tn_tf<false>(cx, cy, cz, ex, ey, ez, rx, ry, rz, nx, ny, nz, 0.0f, tna, tfa, tnb, tfb);
+        or_unless_gt(m, tna, tfa, 1u << SHIFT);
+        or_unless_gt(m, tnb, tfb, 2u << SHIFT);
+    } else {
+        m |= slab_pair(cx, cy, cz, ex, ey, ez, rx, ry, rz, nx, ny, nz) << SHIFT;
+    }
 }
 
 // slab constants of one ray for the pair tests (make_ray_bvh, rdr_core.cuh): r = 1/d (clamped to +-1e30 for zero /
@@ -162,39 +193,33 @@ __device__ __forceinline__ SlabRay slab_ray_setup(const CullConsts &cc, v3 o, v3
 }
 
 // the ray against the first n_top (<= 32) top-level boxes of the kernel parameters: bit k = box k may be hit.
-// The operands are constant-bank addresses (LDCU.128 into uniform registers).  RDR_TOP_GROUP pairs are tested per
-// iteration of a warp-uniform loop (the constant bank is indexed with a uniform register): the fully unrolled form
-// (RDR_TOP_GROUP = 16) is 8 KB of code for 32 boxes, a quarter of the instruction cache the sample loop lives in.
-#ifndef RDR_TOP_GROUP
-#define RDR_TOP_GROUP 16u
-#endif
-__device__ __forceinline__ uint32_t top_pair_test(const TopPair &t, f32x2 rho2, const SlabRay &R)
+// The operands are constant-bank addresses (LDCU.128 into uniform registers).
+template <uint32_t SHIFT>
+__device__ __forceinline__ void top_pair_test(uint32_t &m, const TopPair &t, f32x2 rho2, const SlabRay &R)
 {
     const f32x2 sp = pk2(t.sphere[0], t.sphere[1]);
     const f32x2 ex = fma2(sp, rho2, pk2(t.ex[0], t.ex[1])), ey = fma2(sp, rho2, pk2(t.ey[0], t.ey[1])), ez = fma2(sp, rho2, pk2(t.ez[0], t.ez[1]));
-    return slab_pair(pk2(t.cx[0], t.cx[1]), pk2(t.cy[0], t.cy[1]), pk2(t.cz[0], t.cz[1]), ex, ey, ez, R.rx, R.ry, R.rz, R.nx, R.ny, R.nz);
+    slab_pair_acc<SHIFT>(m, pk2(t.cx[0], t.cx[1]), pk2(t.cy[0], t.cy[1]), pk2(t.cz[0], t.cz[1]), ex, ey, ez, R.rx, R.ry, R.rz, R.nx, R.ny, R.nz);
+}
+template <uint32_t K>
+__device__ __forceinline__ void top_pairs4(uint32_t &m, const TopParams &T, f32x2 rho2, const SlabRay &R)
+{
+    uint32_t g = 0u;        // own accumulator per group: keeps the predicated-OR dependency chains short
+    top_pair_test<2u * K>(g, T.pair[K], rho2, R); top_pair_test<2u * K + 2u>(g, T.pair[K + 1u], rho2, R);
+    top_pair_test<2u * K + 4u>(g, T.pair[K + 2u], rho2, R); top_pair_test<2u * K + 6u>(g, T.pair[K + 3u], rho2, R);
+    m |= g;
 }
 
+// Fully unrolled, four pairs per step: every operand is a compile-time constant-bank address.  (A warp-uniform loop over
+// groups of pairs indexes the constant bank with a vector register -- LDC per operand -- and measured 1-2 % slower.)
 __device__ __forceinline__ uint32_t top_scan(const TopParams &T, uint32_t n_top, const SlabRay &R)
 {
     uint32_t m = 0u;
     const f32x2 rho2 = bc2(R.rho);
-    if (RDR_TOP_GROUP >= FUSED_MAX_TOP / 2u) {
-#pragma unroll
-        for (uint32_t k = 0; k < FUSED_MAX_TOP / 2u; ++k) {
-            if ((k & 3u) == 0u && 2u * k >= n_top) break;
-            m |= top_pair_test(T.pair[k], rho2, R) << (2u * k);
-        }
-    } else {
-        const uint32_t n_groups = (n_top + 2u * RDR_TOP_GROUP - 1u) / (2u * RDR_TOP_GROUP);
-#pragma unroll 1
-        for (uint32_t g = 0; g < n_groups; ++g) {
-            uint32_t bits = 0u;
-#pragma unroll
-            for (uint32_t j = 0; j < RDR_TOP_GROUP; ++j) bits |= top_pair_test(T.pair[g * RDR_TOP_GROUP + j], rho2, R) << (2u * j);
-            m |= bits << (2u * RDR_TOP_GROUP * g);
-        }
-    }
+    top_pairs4<0u>(m, T, rho2, R);
+    if (n_top > 8u) top_pairs4<4u>(m, T, rho2, R);
+    if (n_top > 16u) top_pairs4<8u>(m, T, rho2, R);
+    if (n_top > 24u) top_pairs4<12u>(m, T, rho2, R);
     if (n_top < 32u) m &= (1u << n_top) - 1u;
     return m;
 }
@@ -263,7 +288,10 @@ __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams
                 if (CAP8 && p == 0u) { const f4 q = pb[2]; q2.x = q.x; q2.y = q.y; desc = __float_as_uint(q.z); }   // flags + desc in one LDS.128
                 else q2 = *reinterpret_cast<const float2 *>(pb + 3u * p + 2u);
                 const f32x2 e = fma2(pk2(q2.x, q2.y), rho2, pk2(q1.z, q1.w));
-                bits |= slab_pair(pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), e, e, e, qx, qy, qz, mx, my, mz) << (2u * p);
+                if (p == 0u) slab_pair_acc<0u>(bits, pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), e, e, e, qx, qy, qz, mx, my, mz);
+                else if (p == 1u) slab_pair_acc<2u>(bits, pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), e, e, e, qx, qy, qz, mx, my, mz);
+                else if (p == 2u) slab_pair_acc<4u>(bits, pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), e, e, e, qx, qy, qz, mx, my, mz);
+                else slab_pair_acc<6u>(bits, pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), e, e, e, qx, qy, qz, mx, my, mz);
             }
             const uint32_t count = desc & 63u, n_sph = (desc >> 6) & 63u;
             const uint32_t left = count > m0 ? count - m0 : 0u;   // members of this cluster in this step
