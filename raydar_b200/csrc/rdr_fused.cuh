@@ -124,6 +124,18 @@ __device__ __forceinline__ void fused_exact(const FusedView &V, FusedWarp ws, ui
 #ifndef RDR_PRED_OR
 #define RDR_PRED_OR 1
 #endif
+// Prepared, NOT yet measured or parity-tested on the GPU (off by default; the default build's SASS is unchanged):
+//   RDR_DIRECT_BALLOT  survivors of the single-primitive top entries (benchmark.rscn: the floor) are appended with one
+//                      ballot per entry instead of the prefix scan + write loop of fused_append (~100 of ~2300 warp
+//                      instructions per trace iteration)
+//   RDR_APPROX_RHO     the per-ray sphere margin rho from sqrt.approx (2 ulp, covered by its 1.0001 safety factor)
+//                      instead of two correctly rounded square roots
+#ifndef RDR_DIRECT_BALLOT
+#define RDR_DIRECT_BALLOT 0
+#endif
+#ifndef RDR_APPROX_RHO
+#define RDR_APPROX_RHO 0
+#endif
 __device__ __forceinline__ void or_unless_gt(uint32_t &m, float tn, float tf, uint32_t bit)
 {
     // tn > tf is false for a NaN operand: the bit is set, as in `(tn > tf ? 0 : bit)`
@@ -185,8 +197,19 @@ __device__ __forceinline__ SlabRay slab_ray_setup(const CullConsts &cc, v3 o, v3
     const float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
     const bool degenerate = !(omax <= cc.origin_bound) || !(a > 1e-30f) || !(a < 1e30f) || !(s_ray < 1e30f) ||
                             isnan_(d.x) || isnan_(d.y) || isnan_(d.z);
+#if RDR_APPROX_RHO
+    {
+        float q1, q2;
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(q1) : "f"(fma(cc.sphere_r_min, cc.sphere_r_min, Ms)));
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(q2) : "f"(s_ray));
+        // q1 may be 2 ulp low: (q1 - r_min) loses at most 2 ulp(q1) <= 2^-22 (r_min + rho), made up by widening with r_min too
+        R.rho = fadd(fsub(q1, cc.sphere_r_min), fmul(1.9073486328125e-06f, q2));
+        R.rho = fma(R.rho, 1.0001f, fmul(4.76837158203125e-07f, cc.sphere_r_min));
+    }
+#else
     R.rho = fadd(fsub(fsqrt(fma(cc.sphere_r_min, cc.sphere_r_min, Ms)), cc.sphere_r_min), fmul(1.9073486328125e-06f, fsqrt(s_ray)));
     R.rho = fmul(R.rho, 1.0001f);
+#endif
     R.nx = fneg(fmul(o.x, R.rx)); R.ny = fneg(fmul(o.y, R.ry)); R.nz = fneg(fmul(o.z, R.rz));
     if (degenerate) { R.rx = R.ry = R.rz = 0.0f; R.nx = R.ny = R.nz = 0.0f; R.rho = 0.0f; }
     return R;
@@ -244,7 +267,26 @@ __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams
     // single-primitive top entries: their box was the entry -> straight to the survivor lists (member slot = C * entry)
     if (P.lay.fused_direct != 0u) {
         const uint32_t dmask = (1u << P.lay.fused_direct) - 1u;
+#if RDR_DIRECT_BALLOT
+        // one ballot per direct entry (<= 4, warp-uniform loop): the survivor's position is the popcount of the ballot
+        // below the lane -- no prefix scan, no per-lane write loop
+        const uint32_t below = (1u << lane) - 1u, cap = CAP8 ? 8u : P.lay.fused_cap;
+#pragma unroll 1
+        for (uint32_t j = 0; j < P.lay.fused_direct; ++j) {
+            const bool hit = ((m >> j) & 1u) != 0u;
+            const uint32_t b = __ballot_sync(FULL, hit);
+            if (j < P.lay.fused_ns_direct) {
+                if (hit) ws.surv_s[n_s + __popc(b & below)] = (uint16_t)((lane << 11) | (cap * j));
+                n_s += __popc(b);
+            } else {
+                if (hit) ws.surv_c[n_c + __popc(b & below)] = (uint16_t)((lane << 11) | (cap * j));
+                n_c += __popc(b);
+            }
+        }
+        __syncwarp();
+#else
         fused_append(ws, lane, lane, 0u, CAP8 ? 8u : P.lay.fused_cap, m & dmask, P.lay.fused_ns_direct, n_s, n_c);
+#endif
         m &= ~dmask;
     }
 

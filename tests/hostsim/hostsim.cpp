@@ -519,4 +519,15 @@ int hs_cluster_info(const RdrSceneFlat *sc, uint32_t *n_top, uint32_t *blob_byte
     return RDR_OK;
 }
 
+// the fused scan's layout figures: [fused_ok, fused_top, fused_cap, fused_direct, fused_ns_direct, fused_stage_bytes, blob_bytes]
+int hs_fused_info(const RdrSceneFlat *sc, uint32_t out[7])
+{
+    Packed pk(sc, false);
+    if (pk.status != RDR_OK) return pk.status;
+    const SceneLayout &L = pk.P.lay;
+    out[0] = L.fused_ok; out[1] = L.fused_top; out[2] = L.fused_cap; out[3] = L.fused_direct; out[4] = L.fused_ns_direct;
+    out[5] = L.fused_stage_bytes; out[6] = L.blob_bytes;
+    return RDR_OK;
+}
+
 }  // extern "C"
