@@ -48,6 +48,17 @@ impl CudaRenderer {
         assert!(st == 0, "rdr_create failed: {}", last_error(std::ptr::null()));
         Self { handle, profiler: Profiler::default(), resolution: (0, 0) }
     }
+    /// `--gpus N`: one sub-renderer per device behind the same handle (rdr_create_multi).  `stripes`: round-robin
+    /// 16-row stripes instead of sample ranges -- the image is then bit-identical to the one-GPU image.
+    pub fn with_gpus(config: RendererConfig, gpus: u32, stripes: bool) -> Self {
+        let cfg = sys::RdrConfig { max_sample_count: config.max_sample_count, max_bounces: config.max_bounces };
+        let devices: Vec<std::os::raw::c_int> = (0..gpus as std::os::raw::c_int).collect();
+        let mut handle = std::ptr::null_mut();
+        let st = unsafe { sys::rdr_create_multi(&cfg, devices.len() as std::os::raw::c_int, devices.as_ptr(), &mut handle) };
+        assert!(st == 0, "rdr_create_multi failed: {}", last_error(std::ptr::null()));
+        if stripes { assert!(unsafe { sys::rdr_set_partition(handle, 1, 16) } == 0, "rdr_set_partition failed"); }
+        Self { handle, profiler: Profiler::default(), resolution: (0, 0) }
+    }
     fn check(&self, st: i32) { assert!(st == 0, "raydar_cuda: {}", last_error(self.handle)); }   // the trait is infallible
     fn sync_profiler(&mut self) {        // timers are pub(super): a sibling module may fill them (timing.rs:12-18)
         let mut p = sys::RdrProfiler::default();
