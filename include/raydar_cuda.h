@@ -52,9 +52,10 @@ enum { RDR_MAT_STRIDE = 11 };  /* albedo3, roughness, metallic, emission_color3,
  *   BVH      8-wide hierarchy (shared memory when it fits, otherwise global memory / L2)
  *   COOP     CLUSTER with the per-lane stages regrouped across the warp (ballot/shuffle work distribution)
  *   FUSED    COOP rebuilt for the sm_100a issue model: packed FFMA2 box tests, top-level boxes in the constant
- *            bank, atomics-free survivor compaction (<= 32 top-level entries, i.e. <= 256 objects; COOP above)
- *   BVH_COOP the hierarchy in pair-packed form (<= 32 root entries, 8-wide nodes), traversed by the whole warp from one
- *            shared task stack (FFMA2 pair tests, prefix-sum compaction, pruning by the best exact hit so far)
+ *            bank, atomics-free survivor compaction, lane state the search does not need in shared-memory columns
+ *            (<= 32 top-level entries of 8 / 16 / 24 / 32 members, i.e. up to ~1000 objects; COOP otherwise)
+ *   BVH_COOP the hierarchy in pair-packed form (<= 32 root entries, 8-wide nodes), traversed by the whole warp: one
+ *            near-first stack per ray, four lanes per node (FFMA2 pair tests), pruning by the best exact hit so far
  *   AUTO     FUSED / COOP up to 1024 objects, BVH_COOP above */
 enum { RDR_ACCEL_AUTO = 0, RDR_ACCEL_BRUTE = 1, RDR_ACCEL_BVH = 2, RDR_ACCEL_CLUSTER = 3, RDR_ACCEL_COOP = 4, RDR_ACCEL_FUSED = 5, RDR_ACCEL_BVH_COOP = 6 };
 
