@@ -124,6 +124,64 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) render_kernel(const __grid_co
     cold_bind(st.cold, reinterpret_cast<unsigned char *>(scratch0 + BLOCK) + (BLOCK / 32) * (MODE == 7 ? BVH2_WARP_BYTES : FUSED_WARP_BYTES));
     lane_init(st, scratch0 + threadIdx.x);
     bool exhausted = false;
+#if RDR_CHUNKED
+    // (pixel, sample-chunk) items in chunk-major order (rdr_layout.h).  A lane that claims chunk c > 0 of a pixel is
+    // PENDING until the pixel's progress word says that chunk c - 1 has been stored; it polls once per iteration and never
+    // blocks the warp, and the lane that owns chunk c - 1 claimed it earlier and is resident (persistent grid), so the
+    // wait always ends.  Store side: accumulator, __threadfence, progress word; load side: progress word (volatile),
+    // __threadfence, accumulator past L1 (ld.global.cg: the line may sit in this SM's L1 from a neighbouring pixel).
+    const uint32_t n_items = n_owned * P.n_chunks;
+    bool pending = false;
+    for (;;) {
+        if (pending && *reinterpret_cast<volatile uint32_t *>(P.progress + st.pixel) == P.progress_base + st.s) {
+            __threadfence();
+            const float4 a = __ldcg(reinterpret_cast<const float4 *>(P.accum + st.pixel));
+            f4 acc; acc.x = a.x; acc.y = a.y; acc.z = a.z; acc.w = a.w;
+            const uint32_t s_begin = st.s, s_end = min(s_begin + P.chunk_samples, P.sample_count);
+            lane_start_item(P, st.pixel, acc, s_begin, s_end, st);
+            pending = false;
+            if (!st.alive) {
+                P.accum[st.pixel] = st.acc(); __threadfence();
+                *reinterpret_cast<volatile uint32_t *>(P.progress + st.pixel) = P.progress_base + s_end;
+            }
+        }
+        while (!st.alive && !pending && !exhausted) {
+            const uint32_t k = atomicAdd(P.pixel_counter, 1u);
+            if (k >= n_items) { exhausted = true; break; }
+            const uint32_t c = k / n_owned;
+            const uint32_t pixel = stripe_pixel(P.cam.width, P.stripe_rows, P.stripe_index, P.stripe_count, k - c * n_owned);
+            if (c != 0u) { pending = true; st.pixel = pixel; st.s = st.lane_zero + c * P.chunk_samples; break; }
+            const uint32_t s_end = min(P.chunk_samples, P.sample_count);
+            lane_start_item(P, pixel, P.accum[pixel], 0u, s_end, st);
+            if (!st.alive) {                                // nothing to trace (no bounces)
+                P.accum[pixel] = st.acc(); __threadfence();
+                *reinterpret_cast<volatile uint32_t *>(P.progress + pixel) = P.progress_base + s_end;
+            }
+        }
+        if (!__any_sync(0xffffffffu, st.alive)) {
+            if (!__any_sync(0xffffffffu, pending)) break;
+            __nanosleep(200);                               // only pending lanes left in this warp: poll again
+            continue;
+        }
+        const bool tracing = st.alive;
+        lane_park(st);
+        const Hit h = trace_warp<MODE>(S, P, scratch0, tracing, st.ro, st.rd);
+        lane_unpark(st);
+        if (tracing) lane_accept_hit(st, h);
+        __syncwarp();
+        if (tracing && st.hit.idx < 0) lane_miss(P, st);
+        __syncwarp();
+        bool shade = st.alive;
+        while (__any_sync(0xffffffffu, shade)) {
+            if (shade) shade = !lane_shade_hit(P, S, st) && st.alive;
+        }
+        if (tracing && !st.alive) {                         // the lane's chunk is done
+            P.accum[st.pixel] = st.acc(); __threadfence();
+            *reinterpret_cast<volatile uint32_t *>(P.progress + st.pixel) = P.progress_base + f2u(st.cold.get(COLD_S_END));
+        }
+    }
+    return;
+#endif
     for (;;) {
         while (!st.alive && !exhausted) {
             const uint32_t k = atomicAdd(P.pixel_counter, 1u);
