@@ -76,15 +76,6 @@ __device__ __forceinline__ CoopWarpScratch coop_scratch(unsigned char *base, uin
     return w;
 }
 
-// order-preserving key of a hit: t is -0, >= +0 or NaN (cpu.rs:54-58,90-97); -0 == +0 for the comparison, NaN last
-__device__ __forceinline__ unsigned long long coop_key(float t, int idx)
-{
-    const uint32_t bits = __float_as_uint(t);
-    const uint32_t kt = isnan_(t) ? 0x7fc00000u : (bits & 0x7fffffffu);
-    const uint32_t zflag = (bits == 0x80000000u) ? 1u : 0u;
-    return ((unsigned long long)kt << 32) | ((unsigned long long)(uint32_t)idx << 1) | zflag;
-}
-
 // E: exact tests on the warp's survivor lists, dealt out evenly; a hit is folded into the owner's winner key
 __device__ __forceinline__ void coop_exact(const SceneView &S, const CullConsts &cc, CoopWarpScratch ws, v3 o, v3 d, bool all)
 {

@@ -20,16 +20,36 @@
 // Device-only; must be entered by all 32 lanes of a warp.  Needs lay.fused_ok (<= 32 top entries) and a staged blob.
 #pragma once
 
+// RDR_WARP_EMU (tests/hostsim only): this file is compiled by g++ against tests/hostsim/warp_emu.h, which runs the 32
+// lanes of a warp as fibers and supplies __shfl_sync / __ballot_sync / __syncwarp / atomicMin / threadIdx; the four
+// packed-FP32 helpers and the predicated OR below then have plain C++ bodies (one fmaf per half = the rounding of
+// fma.rn.f32x2).  The device build never defines it.
+#ifdef RDR_WARP_EMU
+#include "rdr_trace.cuh"
+#else
 #include "rdr_device.cuh"
+#endif
 
 namespace rdr {
 
 typedef unsigned long long f32x2;
 
+#ifdef RDR_WARP_EMU
+inline f32x2 pk2(float lo, float hi) { return (f32x2)f2u(lo) | ((f32x2)f2u(hi) << 32); }
+inline f32x2 bc2(float a) { return pk2(a, a); }
+inline void un2(f32x2 v, float &lo, float &hi) { lo = u2f((uint32_t)v); hi = u2f((uint32_t)(v >> 32)); }
+inline f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    float al, ah, bl, bh, cl, ch;
+    un2(a, al, ah); un2(b, bl, bh); un2(c, cl, ch);
+    return pk2(fma(al, bl, cl), fma(ah, bh, ch));
+}
+#else
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ f32x2 bc2(float a) { f32x2 r; asm("mov.b64 %0, {%1,%1};" : "=l"(r) : "f"(a)); return r; }
 __device__ __forceinline__ void un2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+#endif
 
 // per-warp scratch of the fused scan (shared memory)
 constexpr uint32_t FUSED_TASK_CAP = 32u * FUSED_MAX_TOP;      // every ray against every cluster
@@ -139,7 +159,11 @@ __device__ __forceinline__ void fused_exact(const FusedView &V, FusedWarp ws, ui
 __device__ __forceinline__ void or_unless_gt(uint32_t &m, float tn, float tf, uint32_t bit)
 {
     // tn > tf is false for a NaN operand: the bit is set, as in `(tn > tf ? 0 : bit)`
+#ifdef RDR_WARP_EMU
+    if (!(tn > tf)) m |= bit;
+#else
     asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@!p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(tn), "f"(tf), "r"(bit));
+#endif
 }
 template <bool BOUNDED = false>
 __device__ __forceinline__ void slab_pair_tn_tf(f32x2 cx, f32x2 cy, f32x2 cz, f32x2 ex, f32x2 ey, f32x2 ez,
@@ -200,8 +224,12 @@ __device__ __forceinline__ SlabRay slab_ray_setup(const CullConsts &cc, v3 o, v3
 #if RDR_APPROX_RHO
     {
         float q1, q2;
+#ifdef RDR_WARP_EMU
+        q1 = fsqrt(fma(cc.sphere_r_min, cc.sphere_r_min, Ms)); q2 = fsqrt(s_ray);
+#else
         asm("sqrt.approx.f32 %0, %1;" : "=f"(q1) : "f"(fma(cc.sphere_r_min, cc.sphere_r_min, Ms)));
         asm("sqrt.approx.f32 %0, %1;" : "=f"(q2) : "f"(s_ray));
+#endif
         // q1 may be 2 ulp low: (q1 - r_min) loses at most 2 ulp(q1) <= 2^-22 (r_min + rho), made up by widening with r_min too
         R.rho = fadd(fsub(q1, cc.sphere_r_min), fmul(1.9073486328125e-06f, q2));
         R.rho = fma(R.rho, 1.0001f, fmul(4.76837158203125e-07f, cc.sphere_r_min));

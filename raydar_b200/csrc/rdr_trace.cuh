@@ -390,6 +390,17 @@ RDR_HD Hit trace_any(const SceneView &S, const CullConsts &cc, uint32_t *scratch
     return trace_brute<true>(S, cc, scratch, stride, o, d, stats);
 }
 
+// order-preserving 64-bit key of a hit for the warp-cooperative searches, which fold a ray's candidates with atomicMin:
+// (t, original index) ascending = the first-minimum rule of trace_ray (cpu.rs:344-352).  t is -0, >= +0 or NaN
+// (cpu.rs:54-58,90-97); -0 == +0 for the comparison (bit 0 remembers the sign), NaN last.
+RDR_HD unsigned long long coop_key(float t, int idx)
+{
+    const uint32_t bits = f2u(t);
+    const uint32_t kt = isnan_(t) ? 0x7fc00000u : (bits & 0x7fffffffu);
+    const uint32_t zflag = (bits == 0x80000000u) ? 1u : 0u;
+    return ((unsigned long long)kt << 32) | ((unsigned long long)(uint32_t)idx << 1) | zflag;
+}
+
 // 0, but opaque to the compiler's uniformity analysis (see LaneState)
 RDR_HD uint32_t lane_varying_zero(uint32_t *scratch)
 {

@@ -15,6 +15,11 @@
 #include "rdr_pack.h"
 #include "rdr_trace.cuh"
 
+// the device-only fused scan, compiled for the CPU against the warp emulator (32 fibers = one warp)
+#define RDR_WARP_EMU 1
+#include "warp_emu.h"
+#include "rdr_fused.cuh"
+
 using namespace rdr;
 
 namespace {
@@ -517,6 +522,52 @@ int hs_cluster_info(const RdrSceneFlat *sc, uint32_t *n_top, uint32_t *blob_byte
     if (pk.status != RDR_OK) return pk.status;
     *n_top = pk.P.lay.n_top; *blob_bytes = pk.P.lay.blob_bytes;
     return RDR_OK;
+}
+
+// The PRODUCT's warp-cooperative fused scan (trace_fused, rdr_fused.cuh: the search behind RDR_ACCEL_AUTO up to ~1000
+// objects) on the CPU: rays are taken 32 at a time as the lanes of one emulated warp (warp_emu.h); lanes past n are dead
+// (alive = false), as idle lanes are in the kernel.  Returns RDR_ERR_UNSUPPORTED when the scene has no fused layout and
+// RDR_ERR_INVALID when the emulated warp deadlocks (a lane left a rendezvous the others still wait at).
+int hs_trace_fused(const RdrSceneFlat *sc, uint32_t n, const float *rays, int32_t *ids, float *ts)
+{
+    Packed pk(sc, false);
+    if (pk.status != RDR_OK) return pk.status;
+    if (!pk.P.lay.fused_ok) return RDR_ERR_UNSUPPORTED;
+    FusedView V;
+    V.pair_block = pk.S.pair_block; V.member_geom = pk.S.fused_geom; V.member_idx = pk.S.fused_idx;
+    const bool cap8 = pk.P.lay.fused_cap == 8u;
+    const int64_t n_warps = ((int64_t)n + 31) / 32;
+    int bad = 0;
+#pragma omp parallel
+    {
+        warp_emu::Warp *W = new warp_emu::Warp();
+        std::vector<unsigned long long> scratch(FUSED_WARP_BYTES / 8u + 1u);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t w = 0; w < n_warps; ++w) {
+            const FusedWarp ws = fused_warp(reinterpret_cast<unsigned char *>(scratch.data()), 0u);
+            Hit out[32];
+            const bool ok = warp_emu::run_warp(*W, [&](int lane) {
+                const int64_t i = w * 32 + lane;
+                const bool alive = i < (int64_t)n;
+                const v3 o = alive ? mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]) : mk3(0.0f, 0.0f, 0.0f);
+                const v3 d = alive ? mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]) : mk3(0.0f, 0.0f, 1.0f);
+                out[lane] = cap8 ? trace_fused<true>(V, pk.P, ws, alive, o, d) : trace_fused<false>(V, pk.P, ws, alive, o, d);
+            });
+            if (!ok) {
+#pragma omp atomic write
+                bad = 1;
+                continue;
+            }
+            for (int lane = 0; lane < 32; ++lane) {
+                const int64_t i = w * 32 + lane;
+                if (i >= (int64_t)n) break;
+                ids[i] = out[lane].idx;
+                ts[i] = out[lane].idx >= 0 ? out[lane].t : 0.0f;
+            }
+        }
+        delete W;
+    }
+    return bad ? RDR_ERR_INVALID : RDR_OK;
 }
 
 // the fused scan's layout figures: [fused_ok, fused_top, fused_cap, fused_direct, fused_ns_direct, fused_stage_bytes, blob_bytes]

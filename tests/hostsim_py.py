@@ -22,16 +22,32 @@ class TraceStats(C.Structure):
                 ("nodes_visited", C.c_uint64), ("entries_hit", C.c_uint64)]
 
 
-def build():
+def build(variant: str = "", defines=()):
+    """libhostsim.so, or libhostsim_<variant>.so compiled with extra -D switches (the prepared kernel variants of
+    rdr_fused.cuh, so that their logic is checked on the CPU before they ever run on a GPU)."""
     csrc = os.path.join(_ROOT, "raydar_b200", "csrc")
-    deps = [_SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(_ROOT, "include", "raydar_cuda.h")]
-    if os.path.exists(_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(_LIB) for d in deps):
-        return _LIB
+    out = _LIB if not variant else _LIB.replace("libhostsim.so", f"libhostsim_{variant}.so")
+    deps = [_SRC, os.path.join(_HERE, "hostsim", "warp_emu.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc)] + \
+           [os.path.join(_ROOT, "include", "raydar_cuda.h")]
+    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
     cmd = ["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-std=c++17", "-ffp-contract=off",
            "-fno-fast-math", "-mfma", "-fopenmp", "-shared", "-fPIC", "-Wno-unknown-pragmas",
-           "-I", os.path.join(_ROOT, "include"), "-I", csrc, _SRC, "-o", _LIB]
+           "-I", os.path.join(_ROOT, "include"), "-I", csrc, "-I", os.path.join(_HERE, "hostsim"),
+           *[f"-D{d}" for d in defines], _SRC, "-o", out]
     subprocess.run(cmd, check=True, capture_output=True)
-    return _LIB
+    return out
+
+
+def trace_fused_variant(variant, defines, scene, rays):
+    """trace_fused of a build with extra -D switches (only this entry point of the variant library is used)."""
+    L = C.CDLL(build(variant, defines))
+    L.hs_trace_fused.argtypes = [C.POINTER(rb.RdrSceneFlat), C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+    f = rb._as_flat(scene)
+    rays = np.ascontiguousarray(rays, np.float32)
+    n = rays.shape[0]; ids = np.zeros(n, np.int32); ts = np.zeros(n, np.float32)
+    _ok(L.hs_trace_fused(C.byref(f), n, _fp(rays), _ip(ids), _fp(ts)))
+    return ids, ts
 
 
 _lib = None
@@ -59,6 +75,8 @@ def lib():
         L.hs_bvh2_warp_sim.argtypes = [sfp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
         L.hs_bvh2_perray_sim.argtypes = [sfp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
         L.hs_cluster_info.argtypes = [sfp, u32p, u32p]
+        L.hs_trace_fused.argtypes = [sfp, C.c_uint32, fp, i32p, fp]
+        L.hs_fused_info.argtypes = [sfp, u32p]
         L.hs_stripe_pixels.argtypes = [C.c_uint32] * 5 + [u32p]
         L.hs_stripe_pixels.restype = C.c_uint32
         L.hs_render_stripes.argtypes = [sfp, C.c_uint64] + [C.c_uint32] * 6 + [fp]
@@ -98,6 +116,22 @@ def render(scene, seed, sample_begin, n_samples, max_bounces, accum=None, use_cu
     st = TraceStats()
     _ok(lib().hs_render(C.byref(f), int(use_cull), seed, sample_begin, n_samples, max_bounces, _fp(accum), C.byref(st)))
     return accum, st
+
+
+def trace_fused(scene, rays):
+    """Nearest hits by the product's warp-cooperative fused scan, run on the CPU under the warp emulator."""
+    f = rb._as_flat(scene)
+    rays = np.ascontiguousarray(rays, np.float32)
+    n = rays.shape[0]; ids = np.zeros(n, np.int32); ts = np.zeros(n, np.float32)
+    _ok(lib().hs_trace_fused(C.byref(f), n, _fp(rays), _ip(ids), _fp(ts)))
+    return ids, ts
+
+
+def fused_info(scene):
+    f = rb._as_flat(scene)
+    out = (C.c_uint32 * 7)()
+    _ok(lib().hs_fused_info(C.byref(f), out))
+    return dict(zip(("fused_ok", "fused_top", "fused_cap", "fused_direct", "fused_ns_direct", "fused_stage_bytes", "blob_bytes"), out))
 
 
 def stripe_pixels(width, height, rows, index, count):
