@@ -15,6 +15,7 @@
 #include "rdr_device.cuh"
 #include "rdr_fused.cuh"
 #include "rdr_bvh2.cuh"
+#include "rdr_loop.cuh"
 #include "rdr_launch.h"
 
 namespace rdr {
@@ -69,37 +70,6 @@ __device__ __forceinline__ Hit trace_warp(const SceneView &S, const FrameParams 
     return h;
 }
 
-// Cold per-lane state (accumulator, primary direction, primary hit: LaneStateT in rdr_trace.cuh) in shared memory:
-// word i of the lane at base[i * BLOCK + threadIdx.x] (conflict-free columns).  The COLD variants of the warp-cooperative
-// kernels run their hot loop with 9 registers fewer, and with 18 fewer inside the nearest-hit search (lane_park), which is
-// what lets a 896-thread CTA (28 warps per SM at 72 registers) run without spills.
-template <int BLOCK>
-struct ColdShared {
-    float *col;             // &base[threadIdx.x]
-    __device__ __forceinline__ float get(int i) const { return col[i * BLOCK]; }
-    __device__ __forceinline__ void set(int i, float v) { col[i * BLOCK] = v; }
-};
-template <int BLOCK, bool COLD> struct lane_state_of { typedef LaneState type; };
-template <int BLOCK> struct lane_state_of<BLOCK, true> { typedef LaneStateT<ColdShared<BLOCK> > type; };
-// the path state the scan does not need (throughput, light, RNG counters: 9 words) waits in the lane's shared-memory
-// columns while the warp is inside the nearest-hit search
-template <class ST> __device__ __forceinline__ void lane_park(ST &) {}
-template <class ST> __device__ __forceinline__ void lane_unpark(ST &) {}
-template <int BLOCK> __device__ __forceinline__ void lane_park(LaneStateT<ColdShared<BLOCK> > &st)
-{
-    st.cold.set(COLD_PARK + 0, st.light.x); st.cold.set(COLD_PARK + 1, st.light.y); st.cold.set(COLD_PARK + 2, st.light.z);
-    st.cold.set(COLD_PARK + 3, st.atten.x); st.cold.set(COLD_PARK + 4, st.atten.y); st.cold.set(COLD_PARK + 5, st.atten.z);
-    st.cold.set(COLD_PARK + 6, u2f(st.pixel)); st.cold.set(COLD_PARK + 7, u2f(st.s)); st.cold.set(COLD_PARK + 8, u2f(st.bounce));
-}
-template <int BLOCK> __device__ __forceinline__ void lane_unpark(LaneStateT<ColdShared<BLOCK> > &st)
-{
-    st.light = mk3(st.cold.get(COLD_PARK + 0), st.cold.get(COLD_PARK + 1), st.cold.get(COLD_PARK + 2));
-    st.atten = mk3(st.cold.get(COLD_PARK + 3), st.cold.get(COLD_PARK + 4), st.cold.get(COLD_PARK + 5));
-    st.pixel = f2u(st.cold.get(COLD_PARK + 6)); st.s = f2u(st.cold.get(COLD_PARK + 7)); st.bounce = f2u(st.cold.get(COLD_PARK + 8));
-}
-__device__ __forceinline__ void cold_bind(ColdRegs &, unsigned char *) {}
-template <int BLOCK> __device__ __forceinline__ void cold_bind(ColdShared<BLOCK> &c, unsigned char *base) { c.col = reinterpret_cast<float *>(base) + threadIdx.x; }
-
 // ---- the sample loop (LaneState / lane_shade / trace_brute in rdr_trace.cuh) ------------------------------
 // Persistent lanes in warp lock-step.  The grid is sized to the machine (SMs x resident CTAs), not to the
 // image.  Each iteration:
@@ -117,96 +87,16 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) render_kernel(const __grid_co
     extern __shared__ __align__(128) unsigned char smem[];
     const SceneView S = scene_view(stage_scene<MODE>(smem, P), P.lay);
     uint32_t *scratch0 = scratch_base<MODE>(smem, P);
-    const uint32_t n_owned = P.owned_pixels;        // the whole image, or this shard's row stripes (rdr_set_row_stripes)
-
-    typename lane_state_of<BLOCK, COLD>::type st;
+#define RDR_LOOP_STATE typename lane_state_of<BLOCK, COLD>::type
     // the cold columns follow the per-warp scratch of the cooperative search (mode_smem_bytes)
-    cold_bind(st.cold, reinterpret_cast<unsigned char *>(scratch0 + BLOCK) + (BLOCK / 32) * (MODE == 7 ? BVH2_WARP_BYTES : FUSED_WARP_BYTES));
-    lane_init(st, scratch0 + threadIdx.x);
-    bool exhausted = false;
-#if RDR_CHUNKED
-    // (pixel, sample-chunk) items in chunk-major order (rdr_layout.h).  A lane that claims chunk c > 0 of a pixel is
-    // PENDING until the pixel's progress word says that chunk c - 1 has been stored; it polls once per iteration and never
-    // blocks the warp, and the lane that owns chunk c - 1 claimed it earlier and is resident (persistent grid), so the
-    // wait always ends.  Store side: accumulator, __threadfence, progress word; load side: progress word (volatile),
-    // __threadfence, accumulator past L1 (ld.global.cg: the line may sit in this SM's L1 from a neighbouring pixel).
-    const uint32_t n_items = n_owned * P.n_chunks;
-    bool pending = false;
-    for (;;) {
-        if (pending && *reinterpret_cast<volatile uint32_t *>(P.progress + st.pixel) == P.progress_base + st.s) {
-            __threadfence();
-            const float4 a = __ldcg(reinterpret_cast<const float4 *>(P.accum + st.pixel));
-            f4 acc; acc.x = a.x; acc.y = a.y; acc.z = a.z; acc.w = a.w;
-            const uint32_t s_begin = st.s, s_end = min(s_begin + P.chunk_samples, P.sample_count);
-            lane_start_item(P, st.pixel, acc, s_begin, s_end, st);
-            pending = false;
-            if (!st.alive) {
-                P.accum[st.pixel] = st.acc(); __threadfence();
-                *reinterpret_cast<volatile uint32_t *>(P.progress + st.pixel) = P.progress_base + s_end;
-            }
-        }
-        while (!st.alive && !pending && !exhausted) {
-            const uint32_t k = atomicAdd(P.pixel_counter, 1u);
-            if (k >= n_items) { exhausted = true; break; }
-            const uint32_t c = k / n_owned;
-            const uint32_t pixel = stripe_pixel(P.cam.width, P.stripe_rows, P.stripe_index, P.stripe_count, k - c * n_owned);
-            if (c != 0u) { pending = true; st.pixel = pixel; st.s = st.lane_zero + c * P.chunk_samples; break; }
-            const uint32_t s_end = min(P.chunk_samples, P.sample_count);
-            lane_start_item(P, pixel, P.accum[pixel], 0u, s_end, st);
-            if (!st.alive) {                                // nothing to trace (no bounces)
-                P.accum[pixel] = st.acc(); __threadfence();
-                *reinterpret_cast<volatile uint32_t *>(P.progress + pixel) = P.progress_base + s_end;
-            }
-        }
-        if (!__any_sync(0xffffffffu, st.alive)) {
-            if (!__any_sync(0xffffffffu, pending)) break;
-            __nanosleep(200);                               // only pending lanes left in this warp: poll again
-            continue;
-        }
-        const bool tracing = st.alive;
-        lane_park(st);
-        const Hit h = trace_warp<MODE>(S, P, scratch0, tracing, st.ro, st.rd);
-        lane_unpark(st);
-        if (tracing) lane_accept_hit(st, h);
-        __syncwarp();
-        if (tracing && st.hit.idx < 0) lane_miss(P, st);
-        __syncwarp();
-        bool shade = st.alive;
-        while (__any_sync(0xffffffffu, shade)) {
-            if (shade) shade = !lane_shade_hit(P, S, st) && st.alive;
-        }
-        if (tracing && !st.alive) {                         // the lane's chunk is done
-            P.accum[st.pixel] = st.acc(); __threadfence();
-            *reinterpret_cast<volatile uint32_t *>(P.progress + st.pixel) = P.progress_base + f2u(st.cold.get(COLD_S_END));
-        }
-    }
-    return;
-#endif
-    for (;;) {
-        while (!st.alive && !exhausted) {
-            const uint32_t k = atomicAdd(P.pixel_counter, 1u);
-            if (k >= n_owned) { exhausted = true; break; }
-            const uint32_t pixel = stripe_pixel(P.cam.width, P.stripe_rows, P.stripe_index, P.stripe_count, k);
-            lane_start_pixel(P, pixel, P.accum[pixel], st);
-            if (!st.alive) P.accum[pixel] = st.acc();      // nothing to trace (no samples or no bounces)
-        }
-        if (!__any_sync(0xffffffffu, st.alive)) break;
-        // every lane passes through the same top-level statements each iteration, so the full-mask
-        // __syncwarp()s are safe; they pin the reconvergence points between the phases
-        const bool tracing = st.alive;
-        lane_park(st);
-        const Hit h = trace_warp<MODE>(S, P, scratch0, tracing, st.ro, st.rd);
-        lane_unpark(st);
-        if (tracing) lane_accept_hit(st, h);
-        __syncwarp();
-        if (tracing && st.hit.idx < 0) lane_miss(P, st);
-        __syncwarp();
-        bool shade = st.alive;
-        while (__any_sync(0xffffffffu, shade)) {             // one pass; a second only after a bounce-limit restart
-            if (shade) shade = !lane_shade_hit(P, S, st) && st.alive;
-        }
-        if (tracing && !st.alive) P.accum[st.pixel] = st.acc();
-    }
+#define RDR_LOOP_COLD_BASE (reinterpret_cast<unsigned char *>(scratch0 + BLOCK) + (BLOCK / 32) * (MODE == 7 ? BVH2_WARP_BYTES : FUSED_WARP_BYTES))
+#define RDR_LOOP_LANE_SCRATCH (scratch0 + threadIdx.x)
+#define RDR_LOOP_TRACE(alive, o, d) trace_warp<MODE>(S, P, scratch0, alive, o, d)
+#include "rdr_loop_body.inc"
+#undef RDR_LOOP_STATE
+#undef RDR_LOOP_COLD_BASE
+#undef RDR_LOOP_LANE_SCRATCH
+#undef RDR_LOOP_TRACE
 }
 
 // ---- print_frame_buffer (cpu.rs:221-230): one uchar4 (32-bit) store per pixel ------------------------

@@ -19,6 +19,7 @@
 #define RDR_WARP_EMU 1
 #include "warp_emu.h"
 #include "rdr_fused.cuh"
+#include "rdr_loop.cuh"
 
 using namespace rdr;
 
@@ -568,6 +569,73 @@ int hs_trace_fused(const RdrSceneFlat *sc, uint32_t n, const float *rays, int32_
         delete W;
     }
     return bad ? RDR_ERR_INVALID : RDR_OK;
+}
+
+// The render kernel's sample loop (rdr_loop_body.inc, the very text render_kernel<5 / 6, ...> compiles) around the fused
+// scan, for one emulated CTA of EMU_WARPS warps that share the atomic pixel counter: cold = 1 keeps the cold / parked lane
+// state in "shared-memory" columns (LaneStateT<ColdShared>), 0 in registers.  order: round-robin permutation of the warps
+// (n_order entries, may be NULL).  chunk_samples (RDR_CHUNKED builds only, else ignored): samples per hand-out item.
+}  // extern "C"
+
+constexpr int EMU_WARPS = 4, EMU_BLOCK = 32 * EMU_WARPS;
+
+template <bool COLD>
+static bool emu_render(const Packed &pk, const FrameParams &P, const std::vector<int> &order)
+{
+    const SceneView &S = pk.S;
+    FusedView V;
+    V.pair_block = S.pair_block; V.member_geom = S.fused_geom; V.member_idx = S.fused_idx;
+    const bool cap8 = P.lay.fused_cap == 8u;
+    std::vector<unsigned long long> scratch((size_t)EMU_WARPS * FUSED_WARP_BYTES / 8u + 1u);
+    std::vector<float> cold((size_t)EMU_BLOCK * (COLD_WORDS + COLD_PARK_WORDS), 0.0f);
+    std::vector<uint32_t> lane_words(EMU_BLOCK, 0u);
+    std::vector<warp_emu::Warp> warps(EMU_WARPS);
+    return warp_emu::run_grid(warps, [&](int warp, int lane) {
+        const FusedWarp ws = fused_warp(reinterpret_cast<unsigned char *>(scratch.data()), (uint32_t)warp);
+        (void)lane;
+#define RDR_LOOP_STATE typename lane_state_of<EMU_BLOCK, COLD>::type
+#define RDR_LOOP_COLD_BASE (reinterpret_cast<unsigned char *>(cold.data()))
+#define RDR_LOOP_LANE_SCRATCH (&lane_words[threadIdx.x])
+#define RDR_LOOP_TRACE(alive, o, d) (cap8 ? trace_fused<true>(V, P, ws, alive, o, d) : trace_fused<false>(V, P, ws, alive, o, d))
+#include "rdr_loop_body.inc"
+#undef RDR_LOOP_STATE
+#undef RDR_LOOP_COLD_BASE
+#undef RDR_LOOP_LANE_SCRATCH
+#undef RDR_LOOP_TRACE
+    }, order);
+}
+
+extern "C" {
+
+int hs_render_fused_emu(const RdrSceneFlat *sc, uint64_t seed, uint32_t sample_begin, uint32_t n_samples, uint32_t max_bounces,
+                        int cold, uint32_t stripe_rows, uint32_t stripe_index, uint32_t stripe_count,
+                        const int32_t *order, uint32_t n_order, uint32_t chunk_samples, uint32_t prior_samples, float *accum)
+{
+    Packed pk(sc, false);
+    if (pk.status != RDR_OK) return pk.status;
+    if (!pk.P.lay.fused_ok) return RDR_ERR_UNSUPPORTED;
+    FrameParams P = pk.P;
+    uint32_t counter = 0u;
+    P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
+    P.max_bounces = max_bounces; P.sample_begin = sample_begin; P.sample_count = n_samples;
+    P.accum = reinterpret_cast<f4 *>(accum);
+    P.pixel_counter = &counter;
+    P.stripe_rows = stripe_rows; P.stripe_index = stripe_index; P.stripe_count = stripe_count;
+    P.owned_pixels = stripe_owned_pixels(P.cam.width, P.cam.height, stripe_rows, stripe_index, stripe_count);
+    std::vector<uint32_t> progress;
+#if RDR_CHUNKED
+    progress.assign((size_t)P.cam.width * P.cam.height, prior_samples);       // every pixel holds prior_samples samples
+    P.chunk_samples = chunk_samples ? chunk_samples : n_samples;
+    P.n_chunks = (n_samples + P.chunk_samples - 1u) / P.chunk_samples;
+    P.progress_base = prior_samples;
+    P.progress = progress.data();
+#else
+    (void)chunk_samples; (void)prior_samples;
+#endif
+    if (n_samples == 0u || P.owned_pixels == 0u) return RDR_OK;              // launch_render skips empty launches
+    std::vector<int> ord(order, order + (order ? n_order : 0u));
+    const bool ok = cold ? emu_render<true>(pk, P, ord) : emu_render<false>(pk, P, ord);
+    return ok ? RDR_OK : RDR_ERR_INVALID;
 }
 
 // the fused scan's layout figures: [fused_ok, fused_top, fused_cap, fused_direct, fused_ns_direct, fused_stage_bytes, blob_bytes]

@@ -25,9 +25,12 @@ constexpr size_t STACK_BYTES = 256u << 10;
 
 struct Warp {
     ucontext_t main_ctx, ctx[LANES];
+    ucontext_t *sched = nullptr;        // the context lanes yield to (this warp's main_ctx, or the grid's)
     std::vector<char> stacks;
     bool done[LANES];
     int cur = 0;
+    unsigned tid_base = 0;              // threadIdx.x of lane 0 (warps of one emulated CTA: 0, 32, 64, ...)
+    int warp_index = 0;
     uint32_t arrived = 0, gen = 0;
     uint32_t slot[2][LANES];
     uint64_t progress = 0;              // bumped by every rendezvous arrival and every lane exit (deadlock detection)
@@ -38,7 +41,7 @@ struct Warp {
 inline Warp *&current() { static thread_local Warp *w = nullptr; return w; }
 inline unsigned lane() { return (unsigned)current()->cur; }
 
-inline void yield_lane() { Warp *w = current(); swapcontext(&w->ctx[w->cur], &w->main_ctx); }
+inline void yield_lane() { Warp *w = current(); swapcontext(&w->ctx[w->cur], w->sched); }
 
 // all 32 lanes meet here
 inline void rendezvous()
@@ -76,25 +79,31 @@ inline void lane_entry()
     w->body(w->cur);
     w->done[w->cur] = true;
     ++w->progress;
-    swapcontext(&w->ctx[w->cur], &w->main_ctx);      // never resumed
+    swapcontext(&w->ctx[w->cur], w->sched);          // never resumed
 }
 
-// runs body(lane) for lanes 0..31 as one warp; false = deadlock (a lane exited or stalled while others wait)
-inline bool run_warp(Warp &w, std::function<void(int)> body)
+inline void prepare_lanes(Warp &w)
 {
     if (w.stacks.empty()) w.stacks.resize(STACK_BYTES * LANES);
-    w.body = std::move(body);
     w.arrived = 0; w.gen = 0; w.progress = 0; w.deadlock = false;
-    Warp *prev = current();
-    current() = &w;
     for (int i = 0; i < LANES; ++i) {
         w.done[i] = false;
         getcontext(&w.ctx[i]);
         w.ctx[i].uc_stack.ss_sp = w.stacks.data() + STACK_BYTES * i;
         w.ctx[i].uc_stack.ss_size = STACK_BYTES;
-        w.ctx[i].uc_link = &w.main_ctx;
+        w.ctx[i].uc_link = w.sched;
         makecontext(&w.ctx[i], (void (*)())lane_entry, 0);
     }
+}
+
+// runs body(lane) for lanes 0..31 as one warp; false = deadlock (a lane exited or stalled while others wait)
+inline bool run_warp(Warp &w, std::function<void(int)> body)
+{
+    w.sched = &w.main_ctx;
+    w.body = std::move(body);
+    Warp *prev = current();
+    current() = &w;
+    prepare_lanes(w);
     for (;;) {
         bool all_done = true;
         const uint64_t before = w.progress;
@@ -111,7 +120,44 @@ inline bool run_warp(Warp &w, std::function<void(int)> body)
     return !w.deadlock;
 }
 
-struct ThreadIdx { unsigned x, y, z; ThreadIdx() : x(lane()), y(0), z(0) {} };
+// Several warps of one emulated CTA (threadIdx.x = 32 * warp + lane), interleaved lane by lane on one OS thread: what a
+// kernel whose warps talk through global memory (an atomic work counter, a polled progress word) needs.  `order` permutes
+// the round-robin so that tests can try different interleavings.  false = a warp deadlocked or max_passes was reached
+// (a protocol that never terminates).
+inline bool run_grid(std::vector<Warp> &warps, std::function<void(int, int)> body, const std::vector<int> &order = {},
+                     uint64_t max_passes = 50u * 1000u * 1000u)
+{
+    ucontext_t grid_ctx;
+    Warp *prev = current();
+    for (size_t k = 0; k < warps.size(); ++k) {
+        Warp &w = warps[k];
+        w.sched = &grid_ctx; w.warp_index = (int)k; w.tid_base = 32u * (unsigned)k;
+        w.body = [&body, k](int lane) { body((int)k, lane); };
+        prepare_lanes(w);
+    }
+    bool ok = true;
+    for (uint64_t pass = 0;; ++pass) {
+        bool all_done = true, any_progress = false;
+        for (size_t kk = 0; kk < warps.size(); ++kk) {
+            Warp &w = warps[order.empty() ? kk : (size_t)order[kk % order.size()] % warps.size()];
+            const uint64_t before = w.progress;
+            for (int i = 0; i < LANES; ++i) {
+                if (w.done[i]) continue;
+                all_done = false;
+                w.cur = i;
+                current() = &w;
+                swapcontext(&grid_ctx, &w.ctx[i]);
+            }
+            any_progress |= w.progress != before;
+        }
+        if (all_done) break;
+        if (!any_progress || pass >= max_passes) { ok = false; break; }
+    }
+    current() = prev;
+    return ok;
+}
+
+struct ThreadIdx { unsigned x, y, z; ThreadIdx() : x(current()->tid_base + lane()), y(0), z(0) {} };
 
 }  // namespace warp_emu
 
@@ -144,6 +190,12 @@ inline int __ffs(int v) { return __builtin_ffs(v); }
 inline uint32_t __float_as_uint(float f) { uint32_t u; __builtin_memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(uint32_t u) { float f; __builtin_memcpy(&f, &u, 4); return f; }
 inline float __frcp_rn(float x) { return 1.0f / x; }                         // IEEE division: correctly rounded, as rcp.rn
+inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { const uint32_t old = *p; *p = old + v; return old; }
+inline void __threadfence() {}
+inline void __nanosleep(unsigned) { warp_emu::yield_lane(); }
+struct float4 { float x, y, z, w; };
+inline float4 __ldcg(const float4 *p) { return *p; }
+inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v)
 {
     const unsigned long long old = *p;                                       // lanes never run concurrently

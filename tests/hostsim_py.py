@@ -127,6 +127,23 @@ def trace_fused(scene, rays):
     return ids, ts
 
 
+def render_fused_emu(scene, seed, sample_begin, n_samples, max_bounces, cold=True, stripes=(0, 0, 1), order=None,
+                     chunk_samples=0, prior_samples=0, accum=None, variant=None):
+    """The render kernel's sample loop + fused scan under the warp emulator (one CTA of 4 warps sharing the pixel counter).
+    variant = (name, defines): a hostsim build with extra -D switches (e.g. RDR_CHUNKED=1)."""
+    L = lib() if variant is None else C.CDLL(build(*variant))
+    L.hs_render_fused_emu.argtypes = [C.POINTER(rb.RdrSceneFlat), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                      C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.c_uint32, C.c_uint32,
+                                      C.c_uint32, C.POINTER(C.c_float)]
+    f = rb._as_flat(scene)
+    if accum is None:
+        accum = np.zeros((f.height, f.width, 4), np.float32)
+    ord_arr = np.ascontiguousarray(order if order is not None else [], np.int32)
+    _ok(L.hs_render_fused_emu(C.byref(f), seed, sample_begin, n_samples, max_bounces, int(cold), stripes[0], stripes[1], stripes[2],
+                              ord_arr.ctypes.data_as(C.POINTER(C.c_int32)), len(ord_arr), chunk_samples, prior_samples, _fp(accum)))
+    return accum
+
+
 def fused_info(scene):
     f = rb._as_flat(scene)
     out = (C.c_uint32 * 7)()

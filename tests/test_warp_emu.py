@@ -160,3 +160,58 @@ def test_prepared_variants_keep_the_winner(hs, orc, benchmark_scene):
     ids_v, t_v = hs.trace_fused_variant("prepared", defines, scene, rays)
     ids_l, t_l, _ = hs.trace(scene, rays, use_cull=False)
     assert np.array_equal(ids_v, ids_l) and np.array_equal(u32(t_v), u32(t_l))
+
+
+# ---- the render kernel's sample loop (rdr_loop_body.inc: the text render_kernel compiles) under the emulator ----------
+@pytest.mark.parametrize("cold", [True, False])
+def test_render_loop_bit_exact(hs, orc, benchmark_scene, cold):
+    """One emulated CTA of 4 warps sharing the atomic pixel counter runs the kernel's loop body around the fused scan:
+    persistent lanes, warp lock-step, sample refill from the cached primary hit, cold / parked lane state in
+    shared-memory columns (cold=True, the shipped 896-thread variant's policy) or in registers."""
+    scene = benchmark_scene.with_resolution(64, 36)
+    want = orc.render(scene, 7, 0, 3, 12, n_threads=2)
+    for order in (None, [3, 1, 0, 2], [0, 0, 0, 1, 2, 3]):               # different interleavings of the warps
+        got = hs.render_fused_emu(scene, 7, 0, 3, 12, cold=cold, order=order)
+        assert np.array_equal(u32(got), u32(want))
+
+
+def test_render_loop_progressive_stripes_and_edges(hs, orc, default_scene, benchmark_scene):
+    scene = benchmark_scene.with_resolution(48, 27)
+    want = orc.render(scene, 5, 0, 5, 12, n_threads=2)
+    acc = hs.render_fused_emu(scene, 5, 0, 2, 12)                         # two launches on one accumulator
+    acc = hs.render_fused_emu(scene, 5, 2, 3, 12, accum=acc)
+    assert np.array_equal(u32(acc), u32(want))
+    total = np.zeros_like(want)                                          # three row-stripe shards, 5 rows per stripe
+    for index in range(3):
+        total += hs.render_fused_emu(scene, 5, 0, 5, 12, stripes=(5, index, 3))
+    assert np.array_equal(u32(total), u32(want))
+    for bounces in (0, 1):                                               # `for _ in 0..0`, and paths cut after one trace
+        want_b = orc.render(scene, 5, 0, 4, bounces, n_threads=2)
+        assert np.array_equal(u32(hs.render_fused_emu(scene, 5, 0, 4, bounces)), u32(want_b))
+    small = default_scene.with_resolution(40, 22)                        # primary rays that miss: pixels finished by the sky
+    assert np.array_equal(u32(hs.render_fused_emu(small, 9, 0, 4, 12)), u32(orc.render(small, 9, 0, 4, 12, n_threads=2)))
+    tiny = benchmark_scene.with_resolution(5, 3)                         # fewer pixels than lanes: most lanes never get work
+    assert np.array_equal(u32(hs.render_fused_emu(tiny, 9, 0, 3, 12)), u32(orc.render(tiny, 9, 0, 3, 12, n_threads=1)))
+
+
+def test_chunked_handout_variant(hs, orc, benchmark_scene):
+    """RDR_CHUNKED (prepared, off by default): (pixel, sample-chunk) items in chunk-major order, a chunk starting from the
+    accumulator its predecessor stored, found through a polled per-pixel progress word.  Bit-exact for every chunk length
+    and interleaving -- including images with fewer pixels than lanes, where chunk c + 1 of a pixel is claimed while chunk
+    c is still running and the pending path is what makes the result right."""
+    variant = ("chunked", ("RDR_CHUNKED=1",))
+    scene = benchmark_scene.with_resolution(48, 27)
+    want = orc.render(scene, 7, 0, 6, 12, n_threads=2)
+    for chunk, order, cold in [(6, None, True), (4, [3, 2, 1, 0], True), (2, [1, 1, 1, 0, 2, 3], False), (1, None, True)]:
+        got = hs.render_fused_emu(scene, 7, 0, 6, 12, cold=cold, order=order, chunk_samples=chunk, variant=variant)
+        assert np.array_equal(u32(got), u32(want)), (chunk, order, cold)
+    acc = hs.render_fused_emu(scene, 7, 0, 2, 12, chunk_samples=1, variant=variant)          # progressive
+    acc = hs.render_fused_emu(scene, 7, 2, 4, 12, chunk_samples=3, prior_samples=2, accum=acc, variant=variant)
+    assert np.array_equal(u32(acc), u32(want))
+    tiny = benchmark_scene.with_resolution(8, 4)                          # 32 pixels, 128 lanes
+    want_t = orc.render(tiny, 3, 0, 24, 12, n_threads=1)
+    for chunk, order in [(1, None), (5, [2, 0, 3, 1]), (7, [3, 3, 2, 2, 1, 0])]:
+        got = hs.render_fused_emu(tiny, 3, 0, 24, 12, order=order, chunk_samples=chunk, variant=variant)
+        assert np.array_equal(u32(got), u32(want_t)), (chunk, order)
+    want_0 = orc.render(tiny, 3, 0, 9, 0, n_threads=1)                    # no bounces: items finish at once
+    assert np.array_equal(u32(hs.render_fused_emu(tiny, 3, 0, 9, 0, chunk_samples=2, variant=variant)), u32(want_0))
