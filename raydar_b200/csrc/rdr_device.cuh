@@ -5,6 +5,7 @@
 
 namespace rdr {
 
+#ifndef RDR_WARP_EMU        // the TMA staging is PTX; the CPU warp emulator (tests/hostsim) only needs the scan below
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // global blob -> shared memory with one cp.async.bulk (SASS UBLKCP) completing on an mbarrier;
@@ -38,6 +39,8 @@ __device__ __forceinline__ uint32_t *mask_base(unsigned char *smem, const SceneL
 {
     return reinterpret_cast<uint32_t *>(smem + L.blob_bytes + 16u);
 }
+
+#endif  // RDR_WARP_EMU
 
 // ---- warp-cooperative cluster scan (MODE 4) ---------------------------------------------------------------------
 // Same two-level structure and the same tests as trace_cluster (rdr_trace.cuh), but the per-lane, divergent

@@ -19,6 +19,8 @@
 #define RDR_WARP_EMU 1
 #include "warp_emu.h"
 #include "rdr_fused.cuh"
+#include "rdr_device.cuh"
+#include "rdr_bvh2.cuh"
 #include "rdr_loop.cuh"
 
 using namespace rdr;
@@ -553,6 +555,87 @@ int hs_trace_fused(const RdrSceneFlat *sc, uint32_t n, const float *rays, int32_
                 const v3 o = alive ? mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]) : mk3(0.0f, 0.0f, 0.0f);
                 const v3 d = alive ? mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]) : mk3(0.0f, 0.0f, 1.0f);
                 out[lane] = cap8 ? trace_fused<true>(V, pk.P, ws, alive, o, d) : trace_fused<false>(V, pk.P, ws, alive, o, d);
+            });
+            if (!ok) {
+#pragma omp atomic write
+                bad = 1;
+                continue;
+            }
+            for (int lane = 0; lane < 32; ++lane) {
+                const int64_t i = w * 32 + lane;
+                if (i >= (int64_t)n) break;
+                ids[i] = out[lane].idx;
+                ts[i] = out[lane].idx >= 0 ? out[lane].t : 0.0f;
+            }
+        }
+        delete W;
+    }
+    return bad ? RDR_ERR_INVALID : RDR_OK;
+}
+
+// The warp-cooperative cluster scan (trace_cluster_coop, rdr_device.cuh: what RDR_ACCEL_AUTO runs when a scan-packed scene
+// has more than 32 top-level entries for the fused scan) under the warp emulator.
+int hs_trace_coop(const RdrSceneFlat *sc, uint32_t n, const float *rays, int32_t *ids, float *ts)
+{
+    Packed pk(sc, false);
+    if (pk.status != RDR_OK) return pk.status;
+    const int64_t n_warps = ((int64_t)n + 31) / 32;
+    int bad = 0;
+#pragma omp parallel
+    {
+        warp_emu::Warp *W = new warp_emu::Warp();
+        std::vector<unsigned long long> scratch(COOP_WARP_BYTES / 8u + 1u);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t w = 0; w < n_warps; ++w) {
+            const CoopWarpScratch ws = coop_scratch(reinterpret_cast<unsigned char *>(scratch.data()), 0u);
+            Hit out[32];
+            const bool ok = warp_emu::run_warp(*W, [&](int lane) {
+                const int64_t i = w * 32 + lane;
+                const bool alive = i < (int64_t)n;
+                const v3 o = alive ? mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]) : mk3(0.0f, 0.0f, 0.0f);
+                const v3 d = alive ? mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]) : mk3(0.0f, 0.0f, 1.0f);
+                out[lane] = trace_cluster_coop(pk.S, pk.P.cull, ws, alive, o, d);
+            });
+            if (!ok) {
+#pragma omp atomic write
+                bad = 1;
+                continue;
+            }
+            for (int lane = 0; lane < 32; ++lane) {
+                const int64_t i = w * 32 + lane;
+                if (i >= (int64_t)n) break;
+                ids[i] = out[lane].idx;
+                ts[i] = out[lane].idx >= 0 ? out[lane].t : 0.0f;
+            }
+        }
+        delete W;
+    }
+    return bad ? RDR_ERR_INVALID : RDR_OK;
+}
+
+// The warp-cooperative hierarchy (trace_bvh2, rdr_bvh2.cuh: RDR_ACCEL_AUTO above 1024 objects, BASELINE config 4) under
+// the warp emulator, on a scene packed as a hierarchy.
+int hs_trace_bvh2(const RdrSceneFlat *sc, uint32_t n, const float *rays, int32_t *ids, float *ts)
+{
+    Packed pk(sc, true);
+    if (pk.status != RDR_OK) return pk.status;
+    if (pk.P.lay.mode != 1u || !pk.P.lay.bvh2_ok) return RDR_ERR_UNSUPPORTED;
+    const int64_t n_warps = ((int64_t)n + 31) / 32;
+    int bad = 0;
+#pragma omp parallel
+    {
+        warp_emu::Warp *W = new warp_emu::Warp();
+        std::vector<unsigned long long> scratch(BVH2_WARP_BYTES / 8u + 1u);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t w = 0; w < n_warps; ++w) {
+            const Bvh2Warp ws = bvh2_warp(reinterpret_cast<unsigned char *>(scratch.data()), 0u);
+            Hit out[32];
+            const bool ok = warp_emu::run_warp(*W, [&](int lane) {
+                const int64_t i = w * 32 + lane;
+                const bool alive = i < (int64_t)n;
+                const v3 o = alive ? mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]) : mk3(0.0f, 0.0f, 0.0f);
+                const v3 d = alive ? mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]) : mk3(0.0f, 0.0f, 1.0f);
+                out[lane] = trace_bvh2(pk.S, pk.P, ws, alive, o, d);
             });
             if (!ok) {
 #pragma omp atomic write

@@ -167,6 +167,8 @@ struct ThreadIdx { unsigned x, y, z; ThreadIdx() : x(current()->tid_base + lane(
 #define threadIdx (warp_emu::ThreadIdx())
 
 struct float2 { float x, y; };
+struct uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
 
 inline uint32_t __shfl_sync(uint32_t, uint32_t v, uint32_t src) { return warp_emu::exchange(v, src); }
 inline float __shfl_sync(uint32_t, float v, uint32_t src)
@@ -176,12 +178,14 @@ inline float __shfl_sync(uint32_t, float v, uint32_t src)
     float r; __builtin_memcpy(&r, &u, 4);
     return r;
 }
+inline int __shfl_sync(uint32_t, int v, uint32_t src) { return (int)warp_emu::exchange((uint32_t)v, src); }
 inline uint32_t __shfl_up_sync(uint32_t, uint32_t v, uint32_t delta)
 {
     const unsigned l = warp_emu::lane();
     const uint32_t got = warp_emu::exchange(v, l >= delta ? l - delta : l);
     return l >= delta ? got : v;
 }
+inline uint32_t __shfl_xor_sync(uint32_t, uint32_t v, uint32_t lane_mask) { return warp_emu::exchange(v, warp_emu::lane() ^ lane_mask); }
 inline uint32_t __ballot_sync(uint32_t, bool pred) { return warp_emu::gather_mask(pred); }
 inline bool __any_sync(uint32_t, bool pred) { return warp_emu::gather_mask(pred) != 0u; }
 inline void __syncwarp() { warp_emu::rendezvous(); }

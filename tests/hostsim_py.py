@@ -144,6 +144,28 @@ def render_fused_emu(scene, seed, sample_begin, n_samples, max_bounces, cold=Tru
     return accum
 
 
+def trace_bvh2_emu(scene, rays):
+    """Nearest hits by the product's warp-cooperative hierarchy traversal (trace_bvh2), run under the warp emulator."""
+    L = lib()
+    L.hs_trace_bvh2.argtypes = [C.POINTER(rb.RdrSceneFlat), C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+    f = rb._as_flat(scene)
+    rays = np.ascontiguousarray(rays, np.float32)
+    n = rays.shape[0]; ids = np.zeros(n, np.int32); ts = np.zeros(n, np.float32)
+    _ok(L.hs_trace_bvh2(C.byref(f), n, _fp(rays), _ip(ids), _fp(ts)))
+    return ids, ts
+
+
+def trace_coop_emu(scene, rays):
+    """Nearest hits by the product's warp-cooperative cluster scan (trace_cluster_coop), run under the warp emulator."""
+    L = lib()
+    L.hs_trace_coop.argtypes = [C.POINTER(rb.RdrSceneFlat), C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+    f = rb._as_flat(scene)
+    rays = np.ascontiguousarray(rays, np.float32)
+    n = rays.shape[0]; ids = np.zeros(n, np.int32); ts = np.zeros(n, np.float32)
+    _ok(L.hs_trace_coop(C.byref(f), n, _fp(rays), _ip(ids), _fp(ts)))
+    return ids, ts
+
+
 def fused_info(scene):
     f = rb._as_flat(scene)
     out = (C.c_uint32 * 7)()

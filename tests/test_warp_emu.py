@@ -162,6 +162,67 @@ def test_prepared_variants_keep_the_winner(hs, orc, benchmark_scene):
     assert np.array_equal(ids_v, ids_l) and np.array_equal(u32(t_v), u32(t_l))
 
 
+# ---- the warp-cooperative cluster scan (AUTO's fallback when a scene has more than 32 fused top-level entries) -----------
+@pytest.mark.parametrize("name", ["benchmark", "n1000"])
+def test_cooperative_cluster_scan_under_emulator(hs, orc, benchmark_scene, name):
+    scene = benchmark_scene if name == "benchmark" else ss.config4(1000, 96, 54)
+    if name == "n1000":
+        assert hs.fused_info(scene)["fused_ok"] == 0                    # this is the scene size where AUTO runs this scan
+    rng = np.random.default_rng(23)
+    rays = random_rays(rng, 2_403, scale=8.0 if name == "benchmark" else 60.0)
+    rays[:, 1] = np.abs(rays[:, 1])
+    rays[::50, 3 + (np.arange(len(rays[::50])) % 3)] = 0.0
+    rays[::77, :3] *= 1e4
+    ids_e, t_e = hs.trace_coop_emu(scene, rays)
+    ids_l, t_l, _ = hs.trace(scene, rays, use_cull=False)
+    assert np.array_equal(ids_e, ids_l) and np.array_equal(u32(t_e), u32(t_l))
+    prim, _, _ = primary_rays(orc, scene.with_resolution(96, 54), step=2)
+    ids_e, t_e = hs.trace_coop_emu(scene, prim)
+    ids_l, t_l, _ = hs.trace(scene, prim, use_cull=False)
+    assert np.array_equal(ids_e, ids_l) and np.array_equal(u32(t_e), u32(t_l))
+
+
+# ---- the warp-cooperative hierarchy (config 4's search) -------------------------------------------------------------------
+@pytest.mark.parametrize("n", [300, 6_000])
+def test_cooperative_hierarchy_under_emulator(hs, orc, n):
+    """trace_bvh2 (rdr_bvh2.cuh): per-ray near-first stacks served 8 rays per round by groups of 4 lanes, ballot-popcount
+    emission, pruning by the best exact hit -- the same winners as the exact linear scan."""
+    scene = ss.config4(n, 96, 54)
+    rng = np.random.default_rng(n)
+    rays = random_rays(rng, 1_603, scale=90.0)
+    rays[:, 1] = np.abs(rays[:, 1]) * 0.4
+    rays[::50, 3 + (np.arange(len(rays[::50])) % 3)] = 0.0
+    rays[::77, :3] *= 1e4
+    prim, _, _ = primary_rays(orc, scene, step=2)
+    for batch in (rays, prim):
+        ids_e, t_e = hs.trace_bvh2_emu(scene, batch)
+        for i in range(len(batch)):                                      # the oracle's linear scan (cpu.rs:344-352) for every ray
+            idx, t = orc.trace(scene, batch[i, :3], batch[i, 3:])
+            assert idx == ids_e[i], i
+            if idx >= 0:
+                assert u32(np.float32(t)) == u32(t_e[i])
+    assert (hs.trace_bvh2_emu(scene, prim)[0] >= 0).mean() > 0.5
+
+
+def test_cooperative_hierarchy_ties(hs, orc, default_scene):
+    import copy
+    rng = np.random.default_rng(3)
+    kind, geom = [], []
+    for i in range(400):
+        c = rng.integers(-4, 5, 3).astype(np.float32)
+        k = int(rng.integers(0, 2))
+        kind.append(k); geom.append([c[0], c[1], c[2] + 10, [0.5, 1.0][k] * float(rng.choice([1.0, 1.0, 2.0, 8.0]))])
+    s = copy.copy(default_scene)
+    s.kind = np.asarray(kind, np.uint32); s.geom = np.asarray(geom, np.float32)
+    s.material = np.tile(default_scene.material[1], (400, 1))
+    n = 6_000
+    d = np.concatenate([rng.integers(-6, 7, (n, 2)) / np.float32(8.0), np.ones((n, 1))], 1).astype(np.float32)
+    rays = np.concatenate([np.zeros((n, 3), np.float32), d], 1)
+    ids_e, t_e = hs.trace_bvh2_emu(s, rays)
+    ids_l, t_l, _ = hs.trace(s, rays, use_cull=False)
+    assert np.array_equal(ids_e, ids_l) and np.array_equal(u32(t_e), u32(t_l))
+
+
 # ---- the render kernel's sample loop (rdr_loop_body.inc: the text render_kernel compiles) under the emulator ----------
 @pytest.mark.parametrize("cold", [True, False])
 def test_render_loop_bit_exact(hs, orc, benchmark_scene, cold):
