@@ -158,6 +158,29 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
             L.fused_cap = cap;
             if (fs.clusters.size() <= FUSED_MAX_TOP) break;
         }
+        // Surface-area local search on the fused clustering (rdr_bvh.h: refine_clusters): same kernels, same winners --
+        // the boxes only choose what gets tested -- but a quarter fewer (ray, cluster) tasks on benchmark.rscn.  It runs
+        // for 8-member clusters (scenes up to ~250 objects: ~5 ms at 183 objects; 70 - 200 ms for the 24 / 32-member
+        // clusterings of 500 - 900 objects, which is too slow for a new_frame, so those need RDR_CLUSTER_REFINE=2);
+        // RDR_CLUSTER_REFINE=0 switches it off.  The result only depends on the objects, so it is kept for the next
+        // frame of the same geometry (a camera move, a re-render, the other devices of a multi-GPU handle).
+        {
+            const char *re = getenv("RDR_CLUSTER_REFINE");
+            const int mode = re ? atoi(re) : 1;
+            if (fs.clusters.size() <= FUSED_MAX_TOP && (mode >= 2 || (mode == 1 && L.fused_cap == 8u))) {
+                struct RefineCache { std::vector<uint32_t> kind; std::vector<float> geom; uint32_t cap = 0; ClusterSet cs; };
+                static thread_local RefineCache cache;
+                const bool same = cache.cap == L.fused_cap && cache.kind.size() == n && cache.geom.size() == 4u * (size_t)n &&
+                                  memcmp(cache.kind.data(), sc->kind, sizeof(uint32_t) * n) == 0 &&
+                                  memcmp(cache.geom.data(), sc->geom, sizeof(float) * 4u * n) == 0;
+                if (same) fs = cache.cs;
+                else {
+                    refine_clusters(fs, cprims, L.fused_cap);
+                    cache.kind.assign(sc->kind, sc->kind + n); cache.geom.assign(sc->geom, sc->geom + 4u * (size_t)n);
+                    cache.cap = L.fused_cap; cache.cs = fs;
+                }
+            }
+        }
         L.fused_ok = (n > 0u && fs.clusters.size() <= FUSED_MAX_TOP) ? 1u : 0u;
         if (L.fused_ok) {
             for (auto &members : fs.clusters)

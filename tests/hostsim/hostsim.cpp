@@ -721,6 +721,22 @@ int hs_render_fused_emu(const RdrSceneFlat *sc, uint64_t seed, uint32_t sample_b
     return ok ? RDR_OK : RDR_ERR_INVALID;
 }
 
+// fused clustering: cluster[i] = top-level entry that holds original object i (the fused scan's own clustering)
+int hs_fused_clusters(const RdrSceneFlat *sc, int32_t *cluster)
+{
+    Packed pk(sc, false);
+    if (pk.status != RDR_OK) return pk.status;
+    const SceneLayout &L = pk.P.lay;
+    if (!L.fused_ok) return RDR_ERR_UNSUPPORTED;
+    for (uint32_t i = 0; i < L.n_objects; ++i) cluster[i] = -1;
+    for (uint32_t k = 0; k < L.fused_top; ++k) {
+        const f4 *blk = pk.S.pair_block + (size_t)L.fused_stride * k;
+        const uint32_t desc = f2u(blk[2].z), count = desc & 63u, first = desc >> 12;
+        for (uint32_t j = 0; j < count; ++j) cluster[pk.S.fused_idx[first + j]] = (int32_t)k;
+    }
+    return RDR_OK;
+}
+
 // the fused scan's layout figures: [fused_ok, fused_top, fused_cap, fused_direct, fused_ns_direct, fused_stage_bytes, blob_bytes]
 int hs_fused_info(const RdrSceneFlat *sc, uint32_t out[7])
 {

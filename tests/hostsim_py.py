@@ -166,6 +166,16 @@ def trace_coop_emu(scene, rays):
     return ids, ts
 
 
+def fused_clusters(scene):
+    """Top-level entry of the fused clustering that holds each original object."""
+    L = lib()
+    L.hs_fused_clusters.argtypes = [C.POINTER(rb.RdrSceneFlat), C.POINTER(C.c_int32)]
+    f = rb._as_flat(scene)
+    cl = np.zeros(f.n_objects, np.int32)
+    _ok(L.hs_fused_clusters(C.byref(f), _ip(cl)))
+    return cl
+
+
 def fused_info(scene):
     f = rb._as_flat(scene)
     out = (C.c_uint32 * 7)()

@@ -108,3 +108,50 @@ def test_rscn_round_trip(rb, orc, tmp_path):
     # and the C++ update_matrices agrees with the numpy restatement used by the generator
     sc = rb.Scene.load(path).set_resolution(320, 180)
     assert np.array_equal(u32(sc.matrices()[2]), u32(scene.inv_view)) and np.array_equal(u32(sc.matrices()[3]), u32(scene.inv_proj))
+
+
+def test_cluster_refinement_keeps_shape_and_enters_fewer_boxes(hs, orc, benchmark_scene, monkeypatch):
+    """refine_clusters (rdr_bvh.h): a surface-area local search on the fused clustering.  Every object stays in exactly
+    one cluster, the number of clusters and the <= 8 bound are kept, no cluster falls below two members -- and rays of
+    real paths enter clearly fewer cluster boxes (each entered box is a member-stage task of the fused scan)."""
+    import copy
+    other = copy.copy(benchmark_scene)                                   # a different geometry in between: no stale cache
+    other.geom = benchmark_scene.geom.copy(); other.geom[1:, 0] += 0.25
+    monkeypatch.setenv("RDR_CLUSTER_REFINE", "0")
+    plain = hs.fused_clusters(benchmark_scene)
+    monkeypatch.setenv("RDR_CLUSTER_REFINE", "1")
+    hs.fused_clusters(other)
+    refined = hs.fused_clusters(benchmark_scene)
+    assert np.array_equal(hs.fused_clusters(benchmark_scene), refined)  # deterministic, and the cached copy is the same
+    n = benchmark_scene.n_objects
+    for cl in (plain, refined):
+        assert cl.shape == (n,) and cl.min() == 0 and len(np.unique(cl)) == cl.max() + 1
+    assert plain.max() == refined.max()
+    sizes = np.bincount(refined)
+    assert sizes.max() <= 8 and np.array_equal(np.sort(sizes)[:1], [1]) and (np.sort(sizes)[1:] >= 2).all()   # the floor alone
+    assert (plain != refined).any()
+
+    g = benchmark_scene.geom.astype(np.float64); half = np.where(benchmark_scene.kind == 1, g[:, 3] * 0.5, g[:, 3])
+    lo, hi = g[:, :3] - half[:, None], g[:, :3] + half[:, None]
+    rng = np.random.default_rng(1)
+    scene = benchmark_scene.with_resolution(1920, 1080)
+    rays = []
+    for _ in range(400):
+        x, y = int(rng.integers(0, 1920)), int(rng.integers(0, 1080))
+        o, d = orc.camera_ray(scene, x, y)
+        rays.append(np.concatenate([o, d]))
+        steps = orc.trace_path(scene, x, y, int(rng.integers(0, 1000)), 5, 12)
+        steps = steps[0] if isinstance(steps, tuple) else steps
+        rays += [np.array(list(st.origin) + list(st.direction)) for st in steps if st.object >= 0]
+    rays = np.array(rays, np.float64)
+
+    def entered(cl):
+        ids = [c for c in np.unique(cl) if (cl == c).sum() > 1]
+        blo = np.array([lo[cl == c].min(0) for c in ids]); bhi = np.array([hi[cl == c].max(0) for c in ids])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t1 = (blo[None] - rays[:, None, :3]) / rays[:, None, 3:]; t2 = (bhi[None] - rays[:, None, :3]) / rays[:, None, 3:]
+        tn = np.nanmax(np.minimum(t1, t2), axis=2); tf = np.nanmin(np.maximum(t1, t2), axis=2)
+        return (tf >= np.maximum(tn, 0)).sum(1).mean()
+
+    a, b = entered(plain), entered(refined)
+    assert b < 0.85 * a, (a, b)
