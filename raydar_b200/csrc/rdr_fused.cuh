@@ -32,6 +32,15 @@
 
 namespace rdr {
 
+// RDR_EMU_STATS (CPU warp emulator only): per-warp work counters of the fused scan, bumped by lane 0
+#if defined(RDR_WARP_EMU) && defined(RDR_EMU_STATS)
+struct FusedEmuStats { unsigned long long traces, tasks, member_rounds, sphere_rounds, cube_rounds, sphere_tests, cube_tests; };
+inline FusedEmuStats &fused_emu_stats() { static thread_local FusedEmuStats s{}; return s; }
+#define RDR_FSTAT(field, v) do { if (lane == 0u) fused_emu_stats().field += (v); } while (0)
+#else
+#define RDR_FSTAT(field, v) do { } while (0)
+#endif
+
 typedef unsigned long long f32x2;
 
 #ifdef RDR_WARP_EMU
@@ -322,6 +331,7 @@ __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams
     const uint32_t cnt = __popc(m);
     const uint32_t pre = warp_scan_incl(cnt, lane);
     const uint32_t total = __shfl_sync(FULL, pre, 31);
+    RDR_FSTAT(traces, 1u); RDR_FSTAT(tasks, total);
     {
         uint32_t pos = pre - cnt, mm = m;
         while (mm != 0u) {
@@ -339,6 +349,7 @@ __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams
     for (;;) {
         const bool last = t0 >= total;
         if (!last) {
+            RDR_FSTAT(member_rounds, 1u);
             const uint32_t t = t0 + lane;
             const bool has = t < total;
             const uint32_t task = has ? (uint32_t)ws.tasks[t] : (lane << 8);
@@ -375,12 +386,14 @@ __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams
         while (n_s >= 32u || (last && n_s != 0u)) {
             const uint32_t n = n_s < 32u ? n_s : 32u;
             n_s -= n;
+            RDR_FSTAT(sphere_rounds, 1u); RDR_FSTAT(sphere_tests, n);
             fused_exact<true>(V, ws, lane, ws.surv_s, n_s, n, o, d);
         }
 #pragma unroll 1
         while (n_c >= 32u || (last && n_c != 0u)) {
             const uint32_t n = n_c < 32u ? n_c : 32u;
             n_c -= n;
+            RDR_FSTAT(cube_rounds, 1u); RDR_FSTAT(cube_tests, n);
             fused_exact<false>(V, ws, lane, ws.surv_c, n_c, n, o, d);
         }
         if (last) break;

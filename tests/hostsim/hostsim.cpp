@@ -737,6 +737,21 @@ int hs_fused_clusters(const RdrSceneFlat *sc, int32_t *cluster)
     return RDR_OK;
 }
 
+// work counters of the emulated fused scan since the last call (RDR_EMU_STATS builds; zeros otherwise), summed over the
+// calling thread's warps only: run hs_trace_fused with OMP_NUM_THREADS=1 to get totals
+void hs_fused_emu_stats(unsigned long long out[7], int reset)
+{
+#if defined(RDR_EMU_STATS)
+    FusedEmuStats &s = fused_emu_stats();
+    out[0] = s.traces; out[1] = s.tasks; out[2] = s.member_rounds; out[3] = s.sphere_rounds; out[4] = s.cube_rounds;
+    out[5] = s.sphere_tests; out[6] = s.cube_tests;
+    if (reset) s = FusedEmuStats{};
+#else
+    for (int i = 0; i < 7; ++i) out[i] = 0ull;
+    (void)reset;
+#endif
+}
+
 // the fused scan's layout figures: [fused_ok, fused_top, fused_cap, fused_direct, fused_ns_direct, fused_stage_bytes, blob_bytes]
 int hs_fused_info(const RdrSceneFlat *sc, uint32_t out[7])
 {
