@@ -153,8 +153,9 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
         L.n_members = 9u * L.n_top;           // 8 members + 1 pad quad per cluster: 144-byte stride spreads the banks
         // the fused scan's own clustering: the smallest cluster size (8, 16, 24, 32) that leaves <= 32 top entries
         ClusterSet fs;
+        const char *fm_env = getenv("RDR_FUSED_MEMBERS");          // experiments only: fewer members per 8-slot cluster
         for (uint32_t cap = 8u; cap <= 32u; cap += 8u) {
-            fs = build_clusters(cprims, cap);
+            fs = build_clusters(cprims, (cap == 8u && fm_env) ? (uint32_t)std::max(2, std::min(8, atoi(fm_env))) : cap);
             L.fused_cap = cap;
             if (fs.clusters.size() <= FUSED_MAX_TOP) break;
         }
