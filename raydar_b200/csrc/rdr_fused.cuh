@@ -90,13 +90,23 @@ struct FusedView {
     const uint32_t *member_idx;
 };
 
-// inclusive prefix sum over the warp
+// inclusive prefix sum over the warp.  RDR_SCAN_PRED (prepared, off): the shuffle's own "source lane in range" predicate
+// guards the add -- SHFL + @P IADD per step instead of SHFL + SEL + IADD with a separate lane compare.
+#ifndef RDR_SCAN_PRED
+#define RDR_SCAN_PRED 0
+#endif
 __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, uint32_t lane)
 {
 #pragma unroll
     for (uint32_t off = 1u; off < 32u; off <<= 1) {
+#if RDR_SCAN_PRED && !defined(RDR_WARP_EMU)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t@p add.u32 %0, %0, t;\n\t}"
+                     : "+r"(v) : "r"(off));
+        (void)lane;
+#else
         const uint32_t u = __shfl_up_sync(0xffffffffu, v, off);
         if (lane >= off) v += u;
+#endif
     }
     return v;
 }
@@ -159,6 +169,7 @@ __device__ __forceinline__ void fused_exact(const FusedView &V, FusedWarp ws, ui
 //                      instructions per trace iteration)
 //   RDR_APPROX_RHO     the per-ray sphere margin rho from sqrt.approx (2 ulp, covered by its 1.0001 safety factor)
 //                      instead of two correctly rounded square roots
+//   RDR_SCAN_PRED      warp prefix sums with the shuffle's own predicate (warp_scan_incl)
 #ifndef RDR_DIRECT_BALLOT
 #define RDR_DIRECT_BALLOT 0
 #endif
