@@ -61,9 +61,6 @@ struct RdrRenderer {
     unsigned char *d_blob = nullptr; size_t blob_capacity = 0;
     rdr::f4 *d_accum = nullptr; uchar4 *d_rgba = nullptr; size_t pixel_capacity = 0;
     uint32_t *d_counter = nullptr;       // pixel hand-out counter of the persistent render kernel
-#if RDR_CHUNKED
-    uint32_t *d_progress = nullptr;      // per pixel: samples of the frame accumulated so far (chunk hand-out)
-#endif
     int resident_ctas = 0;
     uint32_t sample_count = 0;
     uint64_t launches = 0;
@@ -142,19 +139,6 @@ int render_launch(RdrRenderer *r, uint32_t n)
     P.owned_pixels = rdr::stripe_owned_pixels(P.cam.width, P.cam.height, P.stripe_rows, P.stripe_index, P.stripe_count);
     RDR_CUDA(r, cudaEventRecord(r->ev_start, r->stream));
     if (r->resident_ctas <= 0) RDR_CUDA(r, rdr::render_resident_ctas(P, scan_variant(r), &r->resident_ctas));
-#if RDR_CHUNKED
-    {
-        // about 12 items per resident lane: whole pixels when there are enough of them, otherwise chunks of >= 32 samples
-        const char *e = getenv("RDR_CHUNK_SAMPLES");                     // experiments: force the chunk length
-        const uint64_t lanes = (uint64_t)r->resident_ctas * 896u;       // upper bound of the resident lanes
-        uint32_t chunks = (uint32_t)std::min<uint64_t>((12u * lanes + P.owned_pixels - 1u) / std::max(1u, P.owned_pixels), std::max(1u, n / 32u));
-        if (chunks < 2u) chunks = 1u;
-        P.chunk_samples = e ? (uint32_t)std::max(1, atoi(e)) : (n + chunks - 1u) / chunks;
-        P.n_chunks = (n + P.chunk_samples - 1u) / P.chunk_samples;
-        P.progress_base = r->sample_count;
-        P.progress = r->d_progress;
-    }
-#endif
     RDR_CUDA(r, rdr::launch_render(P, scan_variant(r), r->resident_ctas, r->stream));
     RDR_CUDA(r, cudaEventRecord(r->ev_stop, r->stream));
     r->launches += 1;
@@ -246,9 +230,6 @@ void rdr_destroy(RdrRenderer *r)
     if (r->d_accum) cudaFree(r->d_accum);
     if (r->d_rgba) cudaFree(r->d_rgba);
     if (r->d_counter) cudaFree(r->d_counter);
-#if RDR_CHUNKED
-    if (r->d_progress) cudaFree(r->d_progress);
-#endif
     if (r->ev_start) cudaEventDestroy(r->ev_start);
     if (r->ev_stop) cudaEventDestroy(r->ev_stop);
     if (r->stream) cudaStreamDestroy(r->stream);
@@ -305,17 +286,9 @@ int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene)
         r->d_accum = nullptr; r->d_rgba = nullptr; r->pixel_capacity = 0;
         RDR_CUDA(r, cudaMalloc(&r->d_accum, n_pixels * sizeof(rdr::f4)));
         RDR_CUDA(r, cudaMalloc(&r->d_rgba, n_pixels * sizeof(uchar4)));
-#if RDR_CHUNKED
-        if (r->d_progress) cudaFree(r->d_progress);
-        r->d_progress = nullptr;
-        RDR_CUDA(r, cudaMalloc(&r->d_progress, n_pixels * sizeof(uint32_t)));
-#endif
         r->pixel_capacity = n_pixels;
     }
     if (n_pixels) RDR_CUDA(r, cudaMemsetAsync(r->d_accum, 0, n_pixels * sizeof(rdr::f4), r->stream));
-#if RDR_CHUNKED
-    if (n_pixels) RDR_CUDA(r, cudaMemsetAsync(r->d_progress, 0, n_pixels * sizeof(uint32_t), r->stream));
-#endif
     RDR_CUDA(r, cudaStreamSynchronize(r->stream));   // blob is a local vector: finish the upload before it dies
 
     if (!r->d_counter) RDR_CUDA(r, cudaMalloc(&r->d_counter, sizeof(uint32_t)));
@@ -342,9 +315,6 @@ int rdr_reset_frame(RdrRenderer *r)
     r->device_render_ms = 0.0;
     const size_t n_pixels = (size_t)r->params.cam.width * r->params.cam.height;
     if (n_pixels) RDR_CUDA(r, cudaMemsetAsync(r->d_accum, 0, n_pixels * sizeof(rdr::f4), r->stream));
-#if RDR_CHUNKED
-    if (n_pixels) RDR_CUDA(r, cudaMemsetAsync(r->d_progress, 0, n_pixels * sizeof(uint32_t), r->stream));
-#endif
     r->sample_count = 0;
     return RDR_OK;
 }

@@ -9,8 +9,6 @@
 //   kat_* kernels      per-function known-answer entry points
 #include <cuda_runtime.h>
 
-#include <cstdlib>
-
 #include "raydar_cuda.h"
 #include "rdr_device.cuh"
 #include "rdr_fused.cuh"
@@ -290,26 +288,27 @@ static size_t smem_optin_limit()
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 48u << 10;
     return (size_t)v;
 }
-static int env_int(const char *name, int dflt)
-{
-    const char *e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-// RDR_FUSED_CTA / RDR_BVH2_CTA (experiments) force a shape: fused 1 = 896 cold, 3 = 768 cold, 4 = 768 registers,
-// 0 = 3 x 256 registers; hierarchy 0 = 768, 1 = 640, 2 = 512 (registers).
+// -DRDR_FUSED_CTA / -DRDR_BVH2_CTA (kernel experiments, raydar_b200.build.build_variant) force a shape: fused 1 = 896 cold,
+// 3 = 768 cold, 4 = 768 registers, 0 = 3 x 256 registers; hierarchy 0 = 768, 1 = 640, 2 = 512 (registers).
+#ifndef RDR_FUSED_CTA
+#define RDR_FUSED_CTA -1
+#endif
+#ifndef RDR_BVH2_CTA
+#define RDR_BVH2_CTA -1
+#endif
 static RenderShape render_shape(const FrameParams &P, int mode)
 {
     if (mode < 5) return RenderShape{RDR_BLOCK, false};
     const size_t limit = smem_optin_limit();
     if (mode == 7) {
-        static const int cfg = env_int("RDR_BVH2_CTA", -1);
+        const int cfg = RDR_BVH2_CTA;
         switch (cfg) {
         case 0: return RenderShape{768u, false};
         case 2: return RenderShape{512u, false};
         default: return RenderShape{640u, false};      // its per-ray stacks (9.9 KB per warp) leave no room for cold columns
         }
     }
-    static const int cfg = env_int("RDR_FUSED_CTA", -1);
+    const int cfg = RDR_FUSED_CTA;
     if (cfg == 0) return RenderShape{RDR_BLOCK, false};
     if (cfg == 1) return RenderShape{896u, true};
     if (cfg == 3) return RenderShape{768u, true};

@@ -50,12 +50,6 @@
 
 #include "rdr_core.cuh"
 
-// RDR_CHUNKED (prepared, off: NOT yet run on a GPU): hand out (pixel, sample-chunk) items instead of whole pixels, so
-// that a launch with few pixels per lane (row stripes on many GPUs: 2 pixels of 8192 spp per lane at 1080p on 8 GPUs)
-// still ends balanced.  The default build is unchanged by it (SASS fingerprint checked, scripts/sass_fingerprint.sh).
-#ifndef RDR_CHUNKED
-#define RDR_CHUNKED 0
-#endif
 
 namespace rdr {
 
@@ -119,13 +113,6 @@ struct FrameParams {
     // s % stripe_count == stripe_index.  stripe_count <= 1: the whole image.  owned_pixels = pixels handed out.
     uint32_t stripe_rows, stripe_index, stripe_count;
     uint32_t owned_pixels;
-#if RDR_CHUNKED
-    // (pixel, sample-chunk) hand-out: a launch of sample_count samples is dealt out as owned_pixels * n_chunks items in
-    // chunk-major order; chunk c of a pixel covers samples [c * chunk_samples, ...) and starts from the accumulator that
-    // chunk c - 1 stored (progress[pixel] = samples of the frame accumulated so far, polled without blocking the warp)
-    uint32_t chunk_samples, n_chunks, progress_base;
-    uint32_t *progress;
-#endif
     TopParams top;                       // fused scan only (lay.fused_ok)
 };
 

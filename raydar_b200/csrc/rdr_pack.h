@@ -13,6 +13,10 @@
 #include "rdr_bvh.h"
 #include "rdr_layout.h"
 
+#ifndef RDR_CLUSTER_REFINE
+#define RDR_CLUSTER_REFINE 1
+#endif
+
 namespace rdr {
 
 inline uint32_t round_up_u32(uint32_t v, uint32_t m) { return (v + m - 1u) / m * m; }
@@ -134,8 +138,7 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
             p.c[0] = g[0]; p.c[1] = g[1]; p.c[2] = g[2]; p.index = i; p.cube = sc->kind[i] == RDR_CUBE;
             p.e = p.cube ? std::fabs(g[3]) * 0.5f + cube_pad : std::fabs(g[3]) + 2.0f * cube_pad;
         }
-        const char *cap_env = getenv("RDR_CLUSTER_CAP");          // experiments only
-        ClusterSet cs = build_clusters(cprims, cap_env ? (uint32_t)std::max(2, std::min(8, atoi(cap_env))) : 8u);
+        ClusterSet cs = build_clusters(cprims, 8u);
         // single-primitive entries first: the scan pushes them straight to the exact-test queue
         // ... spheres before cubes among them, and spheres before cubes inside every cluster (the fused scan splits
         // a cluster's survivor bits into a sphere and a cube part with one mask)
@@ -153,21 +156,19 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
         L.n_members = 9u * L.n_top;           // 8 members + 1 pad quad per cluster: 144-byte stride spreads the banks
         // the fused scan's own clustering: the smallest cluster size (8, 16, 24, 32) that leaves <= 32 top entries
         ClusterSet fs;
-        const char *fm_env = getenv("RDR_FUSED_MEMBERS");          // experiments only: fewer members per 8-slot cluster
         for (uint32_t cap = 8u; cap <= 32u; cap += 8u) {
-            fs = build_clusters(cprims, (cap == 8u && fm_env) ? (uint32_t)std::max(2, std::min(8, atoi(fm_env))) : cap);
+            fs = build_clusters(cprims, cap);
             L.fused_cap = cap;
             if (fs.clusters.size() <= FUSED_MAX_TOP) break;
         }
         // Surface-area local search on the fused clustering (rdr_bvh.h: refine_clusters): same kernels, same winners --
         // the boxes only choose what gets tested -- but a quarter fewer (ray, cluster) tasks on benchmark.rscn.  It runs
         // for 8-member clusters (scenes up to ~250 objects: ~5 ms at 183 objects; 70 - 200 ms for the 24 / 32-member
-        // clusterings of 500 - 900 objects, which is too slow for a new_frame, so those need RDR_CLUSTER_REFINE=2);
-        // RDR_CLUSTER_REFINE=0 switches it off.  The result only depends on the objects, so it is kept for the next
+        // clusterings of 500 - 900 objects, which is too slow for a new_frame: compile with -DRDR_CLUSTER_REFINE=2 for those;
+        // 0 switches it off).  Measured on B200: 6,333 against 5,907 Msamples/s on benchmark.rscn (profiles/variants_r03a.txt).  The result only depends on the objects, so it is kept for the next
         // frame of the same geometry (a camera move, a re-render, the other devices of a multi-GPU handle).
         {
-            const char *re = getenv("RDR_CLUSTER_REFINE");
-            const int mode = re ? atoi(re) : 1;
+            const int mode = RDR_CLUSTER_REFINE;
             if (fs.clusters.size() <= FUSED_MAX_TOP && (mode >= 2 || (mode == 1 && L.fused_cap == 8u))) {
                 struct RefineCache { std::vector<uint32_t> kind; std::vector<float> geom; uint32_t cap = 0; ClusterSet cs; };
                 static thread_local RefineCache cache;

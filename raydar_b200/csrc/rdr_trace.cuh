@@ -432,13 +432,8 @@ RDR_HD uint32_t lane_varying_zero(uint32_t *scratch)
 // primary ray direction (3) and the cached primary hit (2) -- sits behind a storage policy: registers (ColdRegs: the
 // host simulation and the per-lane kernels) or the lane's column of a shared-memory array (ColdShared, rdr_kernels.cu:
 // 9 registers fewer in the hot loop of the fused kernel, paid with 9 LDS / 4 STS per finished sample).
-#if RDR_CHUNKED
-enum { COLD_ACC = 0, COLD_CAM_D = 4, COLD_H0_IDX = 7, COLD_H0_T = 8, COLD_S_END = 9, COLD_WORDS = 10,   // + end of the lane's sample chunk
-       COLD_PARK = 10, COLD_PARK_WORDS = 9 };
-#else
 enum { COLD_ACC = 0, COLD_CAM_D = 4, COLD_H0_IDX = 7, COLD_H0_T = 8, COLD_WORDS = 9,
        COLD_PARK = 9, COLD_PARK_WORDS = 9 };     // + the path state parked across a trace (ColdShared only)
-#endif
 struct ColdRegs {
     float w[COLD_WORDS];
     RDR_HD float get(int i) const { return w[i]; }
@@ -516,30 +511,6 @@ RDR_HD void lane_start_pixel(const FrameParams &P, uint32_t pixel, f4 acc, ST &s
     if (st.alive) { st.rd = camera_ray_dir_cold(P.cam, pixel % P.cam.width, pixel / P.cam.width); st.set_cam_d(st.rd); }
 }
 
-#if RDR_CHUNKED
-// take ownership of samples [s_begin, s_end) of `pixel` (acc = the accumulator after samples [0, s_begin))
-template <class ST>
-RDR_HD void lane_start_item(const FrameParams &P, uint32_t pixel, f4 acc, uint32_t s_begin, uint32_t s_end, ST &st)
-{
-    st.pixel = pixel;
-    st.s = st.lane_zero + s_begin; st.bounce = st.lane_zero;
-    st.cold.set(COLD_S_END, u2f(s_end));
-    st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
-    st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
-    if (P.max_bounces == 0u) {
-        for (uint32_t s = s_begin; s < s_end; ++s) {
-            acc.x = fadd(acc.x, 0.0f); acc.y = fadd(acc.y, 0.0f); acc.z = fadd(acc.z, 0.0f); acc.w = fadd(acc.w, 1.0f);
-        }
-        st.set_acc(acc);
-        st.alive = false;
-        return;
-    }
-    st.set_acc(acc);
-    st.alive = s_end > s_begin;
-    st.primary_pending = st.alive;
-    if (st.alive) { st.rd = camera_ray_dir_cold(P.cam, pixel % P.cam.width, pixel / P.cam.width); st.set_cam_d(st.rd); }
-}
-#endif
 
 // the traced hit of the lane's current ray arrives
 template <class ST>
@@ -554,11 +525,7 @@ RDR_HD void lane_accept_hit(ST &st, Hit h)
 template <class ST>
 RDR_HD bool lane_next_sample(const FrameParams &P, ST &st)
 {
-#if RDR_CHUNKED
-    if (++st.s >= f2u(st.cold.get(COLD_S_END))) { st.alive = false; return false; }      // end of the lane's chunk
-#else
     if (++st.s >= P.sample_count) { st.alive = false; return false; }
-#endif
     st.bounce = st.lane_zero; st.hit = st.h0();
     st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]); st.rd = st.cam_d();
     st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);

@@ -705,16 +705,7 @@ int hs_render_fused_emu(const RdrSceneFlat *sc, uint64_t seed, uint32_t sample_b
     P.pixel_counter = &counter;
     P.stripe_rows = stripe_rows; P.stripe_index = stripe_index; P.stripe_count = stripe_count;
     P.owned_pixels = stripe_owned_pixels(P.cam.width, P.cam.height, stripe_rows, stripe_index, stripe_count);
-    std::vector<uint32_t> progress;
-#if RDR_CHUNKED
-    progress.assign((size_t)P.cam.width * P.cam.height, prior_samples);       // every pixel holds prior_samples samples
-    P.chunk_samples = chunk_samples ? chunk_samples : n_samples;
-    P.n_chunks = (n_samples + P.chunk_samples - 1u) / P.chunk_samples;
-    P.progress_base = prior_samples;
-    P.progress = progress.data();
-#else
     (void)chunk_samples; (void)prior_samples;
-#endif
     if (n_samples == 0u || P.owned_pixels == 0u) return RDR_OK;              // launch_render skips empty launches
     std::vector<int> ord(order, order + (order ? n_order : 0u));
     const bool ok = cold ? emu_render<true>(pk, P, ord) : emu_render<false>(pk, P, ord);

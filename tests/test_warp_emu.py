@@ -253,26 +253,3 @@ def test_render_loop_progressive_stripes_and_edges(hs, orc, default_scene, bench
     assert np.array_equal(u32(hs.render_fused_emu(small, 9, 0, 4, 12)), u32(orc.render(small, 9, 0, 4, 12, n_threads=2)))
     tiny = benchmark_scene.with_resolution(5, 3)                         # fewer pixels than lanes: most lanes never get work
     assert np.array_equal(u32(hs.render_fused_emu(tiny, 9, 0, 3, 12)), u32(orc.render(tiny, 9, 0, 3, 12, n_threads=1)))
-
-
-def test_chunked_handout_variant(hs, orc, benchmark_scene):
-    """RDR_CHUNKED (prepared, off by default): (pixel, sample-chunk) items in chunk-major order, a chunk starting from the
-    accumulator its predecessor stored, found through a polled per-pixel progress word.  Bit-exact for every chunk length
-    and interleaving -- including images with fewer pixels than lanes, where chunk c + 1 of a pixel is claimed while chunk
-    c is still running and the pending path is what makes the result right."""
-    variant = ("chunked", ("RDR_CHUNKED=1",))
-    scene = benchmark_scene.with_resolution(48, 27)
-    want = orc.render(scene, 7, 0, 6, 12, n_threads=2)
-    for chunk, order, cold in [(6, None, True), (4, [3, 2, 1, 0], True), (2, [1, 1, 1, 0, 2, 3], False), (1, None, True)]:
-        got = hs.render_fused_emu(scene, 7, 0, 6, 12, cold=cold, order=order, chunk_samples=chunk, variant=variant)
-        assert np.array_equal(u32(got), u32(want)), (chunk, order, cold)
-    acc = hs.render_fused_emu(scene, 7, 0, 2, 12, chunk_samples=1, variant=variant)          # progressive
-    acc = hs.render_fused_emu(scene, 7, 2, 4, 12, chunk_samples=3, prior_samples=2, accum=acc, variant=variant)
-    assert np.array_equal(u32(acc), u32(want))
-    tiny = benchmark_scene.with_resolution(8, 4)                          # 32 pixels, 128 lanes
-    want_t = orc.render(tiny, 3, 0, 24, 12, n_threads=1)
-    for chunk, order in [(1, None), (5, [2, 0, 3, 1]), (7, [3, 3, 2, 2, 1, 0])]:
-        got = hs.render_fused_emu(tiny, 3, 0, 24, 12, order=order, chunk_samples=chunk, variant=variant)
-        assert np.array_equal(u32(got), u32(want_t)), (chunk, order)
-    want_0 = orc.render(tiny, 3, 0, 9, 0, n_threads=1)                    # no bounces: items finish at once
-    assert np.array_equal(u32(hs.render_fused_emu(tiny, 3, 0, 9, 0, chunk_samples=2, variant=variant)), u32(want_0))
