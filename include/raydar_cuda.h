@@ -123,6 +123,8 @@ int rdr_profiler(const RdrRenderer *r, RdrProfiler *out);
 uint32_t rdr_sample_count(const RdrRenderer *r);
 uint32_t rdr_max_sample_count(const RdrRenderer *r);
 uint32_t rdr_max_bounces(const RdrRenderer *r);
+/* On a multi-GPU handle a new max_sample_count takes effect at the next rdr_new_frame (the devices' shares of the
+ * frame's samples are fixed there); max_bounces applies to the next launch, as on one GPU. */
 int rdr_set_max_sample_count(RdrRenderer *r, uint32_t count);
 int rdr_set_max_bounces(RdrRenderer *r, uint32_t bounces);
 
@@ -137,7 +139,7 @@ int rdr_set_sample_offset(RdrRenderer *r, uint32_t first_sample);
  * sum of their accumulators (x + 0 = x) is BIT-IDENTICAL to the one-instance image.  count <= 1 or
  * stripe_rows == 0: the whole image.  Takes effect at the next launch; the accumulator stays W*H. */
 int rdr_set_row_stripes(RdrRenderer *r, uint32_t stripe_rows, uint32_t index, uint32_t count);
-int rdr_set_accel(RdrRenderer *r, int accel);                 /* RDR_ACCEL_* */
+int rdr_set_accel(RdrRenderer *r, int accel);                 /* RDR_ACCEL_*; takes effect at the next rdr_new_frame */
 /* Zero the accumulator and sample_count but keep the scene already resident on the device
  * (new_frame without the scene upload; the editor calls new_frame for every change, the
  * throughput path only needs a fresh accumulator). */
@@ -159,8 +161,39 @@ uint64_t rdr_launch_count(const RdrRenderer *r);
 uint64_t rdr_scene_device_bytes(const RdrRenderer *r);
 
 /* single-process multi-GPU: one sub-renderer per device, sample ranges split evenly, accumulators
- * combined with one ncclReduce(sum, f32) onto devices[0] before resolve. */
+ * combined by the fused peer-memory reduce + resolve (rdr_set_combine) or one ncclReduce(sum, f32) onto devices[0].
+ * Progressive calls: rdr_render_sample adds exactly ONE sample per call, as the trait does (cpu.rs:142-158) -- with the
+ * STRIPES partition every device renders it for its own rows (latency / G), with SAMPLES the devices take turns. */
 int rdr_create_multi(const RdrConfig *config, int n_devices, const int *devices, RdrRenderer **out);
+/* How a multi-GPU handle combines the per-GPU accumulators into the image:
+ *   PEER  fused reduce + resolve over NVLink peer memory: every GPU sums ITS 1/G of the pixels from all accumulators
+ *         (fixed order, device 0 first), quantises (cpu.rs:221-230) and writes its RGBA8 slice straight into the host
+ *         image -- no rooted reduce, no separate resolve or copy.  With the STRIPES partition a GPU only reads its own
+ *         accumulator.  Needs peer access between all devices of the handle.
+ *   NCCL  one ncclReduce(sum, f32) onto devices[0], then resolve and copy there (the fallback, and the check of PEER)
+ *   AUTO  PEER when every pair of devices has peer access, else NCCL (default) */
+enum { RDR_COMBINE_AUTO = 0, RDR_COMBINE_PEER = 1, RDR_COMBINE_NCCL = 2 };
+int rdr_set_combine(RdrRenderer *r, int combine);
+int rdr_combine_in_use(const RdrRenderer *r);                 /* RDR_COMBINE_PEER | RDR_COMBINE_NCCL; AUTO for one device */
+/* Pinned host memory for images, visible to every device: an rgba8 argument that lies in such a buffer is written by
+ * the GPUs directly (PEER combine) or by one asynchronous DMA; any other pointer is accepted too and costs a staging
+ * copy.  The Rust shim keeps one per renderer and copies into the RgbaImage it returns. */
+int rdr_alloc_host_image(size_t bytes, uint8_t **out);
+void rdr_free_host_image(uint8_t *image);
+
+/* ---- one process per GPU (torchrun / MPI style): the same fused combine over CUDA IPC ------------------------- */
+/* Every rank exports its accumulator and device image (RDR_IPC_HANDLE_BYTES each, after rdr_new_frame), the ranks
+ * exchange the handles (all-gather) and attach; rdr_peer_combine then sums this rank's 1/world of the pixels over all
+ * ranks' accumulators and writes the RGBA8 slice into rank 0's device image (rdr_read_image on rank 0 reads it back).
+ * The caller orders the ranks: all renders finished before any combine, all combines before the next frame's reset
+ * (two barriers).  Detach on every rank before a resolution change. */
+enum { RDR_IPC_HANDLE_BYTES = 128 };
+int rdr_ipc_export(RdrRenderer *r, void *handle);
+int rdr_peer_attach(RdrRenderer *r, uint32_t rank, uint32_t world, const void *handles /* world * RDR_IPC_HANDLE_BYTES */);
+int rdr_peer_combine(RdrRenderer *r, uint32_t divisor);
+int rdr_peer_detach(RdrRenderer *r);
+int rdr_read_image(RdrRenderer *r, uint8_t *rgba8);          /* the device image (last resolve / combine) -> host */
+
 /* how a multi-GPU handle splits the frame (takes effect at the next new_frame):
  *   SAMPLES  every device renders the whole image for its share of the sample indices (default; perfect balance,
  *            result equal to one GPU up to f32 summation order)
@@ -183,6 +216,15 @@ int rdr_kat_hit_cube(RdrRenderer *r, uint32_t n, const float *rays, const float 
 int rdr_kat_trace(RdrRenderer *r, uint32_t n, const float *rays, int32_t *ids, float *t);
 /* camera rays of the current frame for n pixels (xy n*2 u32) -> rays n*6 */
 int rdr_kat_camera_rays(RdrRenderer *r, uint32_t n, const uint32_t *xy, float *rays);
+/* the shading helpers, n records of 12 floats in -> 8 floats out (unused slots 0):
+ *   REFLECT       utils/mod.rs:14-16    in v[3] n[3]                               out r[3]
+ *   REFRACT       utils/mod.rs:25-35    in v[3] n[3] ratio                         out r[3]
+ *   CAN_REFRACT   utils/mod.rs:37-44    in v[3] n[3] ratio                         out flag
+ *   WORLD_SAMPLE  world.rs:17-34        in d[3] kind(0 sky, 1 solid) a[3] b[3]     out rgb[3]
+ *   CLOSEST_HIT   cpu.rs:354-394        in o[3] d[3] t is_sphere c[3] size         out p[3] n[3] front
+ *   QUANTISE      cpu.rs:224-228        in sum n                                   out the u8 value */
+enum { RDR_KAT_REFLECT = 0, RDR_KAT_REFRACT = 1, RDR_KAT_CAN_REFRACT = 2, RDR_KAT_WORLD_SAMPLE = 3, RDR_KAT_CLOSEST_HIT = 4, RDR_KAT_QUANTISE = 5 };
+int rdr_kat_vec(RdrRenderer *r, int op, uint32_t n, const float *in, float *out);
 /* raw RNG block of the spec (Philox4x32-10), computed on the device */
 int rdr_kat_rng(RdrRenderer *r, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block, uint32_t out[4]);
 

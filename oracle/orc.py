@@ -98,6 +98,11 @@ def lib():
         L.orc_trace_path.restype = C.c_uint32
         L.orc_render.argtypes = [sp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                  fp, C.c_int, C.POINTER(Stats)]
+        L.orc_bvh_build.argtypes = [sp]; L.orc_bvh_build.restype = C.c_void_p
+        L.orc_bvh_free.argtypes = [C.c_void_p]; L.orc_bvh_free.restype = None
+        L.orc_trace_bvh.argtypes = [sp, C.c_void_p, fp, fp, fp, C.POINTER(C.c_uint64)]; L.orc_trace_bvh.restype = C.c_int
+        L.orc_render_region.argtypes = [sp, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                        C.c_uint32, C.c_uint32, fp, C.c_int, C.POINTER(Stats)]
         L.orc_resolve.argtypes = [fp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint8)]
         L.orc_max_threads.restype = C.c_int
         _lib = L
@@ -280,6 +285,42 @@ def render(scene: Scene, seed: int, sample_begin: int, sample_end: int, max_boun
                      scene.height if row_end is None else row_end, _fp(accum), n_threads,
                      C.byref(st) if want_stats else None)
     return (accum, st) if want_stats else accum
+
+
+class Bvh:
+    """The oracle's own BVH over a scene (not in the reference; see raydar_oracle.h).  Keeps the scene arrays alive."""
+
+    def __init__(self, scene: Scene):
+        self.scene = scene
+        self._s = scene.c_struct()
+        self._h = lib().orc_bvh_build(C.byref(self._s))
+
+    def trace(self, o, d):
+        t = C.c_float(0); tests = C.c_uint64(0)
+        idx = lib().orc_trace_bvh(C.byref(self._s), self._h, _f3(o), _f3(d), C.byref(t), C.byref(tests))
+        return idx, np.float32(t.value), int(tests.value)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.orc_bvh_free(self._h)
+            self._h = None
+
+
+def build_bvh(scene: Scene) -> Bvh:
+    return Bvh(scene)
+
+
+def render_region(scene: Scene, seed: int, sample_begin: int, sample_end: int, max_bounces: int,
+                  x0: int, y0: int, w: int, h: int, n_threads: int = 1, want_stats: bool = False, bvh: Bvh | None = None):
+    """orc.render for a pixel rectangle; returns (accum[h, w, 4], stats, seconds)."""
+    import time
+    s = scene.c_struct()
+    accum = np.zeros((h, w, 4), np.float32)
+    st = Stats()
+    t0 = time.perf_counter()
+    lib().orc_render_region(C.byref(s), bvh._h if bvh is not None else None, seed, sample_begin, sample_end, max_bounces,
+                            x0, y0, w, h, _fp(accum), n_threads, C.byref(st) if want_stats else None)
+    return accum, st, time.perf_counter() - t0
 
 
 def resolve(accum: np.ndarray, sample_count: int) -> np.ndarray:

@@ -8,6 +8,7 @@
 #include "raydar_oracle.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -199,6 +200,164 @@ int orc_trace(const OrcScene *s, const float o[3], const float d[3], float *t_ou
     return best;
 }
 
+
+/* ---- oracle-side BVH (NOT in the reference: cpu.rs:344-352 is a linear scan) ---------------------------------------
+ * A binary median-split hierarchy over the objects' boxes that returns exactly orc_trace's winner: the boxes only
+ * decide which objects get the exact test above; the winner is the (t, index) minimum with NaN last, and a subtree is
+ * skipped only when its (conservatively early) entry distance lies strictly beyond the best exact t so far, so equal-t
+ * candidates with a lower index are still visited.  Conservative: the slab test runs in double precision on boxes
+ * grown per ray by bounds of the exact tests' own f32 noise -- the as-written sphere quadratic cancels badly, so a
+ * sphere can report a hit up to sqrt(r^2 + eps S) from its centre, S = (|o| + |c|)^2 + r^2 (margins are 4x the bound
+ * DESIGN.md 4.2 derives).  Rays with a zero, denormal or non-finite component take the linear scan.
+ * Used to time a CPU path at 100k objects (bench.py) and checked against orc_trace in tests/test_oracle_bvh.py. */
+typedef struct { float lo[3], hi[3]; int32_t left, right; uint32_t first, count; uint32_t has_sphere; } OrcBvhNode;
+struct OrcBvh {
+    OrcBvhNode *nodes; uint32_t n_nodes;
+    uint32_t *order;              /* leaf object indices */
+    double c_max;                 /* max |centre| + extent over the scene */
+    double r_min;                 /* smallest sphere radius */
+    double q_max;                 /* max over spheres of 2 |c|^2 + r^2 */
+};
+
+static void obj_box(const OrcScene *s, uint32_t i, float lo[3], float hi[3])
+{
+    const float *g = s->geom + 4 * (size_t)i;
+    const float e = s->kind[i] == ORC_SPHERE ? fabsf(g[3]) : fabsf(g[3]) * 0.5f;
+    for (int a = 0; a < 3; ++a) { lo[a] = g[a] - e; hi[a] = g[a] + e; }
+}
+
+static int32_t bvh_build_rec(const OrcScene *s, OrcBvh *b, uint32_t first, uint32_t count)
+{
+    const int32_t me = (int32_t)b->n_nodes++;
+    OrcBvhNode *n = &b->nodes[me];
+    n->first = first; n->count = count; n->left = n->right = -1; n->has_sphere = 0;
+    float clo[3] = { INFINITY, INFINITY, INFINITY }, chi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int a = 0; a < 3; ++a) { n->lo[a] = INFINITY; n->hi[a] = -INFINITY; }
+    for (uint32_t k = 0; k < count; ++k) {
+        const uint32_t i = b->order[first + k];
+        float lo[3], hi[3];
+        obj_box(s, i, lo, hi);
+        if (s->kind[i] == ORC_SPHERE) n->has_sphere = 1;
+        for (int a = 0; a < 3; ++a) {
+            if (lo[a] < n->lo[a]) n->lo[a] = lo[a];
+            if (hi[a] > n->hi[a]) n->hi[a] = hi[a];
+            const float c = s->geom[4 * (size_t)i + a];
+            if (c < clo[a]) clo[a] = c;
+            if (c > chi[a]) chi[a] = c;
+        }
+    }
+    if (count <= 4) return me;
+    int axis = 0;
+    if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+    if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+    if (!(chi[axis] > clo[axis])) return me;                       /* coincident centres: one leaf */
+    /* median split by centre: nth_element by simple quickselect */
+    uint32_t *o = b->order + first;
+    uint32_t lo_i = 0, hi_i = count - 1, mid = count / 2;
+    while (lo_i < hi_i) {
+        const float pivot = s->geom[4 * (size_t)o[(lo_i + hi_i) / 2] + axis];
+        uint32_t i = lo_i, j = hi_i;
+        while (i <= j) {
+            while (s->geom[4 * (size_t)o[i] + axis] < pivot) ++i;
+            while (s->geom[4 * (size_t)o[j] + axis] > pivot) --j;
+            if (i <= j) { const uint32_t t = o[i]; o[i] = o[j]; o[j] = t; ++i; if (j == 0) break; --j; }
+        }
+        if (mid <= j) hi_i = j; else if (mid >= i) lo_i = i; else break;
+    }
+    const int32_t l = bvh_build_rec(s, b, first, mid);
+    const int32_t r = bvh_build_rec(s, b, first + mid, count - mid);
+    n = &b->nodes[me];                                              /* (the array does not move: sized up front) */
+    n->left = l; n->right = r;
+    return me;
+}
+
+OrcBvh *orc_bvh_build(const OrcScene *s)
+{
+    OrcBvh *b = (OrcBvh *)calloc(1, sizeof *b);
+    const uint32_t n = s->n_objects;
+    b->nodes = (OrcBvhNode *)calloc(2 * (size_t)n + 1, sizeof *b->nodes);
+    b->order = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+    b->r_min = INFINITY; b->q_max = 0.0; b->c_max = 0.0;
+    for (uint32_t i = 0; i < n; ++i) {
+        b->order[i] = i;
+        const float *g = s->geom + 4 * (size_t)i;
+        const double c2 = (double)g[0] * g[0] + (double)g[1] * g[1] + (double)g[2] * g[2];
+        const double ext = fabs((double)g[3]);
+        if (sqrt(c2) + ext > b->c_max) b->c_max = sqrt(c2) + ext;
+        if (s->kind[i] == ORC_SPHERE) {
+            if (ext < b->r_min) b->r_min = ext;
+            if (2.0 * c2 + ext * ext > b->q_max) b->q_max = 2.0 * c2 + ext * ext;
+        }
+    }
+    if (!(b->r_min < INFINITY)) b->r_min = 0.0;
+    if (n) bvh_build_rec(s, b, 0, n);
+    return b;
+}
+
+void orc_bvh_free(OrcBvh *b)
+{
+    if (!b) return;
+    free(b->nodes); free(b->order); free(b);
+}
+
+/* (t, i) strictly better than the best so far under trace_ray's rule: smaller t, NaN last, first index on ties */
+static inline int hit_better(float t, int i, float bt, int bi)
+{
+    if (bi < 0) return 1;
+    if (ordered_less(t, bt)) return 1;
+    if (ordered_less(bt, t)) return 0;
+    return i < bi;
+}
+
+int orc_trace_bvh(const OrcScene *s, const OrcBvh *b, const float o[3], const float d[3], float *t_out, uint64_t *tests)
+{
+    int ok = 1;
+    for (int a = 0; a < 3; ++a) if (!(fabsf(d[a]) > 1e-30f && fabsf(d[a]) < 1e30f) || !(fabsf(o[a]) < 1e30f)) ok = 0;
+    if (!ok || b->n_nodes == 0) { if (tests) *tests = s->n_objects; return orc_trace(s, o, d, t_out); }
+    const double oo = (double)o[0] * o[0] + (double)o[1] * o[1] + (double)o[2] * o[2];
+    const double s_ray = 2.0 * oo + b->q_max;
+    const double eps = 1.0 / 131072.0;                                   /* 2^-17 */
+    const double rho = sqrt(b->r_min * b->r_min + eps * s_ray) - b->r_min + eps * sqrt(s_ray);
+    const double pad = eps * (b->c_max + sqrt(oo)) + 1e-30;
+    double inv[3], nod[3];
+    for (int a = 0; a < 3; ++a) { inv[a] = 1.0 / (double)d[a]; nod[a] = -(double)o[a] * inv[a]; }
+    int best = -1; float best_t = 0.0f;
+    uint64_t n_tests = 0;
+    int32_t stack[128]; int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const OrcBvhNode *n = &b->nodes[stack[--sp]];
+        const double grow = pad + (n->has_sphere ? rho : 0.0);
+        double tn = 0.0, tf = INFINITY;
+        for (int a = 0; a < 3; ++a) {
+            double t1 = ((double)n->lo[a] - grow) * inv[a] + nod[a], t2 = ((double)n->hi[a] + grow) * inv[a] + nod[a];
+            if (t1 > t2) { const double t = t1; t1 = t2; t2 = t; }
+            if (t1 > tn) tn = t1;
+            if (t2 < tf) tf = t2;
+        }
+        tn *= (1.0 - 1e-9); tf *= (1.0 + 1e-9);
+        if (tn > tf) continue;
+        if (best >= 0 && best_t == best_t && tn > (double)best_t) continue;      /* strictly beyond the best exact t: ties are visited */
+        if (n->left < 0) {
+            for (uint32_t k = 0; k < n->count; ++k) {
+                const uint32_t i = b->order[n->first + k];
+                float t;
+                ++n_tests;
+                if (!hit_object(s, i, o, d, &t)) continue;
+                if (hit_better(t, (int)i, best_t, best)) { best = (int)i; best_t = t; }
+            }
+        } else if (sp + 2 <= 128) {
+            stack[sp++] = n->left; stack[sp++] = n->right;
+        } else {                                                          /* cannot happen for a median-split tree of < 2^60 objects */
+            if (tests) *tests = s->n_objects;
+            return orc_trace(s, o, d, t_out);
+        }
+    }
+    if (tests) *tests = n_tests;
+    if (best >= 0) *t_out = best_t;
+    return best;
+}
+
 /* cpu.rs:354-394 */
 void orc_closest_hit(const OrcScene *s, int obj, const float o_[3], const float d_[3], float t,
                      float pos[3], float normal[3], uint32_t *front_face)
@@ -300,7 +459,7 @@ void orc_first_hit(const OrcScene *s, int32_t *ids, float *ts, int n_threads)
 }
 
 /* ---- per_pixel: cpu.rs:233-342 ---------------------------------------------------------------- */
-static void per_pixel(const OrcScene *s, uint32_t x, uint32_t y, uint32_t sample, uint64_t seed,
+static void per_pixel(const OrcScene *s, const OrcBvh *bvh, uint32_t x, uint32_t y, uint32_t sample, uint64_t seed,
                       uint32_t max_bounces, OrcPathStep *steps, uint32_t *n_steps, float rgba[4], OrcStats *st)
 {
     const uint32_t pixel = y * s->width + x;
@@ -317,8 +476,10 @@ static void per_pixel(const OrcScene *s, uint32_t x, uint32_t y, uint32_t sample
     for (bounce = 0; bounce < max_bounces; ++bounce) {
         float o3[3], d3[3], t = 0.0f;
         st3(o3, ro); st3(d3, rd);
-        if (st) { st->trace_calls++; st->primitive_tests += s->n_objects; if (bounce < 64) st->alive_at_bounce[bounce]++; }
-        int obj = orc_trace(s, o3, d3, &t);
+        if (st) { st->trace_calls++; if (bounce < 64) st->alive_at_bounce[bounce]++; }
+        uint64_t tests = s->n_objects;
+        int obj = bvh ? orc_trace_bvh(s, bvh, o3, d3, &t, &tests) : orc_trace(s, o3, d3, &t);
+        if (st) st->primitive_tests += tests;
         if (obj >= 0) {
             float pf[3], nf[3]; uint32_t front;
             orc_closest_hit(s, obj, o3, d3, t, pf, nf, &front);
@@ -410,7 +571,7 @@ uint32_t orc_trace_path(const OrcScene *s, uint32_t x, uint32_t y, uint32_t samp
                         uint32_t max_bounces, OrcPathStep *steps, float rgba[4])
 {
     uint32_t n = 0;
-    per_pixel(s, x, y, sample, seed, max_bounces, steps, &n, rgba, NULL);
+    per_pixel(s, NULL, x, y, sample, seed, max_bounces, steps, &n, rgba, NULL);
     return n;
 }
 
@@ -437,7 +598,7 @@ void orc_render(const OrcScene *s, uint64_t seed, uint32_t sample_begin, uint32_
             for (int64_t y = row_begin; y < (int64_t)row_end; ++y)
                 for (int64_t x = 0; x < W; ++x) {
                     float c[4];
-                    per_pixel(s, (uint32_t)x, (uint32_t)y, smp, seed, max_bounces, NULL, NULL, c, stats ? &local : NULL);
+                    per_pixel(s, NULL, (uint32_t)x, (uint32_t)y, smp, seed, max_bounces, NULL, NULL, c, stats ? &local : NULL);
                     float *px = accum + 4 * (y * W + x);
                     px[0] = px[0] + c[0]; px[1] = px[1] + c[1]; px[2] = px[2] + c[2]; px[3] = px[3] + c[3];
                 }
@@ -456,8 +617,42 @@ void orc_render(const OrcScene *s, uint64_t seed, uint32_t sample_begin, uint32_
             for (uint32_t smp = sample_begin; smp < sample_end; ++smp)
                 for (int64_t x = 0; x < W; ++x) {
                     float c[4];
-                    per_pixel(s, (uint32_t)x, (uint32_t)y, smp, seed, max_bounces, NULL, NULL, c, stats ? &local : NULL);
+                    per_pixel(s, NULL, (uint32_t)x, (uint32_t)y, smp, seed, max_bounces, NULL, NULL, c, stats ? &local : NULL);
                     float *px = accum + 4 * (y * W + x);
+                    px[0] = px[0] + c[0]; px[1] = px[1] + c[1]; px[2] = px[2] + c[2]; px[3] = px[3] + c[3];
+                }
+        if (stats) {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+            stats_merge(stats, &local);
+        }
+    }
+}
+
+
+/* the same accumulation for the pixel rectangle [x0, x0 + w) x [y0, y0 + h) only, into a w*h*4 buffer; bvh may be NULL
+ * (linear scan, the reference's algorithm).  Bounded samples of large frames for bench.py's CPU legs. */
+void orc_render_region(const OrcScene *s, const OrcBvh *bvh, uint64_t seed, uint32_t sample_begin, uint32_t sample_end,
+                       uint32_t max_bounces, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, float *accum,
+                       int n_threads, OrcStats *stats)
+{
+    if (x0 + w > s->width) w = s->width > x0 ? s->width - x0 : 0;
+    if (y0 + h > s->height) h = s->height > y0 ? s->height - y0 : 0;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+    {
+        OrcStats local; memset(&local, 0, sizeof local);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+        for (int64_t y = 0; y < (int64_t)h; ++y)
+            for (uint32_t smp = sample_begin; smp < sample_end; ++smp)
+                for (int64_t x = 0; x < (int64_t)w; ++x) {
+                    float c[4];
+                    per_pixel(s, bvh, x0 + (uint32_t)x, y0 + (uint32_t)y, smp, seed, max_bounces, NULL, NULL, c, stats ? &local : NULL);
+                    float *px = accum + 4 * (y * (int64_t)w + x);
                     px[0] = px[0] + c[0]; px[1] = px[1] + c[1]; px[2] = px[2] + c[2]; px[3] = px[3] + c[3];
                 }
         if (stats) {

@@ -132,6 +132,18 @@ void orc_render(const OrcScene *s, uint64_t seed, uint32_t sample_begin, uint32_
                 uint32_t max_bounces, uint32_t row_begin, uint32_t row_end, float *accum,
                 int n_threads, OrcStats *stats);
 
+/* Oracle-side BVH: NOT part of the reference (its trace_ray is the linear scan above).  Returns orc_trace's winner
+ * (checked in tests/test_oracle_bvh.py); exists so that a CPU path can be timed at 100k objects.  tests: exact
+ * primitive tests performed (may be NULL). */
+typedef struct OrcBvh OrcBvh;
+OrcBvh *orc_bvh_build(const OrcScene *s);
+void orc_bvh_free(OrcBvh *b);
+int  orc_trace_bvh(const OrcScene *s, const OrcBvh *b, const float o[3], const float d[3], float *t, uint64_t *tests);
+/* orc_render for the pixel rectangle [x0, x0+w) x [y0, y0+h) into a w*h*4 buffer; bvh NULL = linear scan */
+void orc_render_region(const OrcScene *s, const OrcBvh *bvh, uint64_t seed, uint32_t sample_begin, uint32_t sample_end,
+                       uint32_t max_bounces, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h, float *accum,
+                       int n_threads, OrcStats *stats);
+
 /* print_frame_buffer (cpu.rs:221-230) */
 void orc_resolve(const float *accum, uint64_t n_pixels, uint32_t sample_count, uint8_t *rgba8);
 

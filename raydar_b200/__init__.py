@@ -27,6 +27,9 @@ SPHERE, CUBE = 0, 1
 WORLD_SKY, WORLD_SOLID, WORLD_TRANSPARENT = 0, 1, 2
 ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH, ACCEL_CLUSTER, ACCEL_COOP, ACCEL_FUSED, ACCEL_BVH_COOP = 0, 1, 2, 3, 4, 5, 6
 PARTITION_SAMPLES, PARTITION_STRIPES = 0, 1
+KAT_REFLECT, KAT_REFRACT, KAT_CAN_REFRACT, KAT_WORLD_SAMPLE, KAT_CLOSEST_HIT, KAT_QUANTISE = range(6)
+COMBINE_AUTO, COMBINE_PEER, COMBINE_NCCL = 0, 1, 2
+IPC_HANDLE_BYTES = 128
 MAT_STRIDE = 11
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_IO, ERR_PARSE, ERR_NCCL, ERR_NOMEM = range(8)
 
@@ -41,6 +44,8 @@ EXPORTS = [
     "rdr_kat_trace", "rdr_kat_camera_rays", "rdr_kat_rng", "rdr_scene_load_rscn", "rdr_scene_default",
     "rdr_scene_set_resolution", "rdr_scene_override_resolution", "rdr_scene_flat", "rdr_scene_free",
     "rdr_write_png", "rdr_version",
+    "rdr_set_combine", "rdr_combine_in_use", "rdr_alloc_host_image", "rdr_free_host_image",
+    "rdr_kat_vec", "rdr_ipc_export", "rdr_peer_attach", "rdr_peer_combine", "rdr_peer_detach", "rdr_read_image",
 ]
 
 
@@ -119,6 +124,15 @@ def load_library():
     L.rdr_set_row_stripes.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
     L.rdr_set_partition.argtypes = [vp, C.c_int, C.c_uint32]
     L.rdr_debug_set_cull.argtypes = [vp, C.c_int]
+    L.rdr_set_combine.argtypes = [vp, C.c_int]
+    L.rdr_combine_in_use.argtypes = [vp]
+    L.rdr_alloc_host_image.argtypes = [C.c_size_t, C.POINTER(u8p)]
+    L.rdr_free_host_image.argtypes = [u8p]; L.rdr_free_host_image.restype = None
+    L.rdr_ipc_export.argtypes = [vp, C.c_void_p]
+    L.rdr_peer_attach.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.rdr_peer_combine.argtypes = [vp, C.c_uint32]
+    L.rdr_peer_detach.argtypes = [vp]
+    L.rdr_read_image.argtypes = [vp, u8p]
     L.rdr_render_samples.argtypes = [vp, C.c_uint32]
     L.rdr_reset_frame.argtypes = [vp]
     L.rdr_resolve.argtypes = [vp, C.c_uint32, u8p]
@@ -134,6 +148,7 @@ def load_library():
     L.rdr_kat_hit_cube.argtypes = [vp, C.c_uint32, fp, fp, fp, i32p]
     L.rdr_kat_trace.argtypes = [vp, C.c_uint32, fp, i32p, fp]
     L.rdr_kat_camera_rays.argtypes = [vp, C.c_uint32, u32p, fp]
+    L.rdr_kat_vec.argtypes = [vp, C.c_int, C.c_uint32, fp, fp]
     L.rdr_kat_rng.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
     L.rdr_scene_load_rscn.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.rdr_scene_default.argtypes = [C.POINTER(vp)]
@@ -288,9 +303,12 @@ class Renderer:
         _check(self._L.rdr_render_sample(self._h, img.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(produced)), self._h)
         return img if produced.value else None
 
-    def render_frame(self, scene) -> np.ndarray:
+    def render_frame(self, scene, out=None) -> np.ndarray:
+        """out: optional (H, W, 4) uint8 array to receive the image, e.g. a pinned one from alloc_host_image()."""
         f = _as_flat(scene)
-        img = np.empty((f.height, f.width, 4), np.uint8)
+        img = out if out is not None else np.empty((f.height, f.width, 4), np.uint8)
+        if img.shape != (f.height, f.width, 4) or img.dtype != np.uint8 or not img.flags["C_CONTIGUOUS"]:
+            raise RaydarError(ERR_INVALID, "out must be a C-contiguous (H, W, 4) uint8 array")
         _check(self._L.rdr_render_frame(self._h, C.byref(f), img.ctypes.data_as(C.POINTER(C.c_uint8))), self._h)
         self._shape = (f.height, f.width)
         return img
@@ -318,6 +336,31 @@ class Renderer:
     def set_partition(self, partition: int, stripe_rows: int = 0) -> None:
         """Multi-GPU handle only: PARTITION_SAMPLES (sample ranges) or PARTITION_STRIPES (round-robin row stripes)."""
         _check(self._L.rdr_set_partition(self._h, partition, stripe_rows), self._h)
+
+    def set_combine(self, combine: int) -> None:
+        """Multi-GPU handle only: COMBINE_PEER (fused reduce + resolve over NVLink peer memory), COMBINE_NCCL, COMBINE_AUTO."""
+        _check(self._L.rdr_set_combine(self._h, combine), self._h)
+
+    def combine_in_use(self) -> int: return self._L.rdr_combine_in_use(self._h)
+
+    # one process per GPU: the fused combine over CUDA IPC (include/raydar_cuda.h)
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(self._L.rdr_ipc_export(self._h, buf), self._h)
+        return buf.raw
+
+    def peer_attach(self, rank: int, world: int, handles: bytes) -> None:
+        assert len(handles) == world * IPC_HANDLE_BYTES
+        _check(self._L.rdr_peer_attach(self._h, rank, world, handles), self._h)
+
+    def peer_combine(self, divisor: int) -> None: _check(self._L.rdr_peer_combine(self._h, divisor), self._h)
+    def peer_detach(self) -> None: _check(self._L.rdr_peer_detach(self._h), self._h)
+
+    def read_image(self, out=None) -> np.ndarray:
+        img = out if out is not None else np.empty((*self._shape, 4), np.uint8)
+        _check(self._L.rdr_read_image(self._h, img.ctypes.data_as(C.POINTER(C.c_uint8))), self._h)
+        return img
+
     def debug_set_cull(self, enabled: bool) -> None: _check(self._L.rdr_debug_set_cull(self._h, int(enabled)), self._h)
     def reset_frame(self) -> None: _check(self._L.rdr_reset_frame(self._h), self._h)
     def render_samples(self, n: int) -> None: _check(self._L.rdr_render_samples(self._h, n), self._h)
@@ -325,8 +368,8 @@ class Renderer:
     def launch_count(self) -> int: return self._L.rdr_launch_count(self._h)
     def scene_device_bytes(self) -> int: return self._L.rdr_scene_device_bytes(self._h)
 
-    def resolve(self, divisor: int = 0) -> np.ndarray:
-        img = np.empty((*self._shape, 4), np.uint8)
+    def resolve(self, divisor: int = 0, out=None) -> np.ndarray:
+        img = out if out is not None else np.empty((*self._shape, 4), np.uint8)
         _check(self._L.rdr_resolve(self._h, divisor, img.ctypes.data_as(C.POINTER(C.c_uint8))), self._h)
         return img
 
@@ -375,6 +418,13 @@ class Renderer:
         _check(self._L.rdr_kat_camera_rays(self._h, n, xy.ctypes.data_as(C.POINTER(C.c_uint32)), _fp(rays)), self._h)
         return rays
 
+    def kat_vec(self, op: int, records: np.ndarray) -> np.ndarray:
+        """Device execution of a shading helper (KAT_*): records (n, 12) f32 -> (n, 8) f32."""
+        records = np.ascontiguousarray(records, np.float32).reshape(-1, 12)
+        out = np.zeros((records.shape[0], 8), np.float32)
+        _check(self._L.rdr_kat_vec(self._h, op, records.shape[0], _fp(records), _fp(out)), self._h)
+        return out
+
     def kat_rng(self, seed: int, pixel: int, sample: int, bounce: int, block: int):
         out = (C.c_uint32 * 4)()
         _check(self._L.rdr_kat_rng(self._h, seed, pixel, sample, bounce, block, out), self._h)
@@ -384,6 +434,29 @@ class Renderer:
         if getattr(self, "_h", None):
             self._L.rdr_destroy(self._h)
             self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostImage:
+    """A pinned (H, W, 4) uint8 image from rdr_alloc_host_image: the GPUs write it directly.  Keep the object alive while
+    `.array` is in use; close() (or garbage collection) frees it."""
+
+    def __init__(self, height: int, width: int):
+        self._L = load_library()
+        self._p = C.POINTER(C.c_uint8)()
+        _check(self._L.rdr_alloc_host_image(height * width * 4, C.byref(self._p)))
+        self.array = np.ctypeslib.as_array(self._p, shape=(height, width, 4))
+
+    def close(self) -> None:
+        if getattr(self, "_p", None):
+            self.array = None
+            self._L.rdr_free_host_image(self._p)
+            self._p = None
 
     def __del__(self):
         try:

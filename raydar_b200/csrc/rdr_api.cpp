@@ -9,6 +9,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -42,7 +44,24 @@ struct Timer {
     void end_if_not_ended() { if (!has_duration) end(); }
 };
 
+// pinned host image buffers handed out by rdr_alloc_host_image (process-wide)
+std::mutex g_host_images_mutex;
+std::map<uintptr_t, size_t> g_host_images;
+
 }  // namespace
+
+namespace rdr {
+// does [p, p + bytes) lie inside a buffer from rdr_alloc_host_image?  (device-visible on every GPU: kernels may write it)
+bool is_host_image(const void *p, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(g_host_images_mutex);
+    const uintptr_t a = (uintptr_t)p;
+    auto it = g_host_images.upper_bound(a);
+    if (it == g_host_images.begin()) return false;
+    --it;
+    return a >= it->first && a + bytes <= it->first + it->second;
+}
+}  // namespace rdr
 
 struct RdrRenderer {
     int device = 0;
@@ -52,7 +71,8 @@ struct RdrRenderer {
     uint64_t seed = 0x5EEDull;
     uint32_t sample_offset = 0;
     uint32_t stripe_rows = 0, stripe_index = 0, stripe_count = 1;   // rdr_set_row_stripes (count <= 1: whole image)
-    int accel = RDR_ACCEL_AUTO;
+    int accel = RDR_ACCEL_AUTO;          // requested (rdr_set_accel); takes effect at the next rdr_new_frame
+    int frame_accel = RDR_ACCEL_AUTO;    // latched by rdr_new_frame: the current frame's blob was packed for it
     bool use_cull = true;
 
     bool has_frame = false;
@@ -70,6 +90,14 @@ struct RdrRenderer {
     double device_render_ms = 0.0;
 
     rdr::MultiGpu *multi = nullptr;     // non-null for handles made by rdr_create_multi
+
+    // one process per GPU: the other ranks' accumulators and rank 0's device image, mapped through CUDA IPC (rdr_peer_attach)
+    struct PeerLink {
+        uint32_t rank = 0, world = 0;
+        std::vector<const rdr::f4 *> accum;     // by rank (own entry = d_accum)
+        uchar4 *root_rgba = nullptr;
+        std::vector<void *> opened;             // cudaIpcOpenMemHandle results to close
+    } peer;
     std::string last_error;
 };
 
@@ -93,10 +121,7 @@ int fail(RdrRenderer *r, int status, const char *fmt, ...)
 int pack_scene(RdrRenderer *r, const RdrSceneFlat *sc, std::vector<unsigned char> &blob, FrameParams &P)
 {
     std::string err;
-    // RDR_ACCEL_AUTO: the two-level scan while the cluster masks fit (<= 128 clusters), the hierarchy above
-    const bool use_bvh = r->accel == RDR_ACCEL_BVH || r->accel == RDR_ACCEL_BVH_COOP ||
-                         (r->accel == RDR_ACCEL_AUTO && sc && sc->n_objects > RDR_AUTO_BVH_THRESHOLD);
-    const int st = rdr::pack_scene_blob(sc, use_bvh, blob, P, err);
+    const int st = rdr::pack_scene_for_accel(sc, r->accel, RDR_AUTO_BVH_THRESHOLD, blob, P, err);
     return st == RDR_OK ? RDR_OK : fail(r, st, "%s", err.c_str());
 }
 
@@ -104,14 +129,15 @@ int pack_scene(RdrRenderer *r, const RdrSceneFlat *sc, std::vector<unsigned char
 // 3 warp-cooperative cluster scan, 4 fused scan (AUTO; falls back to 3 above 32 top-level entries)
 int scan_variant(const RdrRenderer *r)
 {
+    // the accel latched at rdr_new_frame decides (the blob was packed for it); a layout can only be searched by the
+    // variants it holds the sections for: a hierarchy by 5 / 6, scan lists by 0 - 4 (rdr_kernels.cu: mode_of clamps too)
+    const int accel = r->frame_accel;
+    if (r->has_frame_layout_bvh) return accel == RDR_ACCEL_BVH ? 6 : 5;   // per-lane / warp-cooperative traversal
     if (!r->use_cull) return 1;
-    if (r->accel == RDR_ACCEL_BRUTE) return 0;
-    if (r->accel == RDR_ACCEL_CLUSTER) return 2;
-    if (r->accel == RDR_ACCEL_COOP) return 3;
-    if (r->accel == RDR_ACCEL_BVH) return 6;                // hierarchy, per-lane traversal
-    if (r->accel == RDR_ACCEL_BVH_COOP) return 5;           // hierarchy, warp-cooperative traversal
-    if (r->accel == RDR_ACCEL_AUTO && r->has_frame_layout_bvh) return 5;
-    return 4;                                               // AUTO / FUSED: fused scan (<= 32 top entries), else cooperative
+    if (accel == RDR_ACCEL_BRUTE) return 0;
+    if (accel == RDR_ACCEL_CLUSTER) return 2;
+    if (accel == RDR_ACCEL_COOP) return 3;
+    return 4;                                               // AUTO / FUSED (and a hierarchy request that fell back to the lists): fused scan, else cooperative
 }
 
 int ensure_device(RdrRenderer *r) { RDR_CUDA(r, cudaSetDevice(r->device)); return RDR_OK; }
@@ -225,6 +251,7 @@ void rdr_destroy(RdrRenderer *r)
 {
     if (!r) return;
     if (r->multi) { rdr::multi_destroy(r->multi); r->multi = nullptr; }
+    rdr_peer_detach(r);
     cudaSetDevice(r->device);
     if (r->d_blob) cudaFree(r->d_blob);
     if (r->d_accum) cudaFree(r->d_accum);
@@ -281,6 +308,7 @@ int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene)
     // frame_buffer()/blank_frame_buffer(), cpu.rs:400-423: reallocate on a resolution change, zero-fill
     const size_t n_pixels = (size_t)scene->width * scene->height;
     if (n_pixels > r->pixel_capacity) {
+        if (r->peer.world) { r->has_frame = false; return fail(r, RDR_ERR_INVALID, "resolution grew while peers are attached: rdr_peer_detach on every rank first"); }
         if (r->d_accum) cudaFree(r->d_accum);
         if (r->d_rgba) cudaFree(r->d_rgba);
         r->d_accum = nullptr; r->d_rgba = nullptr; r->pixel_capacity = 0;
@@ -301,6 +329,7 @@ int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene)
     r->sample_count = 0;
     r->has_frame = true;
     r->has_frame_layout_bvh = P.lay.mode == 1u;
+    r->frame_accel = r->accel;
     return RDR_OK;
 }
 
@@ -477,7 +506,127 @@ int rdr_set_accel(RdrRenderer *r, int accel)
 {
     if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
     if (accel < RDR_ACCEL_AUTO || accel > RDR_ACCEL_BVH_COOP) return fail(r, RDR_ERR_INVALID, "unknown accel %d", accel);
-    r->accel = accel;
+    r->accel = accel;                    // takes effect at the next rdr_new_frame (the blob layout depends on it)
+    if (r->multi) rdr::multi_set_accel(r->multi, accel);
+    return RDR_OK;
+}
+
+int rdr_set_combine(RdrRenderer *r, int combine)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    if (combine != RDR_COMBINE_AUTO && combine != RDR_COMBINE_PEER && combine != RDR_COMBINE_NCCL) return fail(r, RDR_ERR_INVALID, "unknown combine %d", combine);
+    if (!r->multi) return fail(r, RDR_ERR_INVALID, "rdr_set_combine needs a handle made by rdr_create_multi");
+    return rdr::multi_set_combine(r, r->multi, combine);
+}
+
+int rdr_combine_in_use(const RdrRenderer *r) { return (r && r->multi) ? rdr::multi_combine_in_use(r->multi) : RDR_COMBINE_AUTO; }
+
+int rdr_alloc_host_image(size_t bytes, uint8_t **out)
+{
+    if (!out || bytes == 0u) return fail(nullptr, RDR_ERR_INVALID, "rdr_alloc_host_image: bad argument");
+    *out = nullptr;
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) return fail(nullptr, e == cudaErrorMemoryAllocation ? RDR_ERR_NOMEM : RDR_ERR_CUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    { std::lock_guard<std::mutex> lock(g_host_images_mutex); g_host_images[(uintptr_t)p] = bytes; }
+    *out = (uint8_t *)p;
+    return RDR_OK;
+}
+
+void rdr_free_host_image(uint8_t *image)
+{
+    if (!image) return;
+    bool known;
+    { std::lock_guard<std::mutex> lock(g_host_images_mutex); known = g_host_images.erase((uintptr_t)image) != 0u; }
+    if (known) cudaFreeHost(image);
+}
+
+// ---- one process per GPU: fused combine over CUDA IPC ------------------------------------------------------------
+int rdr_ipc_export(RdrRenderer *r, void *handle)
+{
+    int st = check_frame(r);
+    if (st) return st;
+    if (r->multi) return fail(r, RDR_ERR_INVALID, "rdr_ipc_export needs a single-GPU handle");
+    if (!handle) return fail(r, RDR_ERR_INVALID, "handle is NULL");
+    static_assert(2 * sizeof(cudaIpcMemHandle_t) == RDR_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h[2];
+    RDR_CUDA(r, cudaIpcGetMemHandle(&h[0], r->d_accum));
+    RDR_CUDA(r, cudaIpcGetMemHandle(&h[1], r->d_rgba));
+    memcpy(handle, h, sizeof h);
+    return RDR_OK;
+}
+
+int rdr_peer_detach(RdrRenderer *r)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    if (r->peer.world == 0u) return RDR_OK;
+    cudaSetDevice(r->device);
+    cudaStreamSynchronize(r->stream);
+    for (void *p : r->peer.opened) cudaIpcCloseMemHandle(p);
+    r->peer = RdrRenderer::PeerLink();
+    return RDR_OK;
+}
+
+int rdr_peer_attach(RdrRenderer *r, uint32_t rank, uint32_t world, const void *handles)
+{
+    int st = check_frame(r);
+    if (st) return st;
+    if (r->multi) return fail(r, RDR_ERR_INVALID, "rdr_peer_attach needs a single-GPU handle");
+    if (!handles || world == 0u || rank >= world || world > rdr::RDR_MAX_PEERS) return fail(r, RDR_ERR_INVALID, "bad rank / world (%u / %u, at most %u ranks)", rank, world, rdr::RDR_MAX_PEERS);
+    rdr_peer_detach(r);
+    const unsigned char *hb = (const unsigned char *)handles;
+    r->peer.accum.assign(world, nullptr);
+    for (uint32_t g = 0; g < world; ++g) {
+        if (g == rank) { r->peer.accum[g] = r->d_accum; continue; }
+        cudaIpcMemHandle_t h; memcpy(&h, hb + (size_t)g * RDR_IPC_HANDLE_BYTES, sizeof h);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { r->peer.world = world; rdr_peer_detach(r); return fail(r, RDR_ERR_CUDA, "cudaIpcOpenMemHandle(accumulator of rank %u): %s", g, cudaGetErrorString(e)); }
+        r->peer.opened.push_back(p);
+        r->peer.accum[g] = (const rdr::f4 *)p;
+    }
+    if (rank == 0u) r->peer.root_rgba = r->d_rgba;
+    else {
+        cudaIpcMemHandle_t h; memcpy(&h, hb + sizeof(cudaIpcMemHandle_t), sizeof h);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { r->peer.world = world; rdr_peer_detach(r); return fail(r, RDR_ERR_CUDA, "cudaIpcOpenMemHandle(image of rank 0): %s", cudaGetErrorString(e)); }
+        r->peer.opened.push_back(p);
+        r->peer.root_rgba = (uchar4 *)p;
+    }
+    r->peer.rank = rank; r->peer.world = world;
+    return RDR_OK;
+}
+
+int rdr_peer_combine(RdrRenderer *r, uint32_t divisor)
+{
+    int st = check_frame(r);
+    if (st) return st;
+    if (r->peer.world == 0u) return fail(r, RDR_ERR_INVALID, "no peers attached: call rdr_peer_attach first");
+    const uint32_t n_pixels = r->params.cam.width * r->params.cam.height;
+    rdr::PeerCombine C{};
+    for (uint32_t g = 0; g < r->peer.world; ++g) C.src[g] = r->peer.accum[g];
+    C.n_src = r->peer.world;
+    C.first = (uint32_t)((uint64_t)n_pixels * r->peer.rank / r->peer.world);
+    C.count = (uint32_t)((uint64_t)n_pixels * (r->peer.rank + 1u) / r->peer.world) - C.first;
+    C.width = r->params.cam.width; C.stripe_count = 1u;
+    C.divisor = (float)divisor;
+    C.rgba = r->peer.root_rgba;
+    RDR_CUDA(r, rdr::launch_peer_combine(C, r->stream));
+    r->launches += C.count ? 1u : 0u;
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RDR_OK;
+}
+
+int rdr_read_image(RdrRenderer *r, uint8_t *rgba8)
+{
+    int st = check_frame(r);
+    if (st) return st;
+    if (r->multi) return fail(r, RDR_ERR_INVALID, "rdr_read_image needs a single-GPU handle (a multi-GPU handle returns the image from rdr_resolve)");
+    if (!rgba8) return fail(r, RDR_ERR_INVALID, "output image is NULL");
+    const size_t n_pixels = (size_t)r->params.cam.width * r->params.cam.height;
+    RDR_CUDA(r, cudaMemcpyAsync(rgba8, r->d_rgba, n_pixels * 4u, cudaMemcpyDeviceToHost, r->stream));
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
     return RDR_OK;
 }
 
@@ -573,6 +722,22 @@ int rdr_kat_trace(RdrRenderer *r, uint32_t n, const float *rays, int32_t *ids, f
     return RDR_OK;
 }
 
+int rdr_kat_vec(RdrRenderer *r, int op, uint32_t n, const float *in, float *out)
+{
+    if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
+    if (op < RDR_KAT_REFLECT || op > RDR_KAT_QUANTISE || !in || !out) return fail(r, RDR_ERR_INVALID, "bad KAT arguments");
+    int st = ensure_device(r);
+    if (st) return st;
+    DevBuf<float> d_in, d_out;
+    RDR_CUDA(r, d_in.alloc(12 * (size_t)n)); RDR_CUDA(r, d_out.alloc(8 * (size_t)n));
+    RDR_CUDA(r, cudaMemcpyAsync(d_in.p, in, 12 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, r->stream));
+    RDR_CUDA(r, rdr::launch_kat_vec(op, n, d_in.p, d_out.p, r->stream));
+    r->launches += 1;
+    RDR_CUDA(r, cudaMemcpyAsync(out, d_out.p, 8 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    return RDR_OK;
+}
+
 int rdr_kat_camera_rays(RdrRenderer *r, uint32_t n, const uint32_t *xy, float *rays)
 {
     int st = check_frame(r);
@@ -616,4 +781,9 @@ int api_render_launch(RdrRenderer *r, uint32_t n) { int st = check_frame(r); ret
 int api_render_finish(RdrRenderer *r, uint32_t n) { return render_finish(r, n); }
 int api_resolve_from(RdrRenderer *r, const rdr::f4 *src, uint32_t divisor, uint8_t *rgba8) { int st = check_frame(r); return st ? st : resolve_from(r, src, divisor, rgba8); }
 void api_attach_multi(RdrRenderer *r, MultiGpu *m) { r->multi = m; }
+cudaEvent_t api_render_done_event(RdrRenderer *r) { return r->ev_stop; }
+uchar4 *api_rgba(RdrRenderer *r) { return r->d_rgba; }
+uint32_t api_width(RdrRenderer *r) { return r->params.cam.width; }
+uint32_t api_height(RdrRenderer *r) { return r->params.cam.height; }
+void api_count_launch(RdrRenderer *r) { r->launches += 1; }
 }  // namespace rdr

@@ -110,6 +110,40 @@ __global__ void __launch_bounds__(256) resolve_kernel(const f4 *__restrict__ acc
     out[i] = o;
 }
 
+// ---- multi-GPU combine: accumulator sum over NVLink peer memory fused with print_frame_buffer -----------------
+// Each GPU owns 1/G of the pixels.  A thread reads its pixel from EVERY accumulator -- its own and the peers', mapped
+// through NVLink peer access (one process) or CUDA IPC (one process per GPU) -- with G independent 16-byte loads in
+// flight, adds them in source order (device 0 first: a fixed order, so the result is deterministic, unlike a ring or
+// tree reduce), quantises (cpu.rs:221-230) and stores the pixel's RGBA8 word where the image is wanted: pinned host
+// memory (every GPU writes its slice over its own PCIe link) or a peer's device image.  No rooted reduce: nothing lands
+// on one GPU, 4x fewer bytes leave the GPUs than with an f32 reduce.  sum != NULL writes the f32 sum instead (parity).
+// Row-stripe partition (stripe_count > 1): the owned pixels are the GPU's own stripes and n_src == 1 -- no peer traffic.
+template <int N>
+__global__ void __launch_bounds__(256) peer_combine_kernel(const __grid_constant__ PeerCombine C)
+{
+    const uint32_t step = gridDim.x * blockDim.x;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < C.count; k += step) {
+        const uint32_t pixel = C.stripe_count > 1u ? stripe_pixel(C.width, C.stripe_rows, C.stripe_index, C.stripe_count, k) : C.first + k;
+        float4 v[N];
+#pragma unroll
+        for (int g = 0; g < N; ++g) v[g] = __ldcg(reinterpret_cast<const float4 *>(C.src[g] + pixel));
+        float4 a = v[0];
+#pragma unroll
+        for (int g = 1; g < N; ++g) { a.x = fadd(a.x, v[g].x); a.y = fadd(a.y, v[g].y); a.z = fadd(a.z, v[g].z); a.w = fadd(a.w, v[g].w); }
+        for (uint32_t g = N; g < C.n_src; ++g) {            // more than N sources (N == 8 only): the rest one by one
+            const float4 b = __ldcg(reinterpret_cast<const float4 *>(C.src[g] + pixel));
+            a.x = fadd(a.x, b.x); a.y = fadd(a.y, b.y); a.z = fadd(a.z, b.z); a.w = fadd(a.w, b.w);
+        }
+        if (C.sum) { f4 o; o.x = a.x; o.y = a.y; o.z = a.z; o.w = a.w; C.sum[pixel] = o; }
+        if (C.rgba) {
+            uchar4 o;
+            o.x = (unsigned char)quantise(a.x, C.divisor); o.y = (unsigned char)quantise(a.y, C.divisor);
+            o.z = (unsigned char)quantise(a.z, C.divisor); o.w = (unsigned char)quantise(a.w, C.divisor);
+            C.rgba[pixel] = o;
+        }
+    }
+}
+
 // ---- debug / parity kernels ---------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(RDR_BLOCK, 2) first_hit_kernel(const __grid_constant__ FrameParams P,
@@ -186,6 +220,30 @@ __global__ void kat_hit_cube_kernel(uint32_t n, const float *__restrict__ rays, 
     t_out[i] = h ? t : 0.0f;
 }
 
+// per-function KATs of the shading helpers: n records of 12 floats in, 8 floats out (include/raydar_cuda.h: RDR_KAT_*)
+__global__ void kat_vec_kernel(int op, uint32_t n, const float *__restrict__ in, float *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *a = in + 12u * i;
+    float *o = out + 8u * i;
+    for (int k = 0; k < 8; ++k) o[k] = 0.0f;
+    const v3 v = mk3(a[0], a[1], a[2]), w = mk3(a[3], a[4], a[5]);
+    if (op == RDR_KAT_REFLECT) { const v3 r = reflect3(v, w); o[0] = r.x; o[1] = r.y; o[2] = r.z; }
+    else if (op == RDR_KAT_REFRACT) { const v3 r = refract3(v, w, a[6]); o[0] = r.x; o[1] = r.y; o[2] = r.z; }
+    else if (op == RDR_KAT_CAN_REFRACT) { o[0] = can_refract3(v, w, a[6]) ? 1.0f : 0.0f; }
+    else if (op == RDR_KAT_WORLD_SAMPLE) {
+        World wd; wd.kind = a[3] != 0.0f ? 1u : 0u;
+        for (int k = 0; k < 3; ++k) { wd.a[k] = a[4 + k]; wd.b[k] = a[7 + k]; }
+        const v3 r = world_sample(wd, v); o[0] = r.x; o[1] = r.y; o[2] = r.z;
+    }
+    else if (op == RDR_KAT_CLOSEST_HIT) {
+        const Surface sf = closest_hit(v, w, a[6], a[7] != 0.0f, mk3(a[8], a[9], a[10]), a[11]);
+        o[0] = sf.p.x; o[1] = sf.p.y; o[2] = sf.p.z; o[3] = sf.n.x; o[4] = sf.n.y; o[5] = sf.n.z; o[6] = sf.front ? 1.0f : 0.0f;
+    }
+    else if (op == RDR_KAT_QUANTISE) { o[0] = (float)quantise(a[0], a[1]); }
+}
+
 __global__ void kat_camera_rays_kernel(const __grid_constant__ FrameParams P, uint32_t n, const uint32_t *__restrict__ xy,
                                        float *__restrict__ rays)
 {
@@ -243,6 +301,7 @@ size_t scene_smem_bytes(const SceneLayout &L, bool staged, uint32_t block)
 static inline int mode_of(const FrameParams &P, int variant)
 {
     if (P.lay.mode == 1u) return (variant == 5 && P.lay.bvh2_ok) ? 7 : 2;      // hierarchy: warp-cooperative or per-lane traversal
+    if (variant > 4) variant = 4;                                   // scan lists hold no hierarchy: 5 / 6 cannot run on them
     if (variant == 4 && !(P.lay.fused_ok && P.staged)) variant = 3;
     if (variant == 4) return P.lay.fused_cap == 8u ? 5 : 6;           // fused scan: 8-member clusters resolved at compile time
     return variant >= 2 ? variant + 1 : variant;
@@ -393,6 +452,25 @@ cudaError_t launch_resolve(const f4 *accum, uchar4 *out, uint32_t n_pixels, floa
     return cudaGetLastError();
 }
 
+cudaError_t launch_peer_combine(const PeerCombine &C, cudaStream_t stream)
+{
+    if (C.count == 0u || C.n_src == 0u) return cudaSuccess;
+    if (C.n_src > RDR_MAX_PEERS) return cudaErrorInvalidValue;
+    uint32_t grid = (C.count + 255u) / 256u;
+    if (grid > 148u * 8u) grid = 148u * 8u;
+    switch (C.n_src) {
+    case 1: peer_combine_kernel<1><<<grid, 256, 0, stream>>>(C); break;
+    case 2: peer_combine_kernel<2><<<grid, 256, 0, stream>>>(C); break;
+    case 3: peer_combine_kernel<3><<<grid, 256, 0, stream>>>(C); break;
+    case 4: peer_combine_kernel<4><<<grid, 256, 0, stream>>>(C); break;
+    case 5: peer_combine_kernel<5><<<grid, 256, 0, stream>>>(C); break;
+    case 6: peer_combine_kernel<6><<<grid, 256, 0, stream>>>(C); break;
+    case 7: peer_combine_kernel<7><<<grid, 256, 0, stream>>>(C); break;
+    default: peer_combine_kernel<8><<<grid, 256, 0, stream>>>(C); break;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_first_hit(const FrameParams &P, int variant, int32_t *ids, float *ts, cudaStream_t stream)
 {
     const uint32_t n_pixels = P.cam.width * P.cam.height;
@@ -435,6 +513,13 @@ cudaError_t launch_kat_hit(bool sphere, uint32_t n, const float *rays, const flo
     if (n == 0u) return cudaSuccess;
     if (sphere) kat_hit_sphere_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(n, rays, prims, t, hit);
     else kat_hit_cube_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(n, rays, prims, t, hit);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kat_vec(int op, uint32_t n, const float *in, float *out, cudaStream_t stream)
+{
+    if (n == 0u) return cudaSuccess;
+    kat_vec_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(op, n, in, out);
     return cudaGetLastError();
 }
 

@@ -1,5 +1,6 @@
 // rdr_multi.h -- single-process multi-GPU renderer: one sub-renderer per device, sample-range
-// sharding (or round-robin row stripes, rdr_set_partition), one ncclReduce(sum, f32) of the per-GPU accumulators onto devices[0].
+// sharding (or round-robin row stripes, rdr_set_partition); the per-GPU accumulators are combined by a fused reduce + resolve
+// kernel over NVLink peer memory, or by one ncclReduce(sum, f32) onto devices[0] (rdr_set_combine).
 // The reference has no multi-device path; this is the B200 extension behind rdr_create_multi.
 #pragma once
 
@@ -29,6 +30,9 @@ int multi_profiler(const MultiGpu *m, RdrProfiler *out);
 void multi_set_config(MultiGpu *m, const RdrConfig &config);
 void multi_set_seed(MultiGpu *m, uint64_t seed);
 void multi_set_partition(MultiGpu *m, int partition, uint32_t stripe_rows);
+void multi_set_accel(MultiGpu *m, int accel);
+int multi_set_combine(RdrRenderer *owner, MultiGpu *m, int combine);
+int multi_combine_in_use(const MultiGpu *m);               // RDR_COMBINE_PEER / RDR_COMBINE_NCCL (AUTO: one device)
 
 // hooks implemented in rdr_api.cpp
 int api_fail(RdrRenderer *r, int status, const char *msg);
@@ -42,5 +46,11 @@ int api_render_launch(RdrRenderer *r, uint32_t n);
 int api_render_finish(RdrRenderer *r, uint32_t n);
 int api_resolve_from(RdrRenderer *r, const f4 *src, uint32_t divisor, uint8_t *rgba8);
 void api_attach_multi(RdrRenderer *r, MultiGpu *m);
+cudaEvent_t api_render_done_event(RdrRenderer *r);        // recorded behind the last render launch on the child's stream
+uchar4 *api_rgba(RdrRenderer *r);
+uint32_t api_width(RdrRenderer *r);
+uint32_t api_height(RdrRenderer *r);
+void api_count_launch(RdrRenderer *r);
+bool is_host_image(const void *p, size_t bytes);          // inside a buffer from rdr_alloc_host_image
 
 }  // namespace rdr

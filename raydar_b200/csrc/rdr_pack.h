@@ -326,4 +326,20 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
     return RDR_OK;
 }
 
+// The layout for a requested search (RDR_ACCEL_*): the hierarchy for BVH / BVH_COOP and, in AUTO, above auto_threshold
+// objects; the scan lists otherwise.  AUTO also takes the hierarchy when the scan's clustering does not fit its masks
+// (more than 128 top-level entries: many primitives far larger than the median each stay alone) instead of failing.
+inline int pack_scene_for_accel(const RdrSceneFlat *sc, int accel, uint32_t auto_threshold, std::vector<unsigned char> &blob,
+                                FrameParams &P, std::string &err)
+{
+    const bool use_bvh = accel == RDR_ACCEL_BVH || accel == RDR_ACCEL_BVH_COOP ||
+                         (accel == RDR_ACCEL_AUTO && sc && sc->n_objects > auto_threshold);
+    int st = pack_scene_blob(sc, use_bvh, blob, P, err);
+    if (st == RDR_ERR_UNSUPPORTED && !use_bvh && accel == RDR_ACCEL_AUTO && sc && sc->world_kind != RDR_WORLD_TRANSPARENT) {
+        err.clear(); blob.clear(); P = FrameParams{};
+        st = pack_scene_blob(sc, true, blob, P, err);
+    }
+    return st;
+}
+
 }  // namespace rdr

@@ -323,6 +323,16 @@ int hs_scene_consts(const RdrSceneFlat *sc, float *q_max, float *origin_bound, f
     return RDR_OK;
 }
 
+// which layout a search request gets (pack_scene_for_accel, the decision rdr_new_frame takes): *mode 0 = scan lists, 1 = hierarchy
+int hs_pack_mode(const RdrSceneFlat *sc, int accel, uint32_t *mode, uint32_t *n_top)
+{
+    std::vector<unsigned char> blob; FrameParams P{}; std::string err;
+    const int st = pack_scene_for_accel(sc, accel, 1024u, blob, P, err);
+    if (st != RDR_OK) return st;
+    *mode = P.lay.mode; *n_top = P.lay.n_top;
+    return RDR_OK;
+}
+
 // hierarchy shape of a scene (BVH mode): nodes, depth is checked by the builder
 int hs_bvh_info(const RdrSceneFlat *sc, uint32_t *n_nodes, uint32_t *mode, uint32_t *blob_bytes)
 {

@@ -71,6 +71,7 @@ def lib():
         L.hs_rng_block.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
         L.hs_scene_consts.argtypes = [sfp, fp, fp, fp]
         L.hs_bvh_info.argtypes = [sfp, u32p, u32p, u32p]
+        L.hs_pack_mode.argtypes = [sfp, C.c_int, u32p, u32p]
         L.hs_bvh2_info.argtypes = [sfp, u32p, u32p, u32p]
         L.hs_bvh2_warp_sim.argtypes = [sfp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
         L.hs_bvh2_perray_sim.argtypes = [sfp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
@@ -166,9 +167,10 @@ def trace_coop_emu(scene, rays):
     return ids, ts
 
 
-def fused_clusters(scene):
-    """Top-level entry of the fused clustering that holds each original object."""
-    L = lib()
+def fused_clusters(scene, variant=None):
+    """Top-level entry of the fused clustering that holds each original object.  variant = (name, defines): a hostsim
+    build with extra -D switches (e.g. RDR_CLUSTER_REFINE=0: the clustering before the surface-area refinement)."""
+    L = C.CDLL(build(*variant)) if variant else lib()
     L.hs_fused_clusters.argtypes = [C.POINTER(rb.RdrSceneFlat), C.POINTER(C.c_int32)]
     f = rb._as_flat(scene)
     cl = np.zeros(f.n_objects, np.int32)
@@ -293,3 +295,11 @@ def scene_consts(scene):
     q = C.c_float(); ob = C.c_float(); pad = C.c_float()
     _ok(lib().hs_scene_consts(C.byref(f), C.byref(q), C.byref(ob), C.byref(pad)))
     return q.value, ob.value, pad.value
+
+
+def pack_mode(scene, accel):
+    """(status, layout mode, scan top entries) of rdr_new_frame's packing decision for `accel` (host only)."""
+    f = rb._as_flat(scene)
+    mode = C.c_uint32(0); n_top = C.c_uint32(0)
+    st = lib().hs_pack_mode(C.byref(f), accel, C.byref(mode), C.byref(n_top))
+    return st, int(mode.value), int(n_top.value)

@@ -110,16 +110,14 @@ def test_rscn_round_trip(rb, orc, tmp_path):
     assert np.array_equal(u32(sc.matrices()[2]), u32(scene.inv_view)) and np.array_equal(u32(sc.matrices()[3]), u32(scene.inv_proj))
 
 
-def test_cluster_refinement_keeps_shape_and_enters_fewer_boxes(hs, orc, benchmark_scene, monkeypatch):
+def test_cluster_refinement_keeps_shape_and_enters_fewer_boxes(hs, orc, benchmark_scene):
     """refine_clusters (rdr_bvh.h): a surface-area local search on the fused clustering.  Every object stays in exactly
     one cluster, the number of clusters and the <= 8 bound are kept, no cluster falls below two members -- and rays of
     real paths enter clearly fewer cluster boxes (each entered box is a member-stage task of the fused scan)."""
     import copy
     other = copy.copy(benchmark_scene)                                   # a different geometry in between: no stale cache
     other.geom = benchmark_scene.geom.copy(); other.geom[1:, 0] += 0.25
-    monkeypatch.setenv("RDR_CLUSTER_REFINE", "0")
-    plain = hs.fused_clusters(benchmark_scene)
-    monkeypatch.setenv("RDR_CLUSTER_REFINE", "1")
+    plain = hs.fused_clusters(benchmark_scene, variant=("norefine", ("RDR_CLUSTER_REFINE=0",)))   # compile-time switch
     hs.fused_clusters(other)
     refined = hs.fused_clusters(benchmark_scene)
     assert np.array_equal(hs.fused_clusters(benchmark_scene), refined)  # deterministic, and the cached copy is the same

@@ -7,6 +7,8 @@ import copy
 import numpy as np
 import pytest
 
+import synth_scenes as ss
+
 
 def u32(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
@@ -144,3 +146,19 @@ def test_degenerate_rays_take_exact_path(hs, orc, benchmark_scene):
         assert idx == ids[i]
         if idx >= 0:
             assert u32(np.float32(t)) == u32(ts[i])
+
+
+def test_auto_packs_a_hierarchy_when_the_scan_clustering_does_not_fit(hs, rb):
+    """AUTO must not fail for <= 1024 objects whose clustering needs more than 128 top-level entries."""
+    import copy
+    base = ss.config4(1023, 64, 36)                          # 1024 objects incl. the ground cube: at the AUTO threshold
+    st, mode, n_top = hs.pack_mode(base, rb.ACCEL_AUTO)
+    assert st == rb.OK
+    big = copy.copy(base); big.geom = base.geom.copy(); big.geom[1:300, 3] *= 40.0     # 299 large primitives stay alone
+    st, mode, _ = hs.pack_mode(big, rb.ACCEL_AUTO)
+    assert (st, mode) == (rb.OK, 1)
+    st, _, _ = hs.pack_mode(big, rb.ACCEL_FUSED)             # an explicit scan request still reports the limit
+    assert st == rb.ERR_UNSUPPORTED
+    small = ss.config4(200, 64, 36)
+    assert hs.pack_mode(small, rb.ACCEL_AUTO)[:2] == (rb.OK, 0)
+    assert hs.pack_mode(small, rb.ACCEL_BVH_COOP)[:2] == (rb.OK, 1)

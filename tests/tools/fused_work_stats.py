@@ -34,12 +34,11 @@ for _ in range(150):
         warps.append([paths[i][it % len(paths[i])] for i in range(32)])
 rays = np.array(warps, np.float32).reshape(-1, 6)
 
-L = C.CDLL(hs.build("stats", ("RDR_EMU_STATS=1",)))
-L.hs_trace_fused.argtypes = [C.POINTER(rb.RdrSceneFlat), C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
 f = rb._as_flat(scene)
 out = (C.c_ulonglong * 7)()
-for env in ("0", "1"):
-    os.environ["RDR_CLUSTER_REFINE"] = env
+for env in ("0", "1"):                     # compile-time switch: one hostsim build per setting
+    L = C.CDLL(hs.build(f"stats_refine{env}", ("RDR_EMU_STATS=1", f"RDR_CLUSTER_REFINE={env}")))
+    L.hs_trace_fused.argtypes = [C.POINTER(rb.RdrSceneFlat), C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
     L.hs_fused_emu_stats(out, 1)
     ids = np.zeros(len(rays), np.int32); ts = np.zeros(len(rays), np.float32)
     L.hs_trace_fused(C.byref(f), len(rays), rays.ctypes.data_as(C.POINTER(C.c_float)), ids.ctypes.data_as(C.POINTER(C.c_int32)),
