@@ -24,10 +24,22 @@ print("kernel:", rows[2][hdr.index("Kernel Name")] if "Kernel Name" in hdr else 
 if len(sys.argv) > 3 and sys.argv[2] == "--traffic-json":
     import json
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    val = lambda k: float(rows[2][hdr.index(k)].replace(",", "")) if k in hdr else None
     tot = sum(float(rows[2][hdr.index(k)]) * scale[rows[1][hdr.index(k)]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     val = lambda k: float(rows[2][hdr.index(k)]) if k in hdr else None
+    # executed FP32 flops (thread-level FADD + FMUL + 2 x FFMA, predicated-on; an FFMA2 counts as two thread FFMAs) per sample of
+    # the capture (argv[4] = samples in the profiled launch) against the algorithmic flops per sample (argv[5])
+    n_samples = float(sys.argv[4]) if len(sys.argv) > 4 else None
+    f_alg = float(sys.argv[5]) if len(sys.argv) > 5 else None
+    fl = None
+    if all(("smsp__sass_thread_inst_executed_op_%s_pred_on.sum" % k) in hdr for k in ("fadd", "fmul", "ffma")):
+        fl = val("smsp__sass_thread_inst_executed_op_fadd_pred_on.sum") + val("smsp__sass_thread_inst_executed_op_fmul_pred_on.sum") + \
+             2.0 * val("smsp__sass_thread_inst_executed_op_ffma_pred_on.sum")
     with open(sys.argv[3], "w") as f:
         json.dump({"dram_bytes_per_launch": tot, "kernel": rows[2][hdr.index("Kernel Name")],
+                   "executed_fp32_flops_per_launch": fl,
+                   "executed_fp32_flops_per_sample": fl / n_samples if fl and n_samples else None,
+                   "executed_over_algorithmic_flops": fl / n_samples / f_alg if fl and n_samples and f_alg else None,
                    "fp32_pipe_active_pct": val("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
                    "fma_pipe_inst_pct": val("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
                    "alu_pipe_inst_pct": val("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),

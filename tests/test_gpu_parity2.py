@@ -23,6 +23,13 @@ def renderer(rb):
     r.close()
 
 
+def same_f32(a, b):
+    """bitwise equal, except that any NaN equals any NaN: x86 and the GPU produce different quiet-NaN payloads for 0/0,
+    and Rust gives no guarantee about them either"""
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
 def _f3(v):
     return (C.c_float * 3)(*[float(x) for x in v])
 
@@ -58,9 +65,9 @@ def test_reflect_refract_can_refract_kats(rb, renderer, orc):
     n_tir = 0
     for k in range(n):
         L.orc_reflect(_f3(v[k]), _f3(nn[k]), out)
-        assert np.array_equal(u32(np.array(out, np.float32)), u32(got_refl[k, :3])), k
+        assert same_f32(np.array(out, np.float32), got_refl[k, :3]), k
         L.orc_refract(_f3(v[k]), _f3(nn[k]), float(ratio[k]), out)
-        assert np.array_equal(u32(np.array(out, np.float32)), u32(got_refr[k, :3])), k
+        assert same_f32(np.array(out, np.float32), got_refr[k, :3]), k
         can = L.orc_can_refract(_f3(v[k]), _f3(nn[k]), float(ratio[k]))
         assert can == int(got_can[k, 0]), k
         n_tir += 0 if can else 1
@@ -84,7 +91,7 @@ def test_world_sample_and_closest_hit_kats(rb, renderer, orc, default_scene):
         s = scene.c_struct(); out = (C.c_float * 3)()
         for k in range(n):
             L.orc_world_sample(C.byref(s), _f3(d[k]), out)
-            assert np.array_equal(u32(np.array(out, np.float32)), u32(got[k, :3])), (kind, k)
+            assert same_f32(np.array(out, np.float32), got[k, :3]), (kind, k)
     # closest_hit through a two-object scene: object 0 a sphere, object 1 a cube
     sc = copy.copy(default_scene)
     sc.kind = np.array([orc.SPHERE, orc.CUBE], np.uint32)
@@ -120,8 +127,8 @@ def test_world_sample_and_closest_hit_kats(rb, renderer, orc, default_scene):
     faces = set()
     for k in range(m):
         L.orc_closest_hit(C.byref(s), int(obj[k]), _f3(o[k]), _f3(dd[k]), float(t[k]), p_o, n_o, C.byref(ff))
-        assert np.array_equal(u32(np.array(p_o, np.float32)), u32(got[k, 0:3])), k
-        assert np.array_equal(u32(np.array(n_o, np.float32)), u32(got[k, 3:6])), k     # bitwise: the sign of a zero component too
+        assert same_f32(np.array(p_o, np.float32), got[k, 0:3]), k
+        assert same_f32(np.array(n_o, np.float32), got[k, 3:6]), k                      # bitwise: the sign of a zero component too
         assert int(ff.value) == int(got[k, 6]), k
         if obj[k] == 1:
             faces.add(tuple(np.array(n_o, np.float32).tolist()))
