@@ -118,6 +118,10 @@ int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene);
 int rdr_render_sample(RdrRenderer *r, uint8_t *rgba8, int *produced);
 /* render_frame(&mut self, &Scene) -> RgbaImage       cpu.rs:119-133 (new_frame + all samples + resolve) */
 int rdr_render_frame(RdrRenderer *r, const RdrSceneFlat *scene, uint8_t *rgba8);
+/* The second half of render_frame on its own: every sample the current frame has left (cpu.rs:126-128) + the image
+ * (cpu.rs:129).  rdr_render_frame == rdr_new_frame + rdr_finish_frame; a host that keeps its own Profiler (the Rust
+ * shim: prepare_timer around the first call, render_timer around the second) calls the halves. */
+int rdr_finish_frame(RdrRenderer *r, uint8_t *rgba8);
 /* profiler(&self) -> &Profiler */
 int rdr_profiler(const RdrRenderer *r, RdrProfiler *out);
 uint32_t rdr_sample_count(const RdrRenderer *r);
@@ -222,8 +226,11 @@ int rdr_kat_camera_rays(RdrRenderer *r, uint32_t n, const uint32_t *xy, float *r
  *   CAN_REFRACT   utils/mod.rs:37-44    in v[3] n[3] ratio                         out flag
  *   WORLD_SAMPLE  world.rs:17-34        in d[3] kind(0 sky, 1 solid) a[3] b[3]     out rgb[3]
  *   CLOSEST_HIT   cpu.rs:354-394        in o[3] d[3] t is_sphere c[3] size         out p[3] n[3] front
- *   QUANTISE      cpu.rs:224-228        in sum n                                   out the u8 value */
-enum { RDR_KAT_REFLECT = 0, RDR_KAT_REFRACT = 1, RDR_KAT_CAN_REFRACT = 2, RDR_KAT_WORLD_SAMPLE = 3, RDR_KAT_CLOSEST_HIT = 4, RDR_KAT_QUANTISE = 5 };
+ *   QUANTISE      cpu.rs:224-228        in sum n                                   out the u8 value
+ *   RAND_FLOATS   utils/mod.rs:47-55, cpu.rs:280 (rand 0.8.5 float maps)  in three raw u32 words as bit patterns
+ *                                       out random::<f32>(w0), gen_range(-1.0..=1.0)(w0), random_in_unit_sphere(w0, w1, w2)[3] */
+enum { RDR_KAT_REFLECT = 0, RDR_KAT_REFRACT = 1, RDR_KAT_CAN_REFRACT = 2, RDR_KAT_WORLD_SAMPLE = 3, RDR_KAT_CLOSEST_HIT = 4, RDR_KAT_QUANTISE = 5,
+       RDR_KAT_RAND_FLOATS = 6 };
 int rdr_kat_vec(RdrRenderer *r, int op, uint32_t n, const float *in, float *out);
 /* raw RNG block of the spec (Philox4x32-10), computed on the device */
 int rdr_kat_rng(RdrRenderer *r, uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t block, uint32_t out[4]);

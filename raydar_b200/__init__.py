@@ -27,7 +27,7 @@ SPHERE, CUBE = 0, 1
 WORLD_SKY, WORLD_SOLID, WORLD_TRANSPARENT = 0, 1, 2
 ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH, ACCEL_CLUSTER, ACCEL_COOP, ACCEL_FUSED, ACCEL_BVH_COOP = 0, 1, 2, 3, 4, 5, 6
 PARTITION_SAMPLES, PARTITION_STRIPES = 0, 1
-KAT_REFLECT, KAT_REFRACT, KAT_CAN_REFRACT, KAT_WORLD_SAMPLE, KAT_CLOSEST_HIT, KAT_QUANTISE = range(6)
+KAT_REFLECT, KAT_REFRACT, KAT_CAN_REFRACT, KAT_WORLD_SAMPLE, KAT_CLOSEST_HIT, KAT_QUANTISE, KAT_RAND_FLOATS = range(7)
 COMBINE_AUTO, COMBINE_PEER, COMBINE_NCCL = 0, 1, 2
 IPC_HANDLE_BYTES = 128
 MAT_STRIDE = 11
@@ -45,7 +45,7 @@ EXPORTS = [
     "rdr_scene_set_resolution", "rdr_scene_override_resolution", "rdr_scene_flat", "rdr_scene_free",
     "rdr_write_png", "rdr_version",
     "rdr_set_combine", "rdr_combine_in_use", "rdr_alloc_host_image", "rdr_free_host_image",
-    "rdr_kat_vec", "rdr_ipc_export", "rdr_peer_attach", "rdr_peer_combine", "rdr_peer_detach", "rdr_read_image",
+    "rdr_kat_vec", "rdr_finish_frame", "rdr_ipc_export", "rdr_peer_attach", "rdr_peer_combine", "rdr_peer_detach", "rdr_read_image",
 ]
 
 
@@ -113,6 +113,7 @@ def load_library():
     L.rdr_new_frame.argtypes = [vp, sfp]
     L.rdr_render_sample.argtypes = [vp, u8p, C.POINTER(C.c_int)]
     L.rdr_render_frame.argtypes = [vp, sfp, u8p]
+    L.rdr_finish_frame.argtypes = [vp, u8p]
     L.rdr_profiler.argtypes = [vp, C.POINTER(RdrProfiler)]
     for name in ("rdr_sample_count", "rdr_max_sample_count", "rdr_max_bounces"):
         getattr(L, name).argtypes = [vp]; getattr(L, name).restype = C.c_uint32
@@ -311,6 +312,12 @@ class Renderer:
             raise RaydarError(ERR_INVALID, "out must be a C-contiguous (H, W, 4) uint8 array")
         _check(self._L.rdr_render_frame(self._h, C.byref(f), img.ctypes.data_as(C.POINTER(C.c_uint8))), self._h)
         self._shape = (f.height, f.width)
+        return img
+
+    def finish_frame(self, out=None) -> np.ndarray:
+        """Every sample the current frame has left, then the image (render_frame without its new_frame)."""
+        img = out if out is not None else np.empty((*self._shape, 4), np.uint8)
+        _check(self._L.rdr_finish_frame(self._h, img.ctypes.data_as(C.POINTER(C.c_uint8))), self._h)
         return img
 
     def profiler(self) -> RdrProfiler:

@@ -80,6 +80,7 @@ struct RdrRenderer {
     FrameParams params{};
     unsigned char *d_blob = nullptr; size_t blob_capacity = 0;
     rdr::f4 *d_accum = nullptr; uchar4 *d_rgba = nullptr; size_t pixel_capacity = 0;
+    rdr::f4 *d_primary = nullptr; int32_t *d_primary_idx = nullptr;   // the frame's primary table (primary_kernel)
     uint32_t *d_counter = nullptr;       // pixel hand-out counter of the persistent render kernel
     int resident_ctas = 0;
     uint32_t sample_count = 0;
@@ -256,6 +257,8 @@ void rdr_destroy(RdrRenderer *r)
     if (r->d_blob) cudaFree(r->d_blob);
     if (r->d_accum) cudaFree(r->d_accum);
     if (r->d_rgba) cudaFree(r->d_rgba);
+    if (r->d_primary) cudaFree(r->d_primary);
+    if (r->d_primary_idx) cudaFree(r->d_primary_idx);
     if (r->d_counter) cudaFree(r->d_counter);
     if (r->ev_start) cudaEventDestroy(r->ev_start);
     if (r->ev_stop) cudaEventDestroy(r->ev_stop);
@@ -311,9 +314,13 @@ int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene)
         if (r->peer.world) { r->has_frame = false; return fail(r, RDR_ERR_INVALID, "resolution grew while peers are attached: rdr_peer_detach on every rank first"); }
         if (r->d_accum) cudaFree(r->d_accum);
         if (r->d_rgba) cudaFree(r->d_rgba);
-        r->d_accum = nullptr; r->d_rgba = nullptr; r->pixel_capacity = 0;
+        if (r->d_primary) cudaFree(r->d_primary);
+        if (r->d_primary_idx) cudaFree(r->d_primary_idx);
+        r->d_accum = nullptr; r->d_rgba = nullptr; r->d_primary = nullptr; r->d_primary_idx = nullptr; r->pixel_capacity = 0;
         RDR_CUDA(r, cudaMalloc(&r->d_accum, n_pixels * sizeof(rdr::f4)));
         RDR_CUDA(r, cudaMalloc(&r->d_rgba, n_pixels * sizeof(uchar4)));
+        RDR_CUDA(r, cudaMalloc(&r->d_primary, n_pixels * sizeof(rdr::f4)));
+        RDR_CUDA(r, cudaMalloc(&r->d_primary_idx, n_pixels * sizeof(int32_t)));
         r->pixel_capacity = n_pixels;
     }
     if (n_pixels) RDR_CUDA(r, cudaMemsetAsync(r->d_accum, 0, n_pixels * sizeof(rdr::f4), r->stream));
@@ -330,6 +337,12 @@ int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene)
     r->has_frame = true;
     r->has_frame_layout_bvh = P.lay.mode == 1u;
     r->frame_accel = r->accel;
+    // the frame's primary table: camera ray + nearest hit of every pixel, once (asynchronous: the render kernels follow on the same stream)
+    r->params.primary = r->d_primary; r->params.primary_idx = r->d_primary_idx;
+    if (n_pixels) {
+        RDR_CUDA(r, rdr::launch_primary(r->params, scan_variant(r), r->d_primary, r->d_primary_idx, r->stream));
+        r->launches += 1;
+    }
     return RDR_OK;
 }
 
@@ -370,14 +383,21 @@ int rdr_render_sample(RdrRenderer *r, uint8_t *rgba8, int *produced)
     return RDR_OK;
 }
 
-int rdr_render_frame(RdrRenderer *r, const RdrSceneFlat *scene, uint8_t *rgba8)
+int rdr_finish_frame(RdrRenderer *r, uint8_t *rgba8)
 {
-    if (r && r->multi) return rdr::multi_render_frame(r, r->multi, scene, rgba8);
-    int st = rdr_new_frame(r, scene);
+    if (r && r->multi) return rdr::multi_finish_frame(r, r->multi, rgba8);
+    int st = check_frame(r);
     if (st) return st;
-    if (r->config.max_sample_count > 0u && (st = render_more(r, r->config.max_sample_count)) != RDR_OK) return st;
+    const uint32_t left = r->config.max_sample_count > r->sample_count ? r->config.max_sample_count - r->sample_count : 0u;
+    if (left > 0u && (st = render_more(r, left)) != RDR_OK) return st;
     // max_sample_count == 0: the reference divides by zero -> NaN -> 0 for every channel (cpu.rs:224)
     return resolve_to_host(r, r->sample_count, rgba8);
+}
+
+int rdr_render_frame(RdrRenderer *r, const RdrSceneFlat *scene, uint8_t *rgba8)
+{
+    int st = rdr_new_frame(r, scene);
+    return st ? st : rdr_finish_frame(r, rgba8);
 }
 
 int rdr_resolve(RdrRenderer *r, uint32_t divisor, uint8_t *rgba8)
@@ -645,14 +665,13 @@ int rdr_first_hit(RdrRenderer *r, int32_t *ids, float *t)
     int st = check_frame(r);
     if (st) return st;
     if (r->multi) return fail(r, RDR_ERR_INVALID, "debug entry points need a single-GPU handle");
+    // the frame's primary table already holds them (primary_kernel, run by rdr_new_frame)
     const size_t n = (size_t)r->params.cam.width * r->params.cam.height;
-    DevBuf<int32_t> d_ids; DevBuf<float> d_t;
-    RDR_CUDA(r, d_ids.alloc(n)); RDR_CUDA(r, d_t.alloc(n));
-    RDR_CUDA(r, rdr::launch_first_hit(r->params, scan_variant(r), d_ids.p, d_t.p, r->stream));
-    r->launches += 1;
-    if (ids) RDR_CUDA(r, cudaMemcpyAsync(ids, d_ids.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, r->stream));
-    if (t) RDR_CUDA(r, cudaMemcpyAsync(t, d_t.p, n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    if (ids) RDR_CUDA(r, cudaMemcpyAsync(ids, r->d_primary_idx, n * sizeof(int32_t), cudaMemcpyDeviceToHost, r->stream));
+    std::vector<rdr::f4> table(t ? n : 0u);
+    if (t && n) RDR_CUDA(r, cudaMemcpyAsync(table.data(), r->d_primary, n * sizeof(rdr::f4), cudaMemcpyDeviceToHost, r->stream));
     RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    if (t) for (size_t i = 0; i < n; ++i) t[i] = table[i].w;
     return RDR_OK;
 }
 
@@ -725,7 +744,7 @@ int rdr_kat_trace(RdrRenderer *r, uint32_t n, const float *rays, int32_t *ids, f
 int rdr_kat_vec(RdrRenderer *r, int op, uint32_t n, const float *in, float *out)
 {
     if (!r) return fail(nullptr, RDR_ERR_INVALID, "renderer is NULL");
-    if (op < RDR_KAT_REFLECT || op > RDR_KAT_QUANTISE || !in || !out) return fail(r, RDR_ERR_INVALID, "bad KAT arguments");
+    if (op < RDR_KAT_REFLECT || op > RDR_KAT_RAND_FLOATS || !in || !out) return fail(r, RDR_ERR_INVALID, "bad KAT arguments");
     int st = ensure_device(r);
     if (st) return st;
     DevBuf<float> d_in, d_out;

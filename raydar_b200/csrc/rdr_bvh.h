@@ -165,14 +165,18 @@ private:
 // Same boxes and the same conservative rules as BvhBuilder, different shape and storage:
 //   root   <= 32 entries, returned as 16 TopPair records (FFMA2 operand order) that travel in the kernel parameters,
 //          plus their payloads;
-//   node   8 entries = 4 pairs (A, B), 16 quads (256 B, one or two 128-byte lines), QUAD-MAJOR: quad i of pair p is
-//          quad 4 i + p, so that the 4 lanes that share a node read 64 contiguous bytes per load instruction:
+//   node   8 entries = 4 pairs (A, B), 16 quads (256 B = two 128-byte lines; the section is 128-byte aligned): quad i
+//          of pair p is quad node2_quad(i, p) = 8 (i / 2) + 2 p + i % 2, so that a lane that serves pair p reads TWO
+//          256-bit words (LDG.256: quads 0 and 1, then quads 2 and 3) and the 4 lanes that share a node read one whole
+//          128-byte line per load instruction (2 L1 wavefronts per node; 64-byte pieces per LDG.128 cost 4):
 //            i = 0: (cxA, cxB, cyA, cyB)   1: (czA, czB, exA, exB)   2: (eyA, eyB, ezA, ezB)
 //            i = 3: (orderA, orderB, payloadA, payloadB)
 //   payload: bit 31 = primitive (else child node index), bit 30 = cube, bit 29 = the box grows by the per-ray rho (a
 //   sphere, or a node that contains one), low 27 bits = index; 0xffffffff = unused entry (its box has e = -1).
 //   order: bits [3 oct, 3 oct + 3) = rank of the entry in the node's near-to-far order for direction octant oct
 //   (same construction as the root's, from the node's own split tree).
+inline uint32_t node2_quad(uint32_t i, uint32_t pair) { return 8u * (i >> 1) + 2u * pair + (i & 1u); }
+
 struct Bvh2Root {
     float cx[32], cy[32], cz[32], ex[32], ey[32], ez[32], sphere[32];
     uint32_t payload[32];
@@ -356,7 +360,7 @@ private:
         }
         for (int k = 0; k < BVH_WIDTH; ++k) {
             const int pair = k >> 1, h = k & 1;
-            auto quad = [&](int i) { return p + 4 * (4 * i + pair); };
+            auto quad = [&](int i) { return p + 4 * node2_quad((uint32_t)i, (uint32_t)pair); };
             if (k >= (int)entries.size()) {
                 quad(1)[2 + h] = quad(2)[0 + h] = quad(2)[2 + h] = -1.0f;      // unused: e = -1, payload = 0xffffffff
                 const uint32_t none = 0xffffffffu; memcpy(&quad(3)[2 + h], &none, 4);

@@ -9,9 +9,9 @@
 //        FRONT-TO-BACK order for the ray's direction octant (the builder's split tree gives 8 fixed permutations);
 //   S    each round the first 8 rays that still have work contribute their next node: the top of the ray's stack, else
 //        the nearest untouched child of the root;
-//   N    FOUR LANES PER TASK: each lane loads one pair of the node's entries (quad-major node: the 4 lanes read 64
-//        contiguous bytes per LDG.128) and tests it with FFMA2, bounded by the ray's best exact t so far; the ray's slab
-//        constants come by indexed shuffle;
+//   N    FOUR LANES PER TASK: each lane loads one pair of the node's entries with two 256-bit loads (LDG.256, sm_100:
+//        the 4 lanes of a task read one whole 128-byte line per instruction) and tests it with FFMA2, bounded by the
+//        ray's best exact t so far; the ray's slab constants come by indexed shuffle;
 //   P    child nodes go onto the owner's stack far first (every node carries its entries' near-to-far ranks per octant,
 //        like the root), primitives to the warp's sphere / cube survivor lists; every position is a popcount of a
 //        ballot or of the group's rank mask (no shuffle scan, no atomics);
@@ -31,13 +31,28 @@
 
 namespace rdr {
 
+// two consecutive quads (32 bytes, 32-byte aligned) with one 256-bit load
+__device__ __forceinline__ void ld_quads2(const f4 *p, f4 &a, f4 &b)
+{
+#ifdef RDR_WARP_EMU
+    a = p[0]; b = p[1];
+#else
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#endif
+}
+
 constexpr uint32_t BVH2_RAY_STACK = 56u;                      // per ray: 8 + 7 x 5 pending siblings (node levels 2..8) and slack
 constexpr uint32_t BVH2_SURV_CAP = 31u + 256u + 1u;           // carried remainder + one root chunk of 32 x 8 primitives
-constexpr uint32_t BVH2_WARP_BYTES = 32u * 8u + 4u * 32u * BVH2_RAY_STACK + 4u * 32u + 8u * 8u + 2u * 4u * BVH2_SURV_CAP;
+// stack entries are 16-bit node indices (the packer enables this traversal for hierarchies of <= 65535 nodes, i.e. up to
+// ~400k objects): 6.3 KB of shared memory per warp instead of 9.9 KB, which is what lets 24 warps and their cold columns
+// share an SM (768-thread CTA; 640 threads, 20 warps and no cold columns before)
+constexpr uint32_t BVH2_MAX_NODES = 65535u;
+constexpr uint32_t BVH2_WARP_BYTES = 32u * 8u + 2u * 32u * BVH2_RAY_STACK + 4u * 32u + 8u * 8u + 2u * 4u * BVH2_SURV_CAP;
 
 struct Bvh2Warp {
     unsigned long long *best;     // [32] winner key per ray (lane)
-    uint32_t *stack;              // [32][BVH2_RAY_STACK] pending child nodes per ray, top = next
+    uint16_t *stack;              // [32][BVH2_RAY_STACK] pending child nodes per ray, top = next
     uint32_t *depth;              // [32] entries on each ray's stack
     uint2 *slot;                  // [8]  this round's tasks: (owner lane, node)
     uint32_t *surv_s, *surv_c;    // [BVH2_SURV_CAP] owner lane << 27 | object; surv_c = surv_s + BVH2_SURV_CAP
@@ -50,8 +65,8 @@ __device__ __forceinline__ Bvh2Warp bvh2_warp(unsigned char *base, uint32_t warp
     w.best = reinterpret_cast<unsigned long long *>(p);
     w.slot = reinterpret_cast<uint2 *>(p + 256u);
     w.depth = reinterpret_cast<uint32_t *>(p + 256u + 64u);
-    w.stack = w.depth + 32u;
-    w.surv_s = w.stack + 32u * BVH2_RAY_STACK;
+    w.stack = reinterpret_cast<uint16_t *>(w.depth + 32u);
+    w.surv_s = reinterpret_cast<uint32_t *>(w.stack + 32u * BVH2_RAY_STACK);
     w.surv_c = w.surv_s + BVH2_SURV_CAP;
     return w;
 }
@@ -153,8 +168,8 @@ __device__ __forceinline__ Hit trace_bvh2(const SceneView &S, const FrameParams 
                 }
                 const uint32_t n_act = __popc(active), n_tasks = n_act < 8u ? n_act : 8u;
                 __syncwarp();
-                // ---- N: 4 lanes per task, one pair of the node's entries per lane (quad-major node: the 4 lanes read 64
-                //      contiguous bytes per LDG.128), bounded by the owner's best exact t so far ----
+                // ---- N: 4 lanes per task, one pair of the node's entries per lane (the 4 lanes read one whole 128-byte
+                //      line per LDG.256), bounded by the owner's best exact t so far ----
                 const bool has = grp < n_tasks;
                 const uint2 task = has ? ws.slot[grp] : make_uint2(lane, 0u);
                 const uint32_t owner = task.x;
@@ -164,8 +179,10 @@ __device__ __forceinline__ Hit trace_bvh2(const SceneView &S, const FrameParams 
                 // best exact t of the owner so far: high word of its key; ~0 (no hit) and a NaN hit read as NaN = no bound
                 const float best = __uint_as_float(reinterpret_cast<const uint32_t *>(ws.best + owner)[1]);
                 const uint32_t dbase = ws.depth[owner];           // after the pop above
-                const f4 *nd = nodes + 16u * (size_t)task.y + sub;
-                const f4 q0 = nd[0], q1 = nd[4], q2 = nd[8], q3 = nd[12];
+                const f4 *nd = nodes + 16u * (size_t)task.y + 2u * sub;        // node2_quad(i, sub): quads (0, 1) here, (2, 3) one line on
+                f4 q0, q1, q2, q3;
+                ld_quads2(nd, q0, q1);
+                ld_quads2(nd + 8, q2, q3);
                 const uint32_t pa = __float_as_uint(q3.z), pb = __float_as_uint(q3.w);
                 // payload bit 29: the box grows by the ray's rho (a sphere, or a node that contains one)
                 const f32x2 sp = pk2((pa & 0x20000000u) ? 1.0f : 0.0f, (pb & 0x20000000u) ? 1.0f : 0.0f);
@@ -188,8 +205,8 @@ __device__ __forceinline__ Hit trace_bvh2(const SceneView &S, const FrameParams 
                 gm |= __shfl_xor_sync(FULL, gm, 2);
                 const uint32_t sbase = owner * BVH2_RAY_STACK + dbase;
                 __syncwarp();                                     // every lane of the group has read depth[owner] before lane 0 rewrites it
-                if (na) ws.stack[sbase + __popc(gm >> (ra + 1u))] = pa & 0x07ffffffu;
-                if (nb) ws.stack[sbase + __popc(gm >> (rb + 1u))] = pb & 0x07ffffffu;
+                if (na) ws.stack[sbase + __popc(gm >> (ra + 1u))] = (uint16_t)(pa & 0xffffu);
+                if (nb) ws.stack[sbase + __popc(gm >> (rb + 1u))] = (uint16_t)(pb & 0xffffu);
                 if (has && sub == 0u) ws.depth[owner] = dbase + __popc(gm);
                 const uint32_t bsa = __ballot_sync(FULL, sa), bsb = __ballot_sync(FULL, sb);
                 const uint32_t bca = __ballot_sync(FULL, ca), bcb = __ballot_sync(FULL, cb);

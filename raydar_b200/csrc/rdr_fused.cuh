@@ -90,16 +90,13 @@ struct FusedView {
     const uint32_t *member_idx;
 };
 
-// inclusive prefix sum over the warp.  RDR_SCAN_PRED (prepared, off): the shuffle's own "source lane in range" predicate
-// guards the add -- SHFL + @P IADD per step instead of SHFL + SEL + IADD with a separate lane compare.
-#ifndef RDR_SCAN_PRED
-#define RDR_SCAN_PRED 0
-#endif
+// inclusive prefix sum over the warp.  The shuffle's own "source lane in range" predicate guards the add: SHFL.UP P +
+// @P IADD per step instead of SHFL + SEL + IADD with a separate lane compare (11 instead of ~20 instructions).
 __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, uint32_t lane)
 {
 #pragma unroll
     for (uint32_t off = 1u; off < 32u; off <<= 1) {
-#if RDR_SCAN_PRED && !defined(RDR_WARP_EMU)
+#ifndef RDR_WARP_EMU
         asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t@p add.u32 %0, %0, t;\n\t}"
                      : "+r"(v) : "r"(off));
         (void)lane;
@@ -158,24 +155,8 @@ __device__ __forceinline__ void fused_exact(const FusedView &V, FusedWarp ws, ui
 
 // two boxes (A, B) against one ray: bit 0 / bit 1 of the result = box A / B may be hit.
 //   c*: centres, e*: half-extents (already inflated), r*: the ray's 1/d, n*: -(o/d)
-// slab_pair_acc ORs the two bits into `m` at compile-time position SHIFT.  RDR_PRED_OR: one compare and one predicated
-// OR per box (FSETP + @!P LOP3) instead of the select / add / shift / or chain the compiler builds from the C form.
-#ifndef RDR_PRED_OR
-#define RDR_PRED_OR 1
-#endif
-// Prepared, NOT yet measured or parity-tested on the GPU (off by default; the default build's SASS is unchanged):
-//   RDR_DIRECT_BALLOT  survivors of the single-primitive top entries (benchmark.rscn: the floor) are appended with one
-//                      ballot per entry instead of the prefix scan + write loop of fused_append (~100 of ~2300 warp
-//                      instructions per trace iteration)
-//   RDR_APPROX_RHO     the per-ray sphere margin rho from sqrt.approx (2 ulp, covered by its 1.0001 safety factor)
-//                      instead of two correctly rounded square roots
-//   RDR_SCAN_PRED      warp prefix sums with the shuffle's own predicate (warp_scan_incl)
-#ifndef RDR_DIRECT_BALLOT
-#define RDR_DIRECT_BALLOT 0
-#endif
-#ifndef RDR_APPROX_RHO
-#define RDR_APPROX_RHO 0
-#endif
+// slab_pair_acc ORs the two bits into `m` at compile-time position SHIFT: one compare and one predicated OR per box
+// (FSETP + @!P LOP3) instead of the select / add / shift / or chain the compiler builds from the C form.
 __device__ __forceinline__ void or_unless_gt(uint32_t &m, float tn, float tf, uint32_t bit)
 {
     // tn > tf is false for a NaN operand: the bit is set, as in `(tn > tf ? 0 : bit)`
@@ -211,14 +192,10 @@ template <uint32_t SHIFT>
 __device__ __forceinline__ void slab_pair_acc(uint32_t &m, f32x2 cx, f32x2 cy, f32x2 cz, f32x2 ex, f32x2 ey, f32x2 ez,
                                               float rx, float ry, float rz, float nx, float ny, float nz)
 {
-    if (RDR_PRED_OR) {
-        float tna, tfa, tnb, tfb;
-        slab_pair_tn_tf<false>(cx, cy, cz, ex, ey, ez, rx, ry, rz, nx, ny, nz, 0.0f, tna, tfa, tnb, tfb);
-        or_unless_gt(m, tna, tfa, 1u << SHIFT);
-        or_unless_gt(m, tnb, tfb, 2u << SHIFT);
-    } else {
-        m |= slab_pair(cx, cy, cz, ex, ey, ez, rx, ry, rz, nx, ny, nz) << SHIFT;
-    }
+    float tna, tfa, tnb, tfb;
+    slab_pair_tn_tf<false>(cx, cy, cz, ex, ey, ez, rx, ry, rz, nx, ny, nz, 0.0f, tna, tfa, tnb, tfb);
+    or_unless_gt(m, tna, tfa, 1u << SHIFT);
+    or_unless_gt(m, tnb, tfb, 2u << SHIFT);
 }
 
 // slab constants of one ray for the pair tests (make_ray_bvh, rdr_core.cuh): r = 1/d (clamped to +-1e30 for zero /
@@ -241,8 +218,9 @@ __device__ __forceinline__ SlabRay slab_ray_setup(const CullConsts &cc, v3 o, v3
     const float omax = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
     const bool degenerate = !(omax <= cc.origin_bound) || !(a > 1e-30f) || !(a < 1e30f) || !(s_ray < 1e30f) ||
                             isnan_(d.x) || isnan_(d.y) || isnan_(d.z);
-#if RDR_APPROX_RHO
     {
+        // rho from sqrt.approx (2 ulp): (q1 - r_min) loses at most 2 ulp(q1) <= 2^-22 (r_min + rho), made up by the 1.0001
+        // factor and by widening with r_min too -- two MUFU.SQRT instead of two correctly rounded square roots
         float q1, q2;
 #ifdef RDR_WARP_EMU
         q1 = fsqrt(fma(cc.sphere_r_min, cc.sphere_r_min, Ms)); q2 = fsqrt(s_ray);
@@ -250,14 +228,9 @@ __device__ __forceinline__ SlabRay slab_ray_setup(const CullConsts &cc, v3 o, v3
         asm("sqrt.approx.f32 %0, %1;" : "=f"(q1) : "f"(fma(cc.sphere_r_min, cc.sphere_r_min, Ms)));
         asm("sqrt.approx.f32 %0, %1;" : "=f"(q2) : "f"(s_ray));
 #endif
-        // q1 may be 2 ulp low: (q1 - r_min) loses at most 2 ulp(q1) <= 2^-22 (r_min + rho), made up by widening with r_min too
         R.rho = fadd(fsub(q1, cc.sphere_r_min), fmul(1.9073486328125e-06f, q2));
         R.rho = fma(R.rho, 1.0001f, fmul(4.76837158203125e-07f, cc.sphere_r_min));
     }
-#else
-    R.rho = fadd(fsub(fsqrt(fma(cc.sphere_r_min, cc.sphere_r_min, Ms)), cc.sphere_r_min), fmul(1.9073486328125e-06f, fsqrt(s_ray)));
-    R.rho = fmul(R.rho, 1.0001f);
-#endif
     R.nx = fneg(fmul(o.x, R.rx)); R.ny = fneg(fmul(o.y, R.ry)); R.nz = fneg(fmul(o.z, R.rz));
     if (degenerate) { R.rx = R.ry = R.rz = 0.0f; R.nx = R.ny = R.nz = 0.0f; R.rho = 0.0f; }
     return R;
@@ -283,6 +256,8 @@ __device__ __forceinline__ void top_pairs4(uint32_t &m, const TopParams &T, f32x
 
 // Fully unrolled, four pairs per step: every operand is a compile-time constant-bank address.  (A warp-uniform loop over
 // groups of pairs indexes the constant bank with a vector register -- LDC per operand -- and measured 1-2 % slower.)
+// (A warp-uniform loop over groups of pairs indexes the constant bank with a vector register -- LDC per operand instead of
+// LDCU.128 -- and measured 2 - 5 % slower even though it takes 2.5 KB out of the hot loop: profiles/variants_r03i.txt.)
 __device__ __forceinline__ uint32_t top_scan(const TopParams &T, uint32_t n_top, const SlabRay &R)
 {
     uint32_t m = 0u;
@@ -315,7 +290,6 @@ __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams
     // single-primitive top entries: their box was the entry -> straight to the survivor lists (member slot = C * entry)
     if (P.lay.fused_direct != 0u) {
         const uint32_t dmask = (1u << P.lay.fused_direct) - 1u;
-#if RDR_DIRECT_BALLOT
         // one ballot per direct entry (<= 4, warp-uniform loop): the survivor's position is the popcount of the ballot
         // below the lane -- no prefix scan, no per-lane write loop
         const uint32_t below = (1u << lane) - 1u, cap = CAP8 ? 8u : P.lay.fused_cap;
@@ -332,9 +306,6 @@ __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams
             }
         }
         __syncwarp();
-#else
-        fused_append(ws, lane, lane, 0u, CAP8 ? 8u : P.lay.fused_cap, m & dmask, P.lay.fused_ns_direct, n_s, n_c);
-#endif
         m &= ~dmask;
     }
 

@@ -4,7 +4,7 @@
 //                      one lane owns one pixel, loops over its samples and bounces, accumulates in
 //                      registers and issues one 16-byte load and one 16-byte store of the accumulator.
 //   resolve_kernel     print_frame_buffer (cpu.rs:221-230)
-//   first_hit_kernel   debug/parity: primary-ray nearest hit per pixel
+//   primary_kernel     the frame's primary table: camera ray + nearest hit per pixel, once per frame (also rdr_first_hit)
 //   trace_path_kernel  debug/parity: one path with every bounce recorded
 //   kat_* kernels      per-function known-answer entry points
 #include <cuda_runtime.h>
@@ -145,9 +145,14 @@ __global__ void __launch_bounds__(256) peer_combine_kernel(const __grid_constant
 }
 
 // ---- debug / parity kernels ---------------------------------------------------------------------------
+// ---- the frame's primary table: camera ray (cpu.rs:199-202,234-251) and its nearest hit, once per pixel per frame ----
+// The reference's camera ray has no jitter, so every sample of a pixel starts from the same ray and the same first hit.
+// rdr_new_frame runs this kernel once; render_kernel then never sets up a camera ray or traces a primary ray, in any
+// launch of the frame (a progressive frame of N one-sample launches saves N - 1 primary traces per pixel).  The table
+// is also what rdr_first_hit returns.
 template <int MODE>
-__global__ void __launch_bounds__(RDR_BLOCK, 2) first_hit_kernel(const __grid_constant__ FrameParams P,
-                                                                int32_t *__restrict__ ids, float *__restrict__ ts)
+__global__ void __launch_bounds__(RDR_BLOCK, 2) primary_kernel(const __grid_constant__ FrameParams P,
+                                                              f4 *__restrict__ primary, int32_t *__restrict__ primary_idx)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const SceneView S = scene_view(stage_scene<MODE>(smem, P), P.lay);
@@ -158,8 +163,9 @@ __global__ void __launch_bounds__(RDR_BLOCK, 2) first_hit_kernel(const __grid_co
     const v3 d = valid ? camera_ray_dir(P.cam, pixel % P.cam.width, pixel / P.cam.width) : mk3(0.0f, 0.0f, 1.0f);
     const Hit h = trace_warp<MODE>(S, P, scratch0, valid, o, d);
     if (!valid) return;
-    ids[pixel] = h.idx;
-    ts[pixel] = h.idx >= 0 ? h.t : 0.0f;
+    f4 out; out.x = d.x; out.y = d.y; out.z = d.z; out.w = h.idx >= 0 ? h.t : 0.0f;
+    primary[pixel] = out;
+    primary_idx[pixel] = h.idx;
 }
 
 template <int MODE>
@@ -242,6 +248,11 @@ __global__ void kat_vec_kernel(int op, uint32_t n, const float *__restrict__ in,
         o[0] = sf.p.x; o[1] = sf.p.y; o[2] = sf.p.z; o[3] = sf.n.x; o[4] = sf.n.y; o[5] = sf.n.z; o[6] = sf.front ? 1.0f : 0.0f;
     }
     else if (op == RDR_KAT_QUANTISE) { o[0] = (float)quantise(a[0], a[1]); }
+    else if (op == RDR_KAT_RAND_FLOATS) {            // the rand 0.8.5 float maps on raw 32-bit words (passed as bit patterns)
+        u4 wds; wds.x = f2u(a[0]); wds.y = f2u(a[1]); wds.z = f2u(a[2]); wds.w = 0u;
+        o[0] = u01(wds.x); o[1] = range_pm1(wds.x);
+        const v3 r = random_in_unit_sphere(wds); o[2] = r.x; o[3] = r.y; o[4] = r.z;
+    }
 }
 
 __global__ void kat_camera_rays_kernel(const __grid_constant__ FrameParams P, uint32_t n, const uint32_t *__restrict__ xy,
@@ -363,9 +374,14 @@ static RenderShape render_shape(const FrameParams &P, int mode)
         const int cfg = RDR_BVH2_CTA;
         switch (cfg) {
         case 0: return RenderShape{768u, false};
+        case 1: return RenderShape{640u, false};
         case 2: return RenderShape{512u, false};
-        default: return RenderShape{640u, false};      // its per-ray stacks (9.9 KB per warp) leave no room for cold columns
+        default: break;
         }
+        // 24 warps with the cold / parked state in shared-memory columns when the footprint fits (6.3 KB of stacks and
+        // lists per warp + 72 B of columns per lane = 207 KB), else 20 warps with the state in registers
+        if (mode_smem_bytes(P.lay, false, 768u, mode, true) <= limit) return RenderShape{768u, true};
+        return RenderShape{640u, false};
     }
     const int cfg = RDR_FUSED_CTA;
     if (cfg == 0) return RenderShape{RDR_BLOCK, false};
@@ -381,7 +397,8 @@ static RenderShape render_shape(const FrameParams &P, int mode)
 #define RDR_RENDER_DISPATCH(mode, shape, F)                                                           \
     do {                                                                                              \
         if ((mode) == 7) {                                                                            \
-            if ((shape).block == 768u) F((render_kernel<7, 768, 1, false>));                          \
+            if ((shape).cold) F((render_kernel<7, 768, 1, true>));                                    \
+            else if ((shape).block == 768u) F((render_kernel<7, 768, 1, false>));                     \
             else if ((shape).block == 512u) F((render_kernel<7, 512, 1, false>));                     \
             else F((render_kernel<7, 640, 1, false>));                                                \
         }                                                                                             \
@@ -471,14 +488,14 @@ cudaError_t launch_peer_combine(const PeerCombine &C, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-cudaError_t launch_first_hit(const FrameParams &P, int variant, int32_t *ids, float *ts, cudaStream_t stream)
+cudaError_t launch_primary(const FrameParams &P, int variant, f4 *primary, int32_t *primary_idx, cudaStream_t stream)
 {
     const uint32_t n_pixels = P.cam.width * P.cam.height;
     if (n_pixels == 0u) return cudaSuccess;
     const size_t smem = mode_smem_bytes(P.lay, P.staged != 0u, RDR_BLOCK, mode_of(P, variant));
     const uint32_t grid = (n_pixels + RDR_BLOCK - 1u) / RDR_BLOCK;
     cudaError_t e;
-#define RDR_K(M, ...) do { if ((e = set_smem(first_hit_kernel<M>, smem)) != cudaSuccess) return e; first_hit_kernel<M><<<grid, RDR_BLOCK, smem, stream>>>(P, ids, ts); } while (0)
+#define RDR_K(M, ...) do { if ((e = set_smem(primary_kernel<M>, smem)) != cudaSuccess) return e; primary_kernel<M><<<grid, RDR_BLOCK, smem, stream>>>(P, primary, primary_idx); } while (0)
     RDR_DISPATCH(mode_of(P, variant), RDR_K, 0);
 #undef RDR_K
     return cudaGetLastError();

@@ -32,7 +32,7 @@ size_t fused_smem_bytes(const SceneLayout &L);       // dynamic shared memory of
 cudaError_t launch_render(const FrameParams &P, int variant, int resident_ctas, cudaStream_t stream);
 cudaError_t render_resident_ctas(const FrameParams &P, int variant, int *out);
 cudaError_t launch_resolve(const f4 *accum, uchar4 *out, uint32_t n_pixels, float divisor, cudaStream_t stream);
-cudaError_t launch_first_hit(const FrameParams &P, int variant, int32_t *ids, float *ts, cudaStream_t stream);
+cudaError_t launch_primary(const FrameParams &P, int variant, f4 *primary, int32_t *primary_idx, cudaStream_t stream);
 cudaError_t launch_kat_trace(const FrameParams &P, int variant, uint32_t n, const float *rays, int32_t *ids, float *ts, cudaStream_t stream);
 cudaError_t launch_trace_path(const FrameParams &P, int variant, uint32_t x, uint32_t y, uint32_t sample,
                               RdrPathStep *steps, uint32_t capacity, uint32_t *n_steps, float *rgba, cudaStream_t stream);

@@ -104,6 +104,10 @@ struct FrameParams {
     const unsigned char *blob;           // device copy of the packed scene
     uint32_t staged;                     // 1: every CTA stages the blob into shared memory; 0: read in place (L2)
     f4 *accum;                           // W*H float RGBA accumulator (row-major, top row first)
+    // primary table of the frame (primary_kernel): the camera ray has no jitter (cpu.rs:199-202), so a pixel's primary
+    // direction and nearest hit are the same for every sample of every launch
+    const f4 *primary;                   // W*H: primary ray direction (x, y, z), nearest-hit t (w)
+    const int32_t *primary_idx;          // W*H: nearest-hit object index, -1 = miss
     uint32_t *pixel_counter;             // next unclaimed pixel of this launch (zeroed before the launch)
     uint32_t seed_lo, seed_hi;
     uint32_t max_bounces;

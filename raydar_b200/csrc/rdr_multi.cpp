@@ -412,15 +412,17 @@ int multi_render_sample(RdrRenderer *owner, MultiGpu *m, uint8_t *rgba8, int *pr
     return RDR_OK;
 }
 
-int multi_render_frame(RdrRenderer *owner, MultiGpu *m, const RdrSceneFlat *scene, uint8_t *rgba8)
+// every sample the frame has left, then the image: one launch per device + one combine kernel per device, one wait
+int multi_finish_frame(RdrRenderer *owner, MultiGpu *m, uint8_t *rgba8)
 {
-    int st = multi_new_frame(owner, m, scene);
-    if (st != RDR_OK) return st;
+    std::vector<uint32_t> share(m->child.size(), 0);
+    for (size_t g = 0; g < m->child.size(); ++g) share[g] = api_samples_left(m->child[g]);
+    int st;
     if (m->child.size() > 1u && use_peer(m)) {
-        if ((st = launch_shares(owner, m, m->count)) != RDR_OK) return st;
-        return peer_resolve(owner, m, &m->count, 0u, rgba8);
+        if ((st = launch_shares(owner, m, share)) != RDR_OK) return st;
+        return peer_resolve(owner, m, &share, 0u, rgba8);
     }
-    if ((st = render_shares(owner, m, m->count)) != RDR_OK) return st;
+    if ((st = render_shares(owner, m, share)) != RDR_OK) return st;
     return multi_resolve(owner, m, 0u, rgba8);
 }
 

@@ -19,7 +19,7 @@ void multi_destroy(MultiGpu *m);
 int multi_new_frame(RdrRenderer *owner, MultiGpu *m, const RdrSceneFlat *scene);
 int multi_render_samples(RdrRenderer *owner, MultiGpu *m, uint32_t n);
 int multi_render_sample(RdrRenderer *owner, MultiGpu *m, uint8_t *rgba8, int *produced);
-int multi_render_frame(RdrRenderer *owner, MultiGpu *m, const RdrSceneFlat *scene, uint8_t *rgba8);
+int multi_finish_frame(RdrRenderer *owner, MultiGpu *m, uint8_t *rgba8);
 int multi_resolve(RdrRenderer *owner, MultiGpu *m, uint32_t divisor, uint8_t *rgba8);
 int multi_read_accum(RdrRenderer *owner, MultiGpu *m, float *dst);
 int multi_synchronize(RdrRenderer *owner, MultiGpu *m);

@@ -92,13 +92,14 @@ inline int pack_scene_blob(const RdrSceneFlat *sc, bool use_bvh, std::vector<uns
         if (builder.build(std::move(prims))) {
             L.mode = 1u;
             L.n_nodes = builder.n_nodes();
-            L.bvh2_ok = ok2 ? 1u : 0u;
+            L.bvh2_ok = (ok2 && builder2.n_nodes() <= 65535u) ? 1u : 0u;   // 16-bit node indices on the traversal stacks (rdr_bvh2.cuh)
             L.n_nodes2 = ok2 ? builder2.n_nodes() : 0u;
             L.bvh2_root = ok2 ? builder2.root.n : 0u;
             uint64_t off = 0;
             L.off_nodes = (uint32_t)off; off += 256ull * L.n_nodes;
             L.off_obj_geom = (uint32_t)off; off += 16ull * n;
             L.off_material = (uint32_t)off; off += 48ull * n;
+            off = (off + 127ull) & ~127ull;                      // a node of the cooperative hierarchy = exactly two 128-byte lines
             L.off_nodes2 = (uint32_t)off; off += 256ull * L.n_nodes2;
             if (off > 0xfffffff0ull) { err = "scene too large"; return RDR_ERR_INVALID; }
             L.blob_bytes = std::max(16u, round_up_u32((uint32_t)off, 16u));

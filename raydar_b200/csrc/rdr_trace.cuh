@@ -424,7 +424,10 @@ RDR_HD uint32_t lane_varying_zero(uint32_t *scratch)
 // lengths differ between pixels.
 //
 // The camera ray has no jitter (cpu.rs:199-202), so all samples of a pixel share the primary ray and its
-// nearest hit; it is traced once per pixel per launch and reused (bit-identical results).
+// nearest hit: both are computed ONCE PER FRAME by primary_kernel (rdr_kernels.cu) into a per-pixel table
+// (FrameParams::primary / primary_idx) and reused by every sample of every launch of the frame (bit-identical
+// results).  A lane that claims a pixel loads 20 bytes instead of running the camera set-up (240 instructions of
+// exact divisions) and a trace, and goes straight to shading the primary hit.
 //
 // Per-pixel accumulation order is sample-ascending, as in the reference, so a launch over samples
 // [s0, s0+n) on top of an accumulator that already holds [0, s0) is bit-identical to one launch.
@@ -446,8 +449,8 @@ struct LaneStateT {
     Hit hit;                // hit to shade next
     v3 ro, rd, light, atten;
     uint32_t pixel, s, bounce, lane_zero;
-    bool alive;             // the lane holds a ray to trace
-    bool primary_pending;   // that ray is the pixel's primary ray
+    bool alive;             // the lane owns a pixel with samples left
+    bool has_ray;           // ... and holds a ray to trace (otherwise st.hit waits to be shaded)
 
     RDR_HD f4 acc() const { f4 a; a.x = cold.get(COLD_ACC); a.y = cold.get(COLD_ACC + 1); a.z = cold.get(COLD_ACC + 2); a.w = cold.get(COLD_ACC + 3); return a; }
     RDR_HD void set_acc(f4 a) { cold.set(COLD_ACC, a.x); cold.set(COLD_ACC + 1, a.y); cold.set(COLD_ACC + 2, a.z); cold.set(COLD_ACC + 3, a.w); }
@@ -474,7 +477,7 @@ template <class ST>
 RDR_HD void lane_init(ST &st, uint32_t *masks)
 {
     st.lane_zero = lane_varying_zero(masks);
-    st.alive = false; st.primary_pending = false;
+    st.alive = false; st.has_ray = false;
     st.pixel = 0u; st.s = st.lane_zero; st.bounce = st.lane_zero;
     f4 z; z.x = z.y = z.z = z.w = 0.0f;
     st.set_acc(z);
@@ -483,20 +486,21 @@ RDR_HD void lane_init(ST &st, uint32_t *masks)
     st.hit.idx = -1; st.hit.t = 0.0f; st.set_h0(st.hit);
 }
 
-// The camera ray is set up once per pixel per launch (once per ~2000 trace iterations at 1024 spp) but is 240
-// instructions of exact divisions and square roots: kept out of line so that the hot loop stays compact in the
-// instruction cache.  Returns its result in registers.
-RDR_HD_NOINLINE v3 camera_ray_dir_cold(const Camera &cam, uint32_t x, uint32_t y) { return camera_ray_dir(cam, x, y); }
+// the sample's path ended with a miss; defined below
+template <class ST> RDR_HD void lane_miss(const FrameParams &P, ST &st);
 
-// take ownership of `pixel` (acc = its current accumulator).  Afterwards either st.alive (the primary ray is
-// waiting to be traced) or the pixel is already finished (no samples / no bounces) and st.acc() is final.
+// take ownership of `pixel`: acc = its current accumulator, cam_d / h0 = its primary ray direction and nearest hit (the
+// frame's primary table).  Afterwards either st.alive -- the primary hit waits in st.hit to be shaded (no ray to trace
+// yet) -- or the pixel is already finished (no samples, no bounces, or a primary ray that misses: every sample is the
+// sky) and st.acc() is final.
 template <class ST>
-RDR_HD void lane_start_pixel(const FrameParams &P, uint32_t pixel, f4 acc, ST &st)
+RDR_HD void lane_start_pixel(const FrameParams &P, uint32_t pixel, f4 acc, v3 cam_d, Hit h0, ST &st)
 {
     st.pixel = pixel;
     st.s = st.lane_zero; st.bounce = st.lane_zero;
     st.light = mk3(0.0f, 0.0f, 0.0f); st.atten = mk3(1.0f, 1.0f, 1.0f);
     st.ro = mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]);
+    st.has_ray = false;
     if (P.max_bounces == 0u) {                // `for _ in 0..0`: light stays zero, alpha still accumulates
         for (uint32_t s = 0; s < P.sample_count; ++s) {
             acc.x = fadd(acc.x, 0.0f); acc.y = fadd(acc.y, 0.0f); acc.z = fadd(acc.z, 0.0f); acc.w = fadd(acc.w, 1.0f);
@@ -507,17 +511,18 @@ RDR_HD void lane_start_pixel(const FrameParams &P, uint32_t pixel, f4 acc, ST &s
     }
     st.set_acc(acc);
     st.alive = P.sample_count > 0u;
-    st.primary_pending = st.alive;
-    if (st.alive) { st.rd = camera_ray_dir_cold(P.cam, pixel % P.cam.width, pixel / P.cam.width); st.set_cam_d(st.rd); }
+    if (!st.alive) return;
+    st.rd = cam_d; st.set_cam_d(cam_d);
+    st.hit = h0; st.set_h0(h0);
+    if (h0.idx < 0) lane_miss(P, st);         // the primary ray misses: every sample is the sky, the pixel ends here
 }
-
 
 // the traced hit of the lane's current ray arrives
 template <class ST>
 RDR_HD void lane_accept_hit(ST &st, Hit h)
 {
-    if (st.primary_pending) { st.set_h0(h); st.primary_pending = false; }
     st.hit = h;
+    st.has_ray = false;
 }
 
 // the finished sample's light is in the accumulator: start the pixel's next sample from the cached primary hit
@@ -562,7 +567,7 @@ RDR_HD bool lane_shade_hit(const FrameParams &P, const SceneView &S, ST &st)
     st.atten = mul3(st.atten, m.albedo);
     st.light = add3(st.light, scale3(m.emission, m.emission_strength));
     ++st.bounce;
-    if (st.bounce < P.max_bounces) return true;
+    if (st.bounce < P.max_bounces) { st.has_ray = true; return true; }
     st.accumulate(st.light);
     lane_next_sample(P, st);
     return false;
@@ -575,10 +580,17 @@ RDR_HD f4 render_pixel(const FrameParams &P, const SceneView &S, uint32_t *masks
 {
     LaneState st;
     lane_init(st, masks);
-    lane_start_pixel(P, pixel, acc, st);
+    // the pixel's primary ray and its nearest hit (the kernel reads them from the frame's primary table)
+    const v3 cam_d = camera_ray_dir(P.cam, pixel % P.cam.width, pixel / P.cam.width);
+    Hit h0; h0.idx = -1; h0.t = 0.0f;
+    if (P.max_bounces != 0u && P.sample_count != 0u)
+        h0 = trace_any<MODE>(S, P.cull, masks, stride, mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]), cam_d, stats);
+    lane_start_pixel(P, pixel, acc, cam_d, h0, st);
     while (st.alive) {
-        lane_accept_hit(st, trace_any<MODE>(S, P.cull, masks, stride, st.ro, st.rd, stats));
-        if (st.hit.idx < 0) lane_miss(P, st);
+        if (st.has_ray) {
+            lane_accept_hit(st, trace_any<MODE>(S, P.cull, masks, stride, st.ro, st.rd, stats));
+            if (st.hit.idx < 0) lane_miss(P, st);
+        }
         while (st.alive && !lane_shade_hit(P, S, st)) {}
     }
     return st.acc();

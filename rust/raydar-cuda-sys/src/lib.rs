@@ -38,6 +38,8 @@ extern "C" {
     pub fn rdr_new_frame(r: *mut RdrRenderer, scene: *const RdrSceneFlat) -> c_int;
     pub fn rdr_render_sample(r: *mut RdrRenderer, rgba8: *mut u8, produced: *mut c_int) -> c_int;
     pub fn rdr_render_frame(r: *mut RdrRenderer, scene: *const RdrSceneFlat, rgba8: *mut u8) -> c_int;
+    /// the second half of render_frame: every sample the current frame has left + the image
+    pub fn rdr_finish_frame(r: *mut RdrRenderer, rgba8: *mut u8) -> c_int;
     pub fn rdr_profiler(r: *const RdrRenderer, out: *mut RdrProfiler) -> c_int;
     pub fn rdr_sample_count(r: *const RdrRenderer) -> u32;
     pub fn rdr_max_sample_count(r: *const RdrRenderer) -> u32;
@@ -47,4 +49,7 @@ extern "C" {
     pub fn rdr_set_seed(r: *mut RdrRenderer, seed: u64) -> c_int;
     /// multi-GPU handle: 0 = sample ranges (default), 1 = round-robin row stripes (bit-identical to one GPU)
     pub fn rdr_set_partition(r: *mut RdrRenderer, partition: c_int, stripe_rows: u32) -> c_int;
+    /// pinned host image buffers: the GPUs write an image that lies in one directly (no staging copy)
+    pub fn rdr_alloc_host_image(bytes: usize, out: *mut *mut u8) -> c_int;
+    pub fn rdr_free_host_image(image: *mut u8);
 }

@@ -6,7 +6,14 @@ use raydar_cuda_sys as sys;
 use super::{timing::Profiler, Renderer, RendererConfig};
 use crate::scene::{objects::Geometry, world::World, Scene};
 
-pub struct CudaRenderer { handle: *mut sys::RdrRenderer, profiler: Profiler, resolution: (u32, u32) }
+pub struct CudaRenderer {
+    handle: *mut sys::RdrRenderer,
+    profiler: Profiler,
+    resolution: (u32, u32),
+    /// pinned image the GPUs write directly (rdr_alloc_host_image), re-allocated when the resolution changes
+    image: *mut u8,
+    image_bytes: usize,
+}
 
 /// Flattened, borrowed view of `&Scene` (the Vec's must outlive the FFI call).
 struct Flat { kind: Vec<u32>, geom: Vec<f32>, material: Vec<f32>, raw: sys::RdrSceneFlat }
@@ -46,7 +53,7 @@ impl CudaRenderer {
         let mut handle = std::ptr::null_mut();
         let st = unsafe { sys::rdr_create(&cfg, 0, &mut handle) };
         assert!(st == 0, "rdr_create failed: {}", last_error(std::ptr::null()));
-        Self { handle, profiler: Profiler::default(), resolution: (0, 0) }
+        Self { handle, profiler: Profiler::default(), resolution: (0, 0), image: std::ptr::null_mut(), image_bytes: 0 }
     }
     /// `--gpus N`: one sub-renderer per device behind the same handle (rdr_create_multi).  `stripes`: round-robin
     /// 16-row stripes instead of sample ranges -- the image is then bit-identical to the one-GPU image.
@@ -57,39 +64,71 @@ impl CudaRenderer {
         let st = unsafe { sys::rdr_create_multi(&cfg, devices.len() as std::os::raw::c_int, devices.as_ptr(), &mut handle) };
         assert!(st == 0, "rdr_create_multi failed: {}", last_error(std::ptr::null()));
         if stripes { assert!(unsafe { sys::rdr_set_partition(handle, 1, 16) } == 0, "rdr_set_partition failed"); }
-        Self { handle, profiler: Profiler::default(), resolution: (0, 0) }
+        Self { handle, profiler: Profiler::default(), resolution: (0, 0), image: std::ptr::null_mut(), image_bytes: 0 }
     }
     fn check(&self, st: i32) { assert!(st == 0, "raydar_cuda: {}", last_error(self.handle)); }   // the trait is infallible
-    fn sync_profiler(&mut self) {        // timers are pub(super): a sibling module may fill them (timing.rs:12-18)
-        let mut p = sys::RdrProfiler::default();
-        unsafe { sys::rdr_profiler(self.handle, &mut p) };
-        self.profiler.set_durations_ns(p.has_frame != 0, p.frame_ns, p.has_sample != 0, p.sample_ns,
-                                       p.has_prepare != 0, p.prepare_ns, p.has_render != 0, p.render_ns);
-        // `set_durations_ns` is a 6-line helper to add to timing.rs (Timer { duration: Some(Duration::from_nanos(..)) })
+    fn image_for(&mut self, w: u32, h: u32) -> *mut u8 {
+        let bytes = (w as usize) * (h as usize) * 4;
+        if bytes > self.image_bytes {
+            unsafe { sys::rdr_free_host_image(self.image) };
+            self.image = std::ptr::null_mut(); self.image_bytes = 0;
+            assert!(unsafe { sys::rdr_alloc_host_image(bytes.max(4), &mut self.image) } == 0, "rdr_alloc_host_image failed");
+            self.image_bytes = bytes.max(4);
+        }
+        self.image
+    }
+    fn take_image(&self, w: u32, h: u32) -> RgbaImage {        // the trait returns an owned image: one host copy of W*H*4 bytes
+        let n = (w as usize) * (h as usize) * 4;
+        RgbaImage::from_raw(w, h, unsafe { std::slice::from_raw_parts(self.image, n) }.to_vec()).unwrap()
     }
 }
 
+// The Profiler's timers are `pub(super)` (timing.rs:12-18), so this sibling module drives them exactly as cpu.rs and
+// vulkan.rs do -- through Timer's public start() / end() / end_multiple() around the blocking FFI calls -- and needs no
+// change to timing.rs.  (The library keeps its own copy of the four durations plus the CUDA-event kernel time:
+// rdr_profiler, used by the C++ CLI and bench.py.)
 impl Renderer for CudaRenderer {
     fn render_frame(&mut self, scene: &Scene) -> RgbaImage {
-        let flat = flatten(scene);
-        let (w, h) = (flat.raw.width, flat.raw.height);
-        let mut buf = vec![0u8; (w * h * 4) as usize];
-        let st = unsafe { sys::rdr_render_frame(self.handle, &flat.raw, buf.as_mut_ptr()) };
-        self.check(st); self.sync_profiler(); self.resolution = (w, h);
-        RgbaImage::from_raw(w, h, buf).unwrap()
+        self.new_frame(scene);                                               // cpu.rs:120: frame + prepare timers start
+        let (w, h) = self.resolution;
+        let img = self.image_for(w, h);
+        let n = self.max_sample_count();
+        self.profiler.prepare_timer.end_if_not_ended();                      // cpu.rs:194
+        self.profiler.render_timer.start();
+        self.profiler.sample_timer.start();
+        let st = unsafe { sys::rdr_finish_frame(self.handle, img) };         // all samples + resolve, blocking (vulkan.rs:168)
+        self.check(st);
+        if n > 0 {                                                           // n == 0: the timers stay unset, as in cpu.rs
+            self.profiler.sample_timer.end_multiple(n);                      // vulkan.rs:175-179: mean per-sample time
+            self.profiler.render_timer.end();
+            self.profiler.frame_timer.end();
+        }
+        self.take_image(w, h)
     }
     fn new_frame(&mut self, scene: &Scene) {
+        self.profiler.frame_timer.start();                                   // cpu.rs:136-137
+        self.profiler.prepare_timer.start();
         let flat = flatten(scene);
-        let st = unsafe { sys::rdr_new_frame(self.handle, &flat.raw) };
+        let st = unsafe { sys::rdr_new_frame(self.handle, &flat.raw) };      // snapshots the scene (vulkan.rs:207-428)
         self.check(st); self.resolution = (flat.raw.width, flat.raw.height);
+        self.profiler.prepare_timer.end();
     }
-    fn render_sample(&mut self, _scene: &Scene) -> Option<RgbaImage> {
+    fn render_sample(&mut self, scene: &Scene) -> Option<RgbaImage> {
+        if self.resolution == (0, 0) { self.new_frame(scene); }              // the reference allocates its frame buffer lazily (cpu.rs:400-411)
         let (w, h) = self.resolution;
-        let mut buf = vec![0u8; (w * h * 4) as usize];
+        let img = self.image_for(w, h);
         let mut produced = 0;
-        let st = unsafe { sys::rdr_render_sample(self.handle, buf.as_mut_ptr(), &mut produced) };
-        self.check(st); self.sync_profiler();
-        if produced != 0 { RgbaImage::from_raw(w, h, buf) } else { None }
+        self.profiler.render_timer.start_if_not_started();                   // cpu.rs:195
+        self.profiler.sample_timer.start();                                  // cpu.rs:196
+        let st = unsafe { sys::rdr_render_sample(self.handle, img, &mut produced) };
+        self.check(st);
+        if produced == 0 { return None; }                                    // cpu.rs:143-145
+        self.profiler.sample_timer.end();                                    // cpu.rs:218
+        if self.sample_count() == self.max_sample_count() {                  // cpu.rs:213-216
+            self.profiler.render_timer.end();
+            self.profiler.frame_timer.end();
+        }
+        Some(self.take_image(w, h))
     }
     fn profiler(&self) -> &Profiler { &self.profiler }
     fn sample_count(&self) -> u32 { unsafe { sys::rdr_sample_count(self.handle) } }
@@ -99,7 +138,9 @@ impl Renderer for CudaRenderer {
     fn set_max_bounces(&mut self, bounces: u32) { unsafe { sys::rdr_set_max_bounces(self.handle, bounces) }; }
 }
 
-impl Drop for CudaRenderer { fn drop(&mut self) { unsafe { sys::rdr_destroy(self.handle) } } }
+impl Drop for CudaRenderer {
+    fn drop(&mut self) { unsafe { sys::rdr_free_host_image(self.image); sys::rdr_destroy(self.handle) } }
+}
 
 fn last_error(h: *const sys::RdrRenderer) -> String {
     unsafe { std::ffi::CStr::from_ptr(sys::rdr_last_error(h)).to_string_lossy().into_owned() }

@@ -12,6 +12,6 @@ for vv in $NAMES; do
   echo "== $vv"
   RAYDAR_CUDA_LIB=$LIBV timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "accumulator_bit_exact and fused or first_hit and fused or edge" 2>&1 | tail -1
   for rep in 1 2; do
-  RAYDAR_CUDA_LIB=$LIBV timeout 600 python bench.py --no-cpu-baseline --steps 3 "$@" 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$vv', d['value'], d['roofline']['kernel_ms'])" | tee -a $OUT/variants_$TAG.txt
+  RAYDAR_CUDA_LIB=$LIBV timeout 600 python bench.py --no-cpu-baseline --no-other-configs --steps 3 "$@" 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$vv', d['value'], d['roofline']['kernel_ms'])" | tee -a $OUT/variants_$TAG.txt
   done
 done

@@ -50,11 +50,11 @@ struct Packed {
     }
 };
 
-// entry k of a quad-major pair-packed node (rdr_bvh.h) in the two-quad entry form of bvh_entry_may_hit
+// entry k of a pair-packed node (rdr_bvh.h: node2_quad) in the two-quad entry form of bvh_entry_may_hit
 void node2_entry(const float *p, int k, f4 &q0, f4 &q1, uint32_t &payload)
 {
     const int pair = k >> 1, h = k & 1;
-    auto quad = [&](int i) { return p + 4 * (4 * i + pair); };
+    auto quad = [&](int i) { return p + 4 * node2_quad((uint32_t)i, (uint32_t)pair); };
     q0.x = quad(0)[0 + h]; q0.y = quad(0)[2 + h]; q0.z = quad(1)[0 + h]; q0.w = quad(1)[2 + h];
     q1.x = quad(2)[0 + h]; q1.y = quad(2)[2 + h]; q1.z = 0.0f;
     memcpy(&payload, &quad(3)[2 + h], 4);
@@ -65,7 +65,7 @@ void node2_entry(const float *p, int k, f4 &q0, f4 &q1, uint32_t &payload)
 // rank of entry k in the node's near-to-far order for direction octant oct
 uint32_t node2_rank(const float *p, int k, int oct)
 {
-    uint32_t r; memcpy(&r, p + 4 * (4 * 3 + (k >> 1)) + (k & 1), 4);
+    uint32_t r; memcpy(&r, p + 4 * node2_quad(3u, (uint32_t)(k >> 1)) + (k & 1), 4);
     return (r >> (3 * oct)) & 7u;
 }
 
@@ -717,6 +717,20 @@ int hs_render_fused_emu(const RdrSceneFlat *sc, uint64_t seed, uint32_t sample_b
     P.owned_pixels = stripe_owned_pixels(P.cam.width, P.cam.height, stripe_rows, stripe_index, stripe_count);
     (void)chunk_samples; (void)prior_samples;
     if (n_samples == 0u || P.owned_pixels == 0u) return RDR_OK;              // launch_render skips empty launches
+    // the frame's primary table (primary_kernel on the device): camera ray + nearest hit per pixel, by the per-lane scan
+    const size_t n_pixels = (size_t)P.cam.width * P.cam.height;
+    std::vector<f4> primary(n_pixels);
+    std::vector<int32_t> primary_idx(n_pixels);
+    {
+        std::vector<uint32_t> masks(pk.masks.size());
+        for (size_t p = 0; p < n_pixels; ++p) {
+            const v3 d = camera_ray_dir(P.cam, (uint32_t)(p % P.cam.width), (uint32_t)(p / P.cam.width));
+            const Hit h = trace_any<3>(pk.S, P.cull, masks.data(), 1, mk3(P.cam.pos[0], P.cam.pos[1], P.cam.pos[2]), d);
+            primary[p].x = d.x; primary[p].y = d.y; primary[p].z = d.z; primary[p].w = h.idx >= 0 ? h.t : 0.0f;
+            primary_idx[p] = h.idx;
+        }
+    }
+    P.primary = primary.data(); P.primary_idx = primary_idx.data();
     std::vector<int> ord(order, order + (order ? n_order : 0u));
     const bool ok = cold ? emu_render<true>(pk, P, ord) : emu_render<false>(pk, P, ord);
     return ok ? RDR_OK : RDR_ERR_INVALID;

@@ -25,7 +25,8 @@ def test_hierarchy_shape(hs):
     assert 5001 / 8 <= n_nodes <= 5001                      # 8-wide: between N/8 and N nodes
     n_nodes2, n_root, ok2 = hs.bvh2_info(scene)               # pair-packed twin: <= 32 root entries, 16 quads per node
     assert ok2 == 1 and 4 <= n_root <= 32 and 5001 / 8 / 1.5 <= n_nodes2 <= 5001
-    raw = 256 * n_nodes + 64 * 5001 + 256 * n_nodes2
+    head = 256 * n_nodes + 64 * 5001
+    raw = head + (-head) % 128 + 256 * n_nodes2             # the cooperative hierarchy's nodes start on a 128-byte line
     assert nbytes == raw + (-raw) % 16
 
 

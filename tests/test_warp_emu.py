@@ -131,18 +131,17 @@ def test_fused_scan_ties_and_tiny_scenes(hs, orc, default_scene):
     assert (ids >= 0).mean() > 0.5
 
 
-def test_prepared_variants_keep_the_winner(hs, orc, benchmark_scene):
-    """The default-off variants of rdr_fused.cuh (RDR_DIRECT_BALLOT: ballot append of the direct entries; RDR_APPROX_RHO:
-    sphere margin without the exact square roots -- exact here, the emulator has no sqrt.approx) return the same winners:
-    checked on the CPU before they are ever enabled on a GPU."""
+def test_direct_entries_by_ballot_keep_the_winner(hs, orc, benchmark_scene):
+    """The single-primitive top entries (the floor of benchmark.rscn; several, spheres among them, in the synthetic
+    scene) reach the survivor lists by one ballot each, and the per-ray sphere margin comes from the widened approximate
+    form (exact square roots here: the emulator has no sqrt.approx): same winners as the exact linear scan."""
     import copy
-    defines = ("RDR_DIRECT_BALLOT=1", "RDR_APPROX_RHO=1")
     rng = np.random.default_rng(17)
     rays = random_rays(rng, 3_001, scale=8.0)
     rays[:, 1] = np.abs(rays[:, 1])
     rays[::50, 3 + (np.arange(len(rays[::50])) % 3)] = 0.0
     rays[::77, :3] *= 1e4
-    ids_v, t_v = hs.trace_fused_variant("prepared", defines, benchmark_scene, rays)
+    ids_v, t_v = hs.trace_fused(benchmark_scene, rays)
     ids_l, t_l, _ = hs.trace(benchmark_scene, rays, use_cull=False)
     assert np.array_equal(ids_v, ids_l) and np.array_equal(u32(t_v), u32(t_l))
     base = ss.config4(80, 96, 54)                                       # several direct entries, spheres among them
@@ -152,12 +151,12 @@ def test_prepared_variants_keep_the_winner(hs, orc, benchmark_scene):
     s.material = np.concatenate([base.material, base.material[1:4]])
     rays = random_rays(rng, 2_401, scale=60.0)
     rays[:, 1] = np.abs(rays[:, 1]) * 0.5
-    ids_v, t_v = hs.trace_fused_variant("prepared", defines, s, rays)
+    ids_v, t_v = hs.trace_fused(s, rays)
     ids_l, t_l, _ = hs.trace(s, rays, use_cull=False)
     assert np.array_equal(ids_v, ids_l) and np.array_equal(u32(t_v), u32(t_l))
     scene = ss.config4(700, 96, 54)                                     # 24-member clusters
     rays = random_rays(rng, 1_601, scale=60.0)
-    ids_v, t_v = hs.trace_fused_variant("prepared", defines, scene, rays)
+    ids_v, t_v = hs.trace_fused(scene, rays)
     ids_l, t_l, _ = hs.trace(scene, rays, use_cull=False)
     assert np.array_equal(ids_v, ids_l) and np.array_equal(u32(t_v), u32(t_l))
 
