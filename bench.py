@@ -319,10 +319,16 @@ def roofline(a, rb, flat, torch, local, kernel_ms, samples_per_launch, traces_pe
         "kernel_ms": kernel_ms, "flops_per_sample": f_sample, "traces_per_sample": traces_per_sample,
         "traces_per_sample_source": traces_source,
         "peak_source": f"{sm_count} SMs x 128 lanes x 2 flop x sm_max_mhz from {peak_src} (nominal at the measured clock; the file has no FP32 figure)",
-        "note": "FP32-pipe bound (no dense contraction, HBM traffic is 32 B/pixel/launch); achieved = algorithmic "
+        "note": "FP32-pipe bound (no dense contraction, HBM traffic is 52 B/pixel/launch); achieved = algorithmic "
                 "flops of the reference's brute-force scan per launch / CUDA-event kernel time",
-        "hbm_algorithmic_bytes_per_launch": a.width * a.height * 32,
+        # accumulator read + write (16 B each) and the primary-table record (20 B) per pixel per launch
+        "hbm_algorithmic_bytes_per_launch": a.width * a.height * 52,
     }
+    if headline and prof.get("executed_fp32_flops_per_sample"):
+        ex = prof["executed_fp32_flops_per_sample"] * samples_per_launch / (kernel_ms * 1e-3) / 1e12
+        out["executed"] = {"tflops": ex, "frac_of_fp32_peak": ex / fp32_peak,
+                           "note": "FP32 flops the kernel EXECUTES (ncu smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on, FFMA = 2) "
+                                   "per sample of the committed capture x this run's samples/s: the machine-level fraction of FP32 peak"}
     return out
 
 
