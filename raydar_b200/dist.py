@@ -46,3 +46,11 @@ def device_accum_tensor(renderer, n_pixels: int, device_index: int):
         __cuda_array_interface__ = {"shape": (n_pixels * 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
     return torch.as_tensor(_Arr(), device=f"cuda:{device_index}")
+
+
+def peer_pixel_slice(rank: int, world: int, n_pixels: int) -> tuple[int, int]:
+    """The pixels rank `rank` combines in the fused reduce + resolve (peer_combine_kernel): (first, count) of the contiguous
+    slice [n*rank/world, n*(rank+1)/world) -- the rule of rdr_peer_combine (rdr_api.cpp) and of the multi-GPU handle
+    (rdr_multi.cpp).  The slices of the ranks are disjoint and cover the image."""
+    first = n_pixels * rank // world
+    return first, n_pixels * (rank + 1) // world - first

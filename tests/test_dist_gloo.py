@@ -26,9 +26,33 @@ def _worker(rank, world, port, mode, out_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     scene = orc.load_rscn(os.path.join(ROOT, "scenes", "default.rscn")).with_resolution(107, 60)
     spp = 6
-    first, count = (rdist.weak_sample_range(rank, spp) if mode == "weak" else rdist.strong_sample_range(rank, world, spp))
+    first, count = (rdist.weak_sample_range(rank, spp) if mode == "weak" else rdist.strong_sample_range(rank, world, spp))   # "peer": strong
     acc, _ = hs.render(scene, 42, first, count, 12)
     t = torch.from_numpy(acc.reshape(-1))
+    if mode == "peer":
+        # CPU model of the fused reduce + resolve (peer_combine_kernel): every rank "reads" all accumulators (all_gather
+        # stands in for the NVLink peer loads), sums ITS pixel slice in rank order, quantises it, and the RGBA8 slices
+        # meet on rank 0
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        n_pixels = acc.shape[0] * acc.shape[1]
+        first, n = rdist.peer_pixel_slice(rank, world, n_pixels)
+        total = parts[0].numpy().reshape(-1, 4)[first:first + n].copy()
+        for p in parts[1:]:
+            total = total + p.numpy().reshape(-1, 4)[first:first + n]
+        mine = torch.from_numpy(orc.resolve(total, spp).reshape(-1).copy())
+        sizes = [rdist.peer_pixel_slice(r, world, n_pixels)[1] * 4 for r in range(world)]
+        slices = [torch.empty(sz, dtype=torch.uint8) for sz in sizes] if rank == 0 else None
+        if rank == 0:
+            slices[0] = mine
+            for r in range(1, world):
+                dist.recv(slices[r], src=r)
+            np.save(out_path, torch.cat(slices).numpy().reshape(acc.shape[0], acc.shape[1], 4))
+        else:
+            dist.send(mine, dst=0)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     rdist.reduce_accum(t, dst=0)
     if rank == 0:
         np.save(out_path, t.numpy().reshape(acc.shape))
@@ -61,3 +85,28 @@ def test_ranges_partition_the_samples():
             covered = [s for b, n in ranges for s in range(b, b + n)]
             assert covered == list(range(total))
         assert [rdist.weak_sample_range(r, 1024)[0] for r in range(world)] == [1024 * r for r in range(world)]
+
+
+
+def test_peer_combine_model(hs, orc, default_scene, tmp_path):
+    """The fused reduce + resolve as a CPU model over gloo: pixel slices per rank, partial sums added in rank order,
+    quantised per slice -- the image equals print_frame_buffer of the ordered sum of the ranks' accumulators."""
+    import torch.multiprocessing as mp
+    from raydar_b200 import dist as rdist
+    world, spp = 2, 6
+    out = str(tmp_path / "img_peer.npy")
+    mp.spawn(_worker, args=(world, _free_port(), "peer", out), nprocs=world, join=True)
+    got = np.load(out)
+    scene = default_scene.with_resolution(107, 60)
+    parts = []
+    for r in range(world):
+        first, count = rdist.strong_sample_range(r, world, spp)
+        parts.append(hs.render(scene, 42, first, count, 12)[0])
+    want = orc.resolve(parts[0] + parts[1], spp)
+    assert np.array_equal(got, want)
+    one = orc.resolve(orc.render(scene, 42, 0, spp, 12, n_threads=2), spp)
+    assert np.abs(got.astype(int) - one.astype(int)).max() <= 1
+    for world in (1, 2, 3, 8):
+        for n in (0, 1, 7, 6420, 1920 * 1080):
+            sl = [rdist.peer_pixel_slice(r, world, n) for r in range(world)]
+            assert sl[0][0] == 0 and all(sl[r][0] + sl[r][1] == (sl[r + 1][0] if r + 1 < world else n) for r in range(world))
