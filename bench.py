@@ -605,7 +605,11 @@ def run_multi(a, rb, torch, dist, world, rank, local):
     e2e = None
     dist.barrier(group=host_group)
     if rank == 0:
-        e2e = multi_handle_leg(a, rb, torch, flat, world, stripes, image_rank0)
+        try:
+            e2e = multi_handle_leg(a, rb, torch, flat, world, stripes, image_rank0)
+        except Exception as exc:                              # the other ranks wait at the barrier below: never leave them there
+            e2e = {"value": None, "ms_per_step": None, "combine": None, "parity_check": False, "render_sample_ms": None, "h2d": 0,
+                   "parity_detail": {"error": f"{type(exc).__name__}: {exc}"}}
     dist.barrier(group=host_group)
     clock_info = clocks.stop() if rank == 0 else None
 
