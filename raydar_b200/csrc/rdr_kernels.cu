@@ -386,6 +386,11 @@ static RenderShape render_shape(const FrameParams &P, int mode)
     const int cfg = RDR_FUSED_CTA;
     if (cfg == 0) return RenderShape{RDR_BLOCK, false};
     if (cfg == 1) return RenderShape{896u, true};
+#ifdef RDR_EXTRA_SHAPES
+    if (cfg == 5) return RenderShape{832u, true};
+    if (cfg == 6) return RenderShape{960u, true};
+    if (cfg == 7) return RenderShape{1024u, true};
+#endif
     if (cfg == 3) return RenderShape{768u, true};
     if (cfg == 4) return RenderShape{768u, false};
     if (mode_smem_bytes(P.lay, true, 896u, mode, true) <= limit) return RenderShape{896u, true};
@@ -393,6 +398,11 @@ static RenderShape render_shape(const FrameParams &P, int mode)
     return RenderShape{768u, false};
 }
 
+#ifdef RDR_EXTRA_SHAPES      // kernel experiments only (build_variant): 832 / 960-thread CTAs of the fused kernel
+#define RDR_EXTRA_SHAPE_DISPATCH(shape, F) if ((shape).block == 832u) F((render_kernel<5, 832, 1, true>)); else if ((shape).block == 960u) F((render_kernel<5, 960, 1, true>)); else if ((shape).block == 1024u) F((render_kernel<5, 1024, 1, true>)); else
+#else
+#define RDR_EXTRA_SHAPE_DISPATCH(shape, F)
+#endif
 // calls F(kernel) with the render kernel instantiation for `mode` and `shape`
 #define RDR_RENDER_DISPATCH(mode, shape, F)                                                           \
     do {                                                                                              \
@@ -408,7 +418,7 @@ static RenderShape render_shape(const FrameParams &P, int mode)
             else F((render_kernel<6, RDR_BLOCK, 3, false>));                                          \
         }                                                                                             \
         else if ((mode) == 5) {                                                                       \
-            if ((shape).cold) { if ((shape).block == 896u) F((render_kernel<5, 896, 1, true>)); else F((render_kernel<5, 768, 1, true>)); } \
+            if ((shape).cold) { RDR_EXTRA_SHAPE_DISPATCH(shape, F) if ((shape).block == 896u) F((render_kernel<5, 896, 1, true>)); else F((render_kernel<5, 768, 1, true>)); } \
             else if ((shape).block == 768u) F((render_kernel<5, 768, 1, false>));                     \
             else F((render_kernel<5, RDR_BLOCK, 3, false>));                                          \
         }                                                                                             \
