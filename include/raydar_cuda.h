@@ -154,6 +154,10 @@ int rdr_render_samples(RdrRenderer *r, uint32_t n);
  * divisor = 0 uses sample_count(). */
 int rdr_resolve(RdrRenderer *r, uint32_t divisor, uint8_t *rgba8);
 int rdr_read_accum(RdrRenderer *r, float *accum_rgba_f32);    /* W*H*4 floats */
+/* The inverse: restore the current frame's accumulation state (W*H*4 floats = sums over `sample_count` samples) -- resume
+ * a progressive render from a saved accumulator: the next launch continues with sample index sample_count, exactly as
+ * if the samples had been rendered by this handle (the reference keeps this state only in memory, cpu.rs:113-114). */
+int rdr_write_accum(RdrRenderer *r, const float *accum_rgba_f32, uint32_t sample_count);
 /* device accumulator (float RGBA, W*H*4) and the stream the kernels run on, for an external
  * NCCL reduce (torch.distributed / ncclReduce) between per-GPU instances */
 int rdr_accum_device_ptr(RdrRenderer *r, void **ptr, size_t *bytes);

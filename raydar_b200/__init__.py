@@ -45,7 +45,7 @@ EXPORTS = [
     "rdr_scene_set_resolution", "rdr_scene_override_resolution", "rdr_scene_flat", "rdr_scene_free",
     "rdr_write_png", "rdr_version",
     "rdr_set_combine", "rdr_combine_in_use", "rdr_alloc_host_image", "rdr_free_host_image",
-    "rdr_kat_vec", "rdr_finish_frame", "rdr_ipc_export", "rdr_peer_attach", "rdr_peer_combine", "rdr_peer_detach", "rdr_read_image",
+    "rdr_kat_vec", "rdr_finish_frame", "rdr_write_accum", "rdr_ipc_export", "rdr_peer_attach", "rdr_peer_combine", "rdr_peer_detach", "rdr_read_image",
 ]
 
 
@@ -138,6 +138,7 @@ def load_library():
     L.rdr_reset_frame.argtypes = [vp]
     L.rdr_resolve.argtypes = [vp, C.c_uint32, u8p]
     L.rdr_read_accum.argtypes = [vp, fp]
+    L.rdr_write_accum.argtypes = [vp, fp, C.c_uint32]
     L.rdr_accum_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.rdr_stream.argtypes = [vp, C.POINTER(vp)]
     L.rdr_synchronize.argtypes = [vp]
@@ -384,6 +385,12 @@ class Renderer:
         acc = np.empty((*self._shape, 4), np.float32)
         _check(self._L.rdr_read_accum(self._h, _fp(acc)), self._h)
         return acc
+
+    def write_accum(self, accum: np.ndarray, sample_count: int) -> None:
+        """Restores the frame's accumulation state (resume a progressive render from a saved accumulator)."""
+        accum = np.ascontiguousarray(accum, np.float32)
+        assert accum.shape == (*self._shape, 4)
+        _check(self._L.rdr_write_accum(self._h, _fp(accum), sample_count), self._h)
 
     def accum_device_ptr(self) -> tuple[int, int]:
         p = C.c_void_p(); n = C.c_size_t()

@@ -456,6 +456,20 @@ int rdr_read_accum(RdrRenderer *r, float *dst)
     return RDR_OK;
 }
 
+int rdr_write_accum(RdrRenderer *r, const float *src, uint32_t sample_count)
+{
+    int st = check_frame(r);
+    if (st) return st;
+    if (r->multi) return fail(r, RDR_ERR_INVALID, "rdr_write_accum needs a single-GPU handle");
+    if (!src) return fail(r, RDR_ERR_INVALID, "src is NULL");
+    if (sample_count > r->config.max_sample_count) return fail(r, RDR_ERR_INVALID, "sample_count %u exceeds max_sample_count %u", sample_count, r->config.max_sample_count);
+    const size_t n_pixels = (size_t)r->params.cam.width * r->params.cam.height;
+    RDR_CUDA(r, cudaMemcpyAsync(r->d_accum, src, n_pixels * sizeof(rdr::f4), cudaMemcpyHostToDevice, r->stream));
+    RDR_CUDA(r, cudaStreamSynchronize(r->stream));
+    r->sample_count = sample_count;
+    return RDR_OK;
+}
+
 int rdr_accum_device_ptr(RdrRenderer *r, void **ptr, size_t *bytes)
 {
     int st = check_frame(r);

@@ -261,3 +261,30 @@ def test_auto_falls_back_to_the_hierarchy_when_the_scan_does_not_fit(rb, orc):
         r.render_frame(small)
         assert np.array_equal(u32(want), u32(r.read_accum())), accel
     r.close()
+
+
+def test_resume_from_a_saved_accumulator_and_resolve_of_edge_sums(rb, orc, default_scene):
+    """rdr_write_accum: (1) a progressive frame saved after k samples and restored on another handle continues to the same
+    accumulator bit for bit (the reference keeps this state only in memory, cpu.rs:113-114); (2) resolve_kernel itself
+    (not only the quantiser KAT) on accumulators holding +-inf, NaN, negative and huge sums."""
+    scene = default_scene.with_resolution(96, 54)
+    a = rb.Renderer(rb.RendererConfig(6, 12)); a.set_seed(3)
+    a.render_frame(scene); want = a.read_accum()
+    a.new_frame(scene); a.render_samples(2); saved = a.read_accum()
+    b = rb.Renderer(rb.RendererConfig(6, 12)); b.set_seed(3)
+    b.new_frame(scene); b.write_accum(saved, 2)
+    assert b.sample_count() == 2
+    img = b.finish_frame()
+    assert np.array_equal(u32(b.read_accum()), u32(want)) and b.sample_count() == 6
+    assert np.array_equal(img, orc.resolve(want, 6))
+    with pytest.raises(rb.RaydarError):
+        b.write_accum(saved, 7)                               # more samples than the frame has
+    edge = np.zeros((54, 96, 4), np.float32)
+    vals = np.array([np.inf, -np.inf, np.nan, -3.5, 1e38, -1e38, 0.0, -0.0, 2.9999998, 3.0, 1e-45, 765.0, 764.9999], np.float32)
+    edge.reshape(-1)[:len(vals) * 40] = np.tile(vals, 40)
+    b.new_frame(scene); b.write_accum(edge, 3)
+    assert np.array_equal(b.resolve(), orc.resolve(edge, 3))
+    assert np.array_equal(b.resolve(0), orc.resolve(edge, 3))
+    b.write_accum(edge, 0)                                    # n = 0: 0/0 = NaN -> 0, x/0 = +-inf -> 255 / 0
+    assert np.array_equal(b.resolve(), orc.resolve(edge, 0))
+    a.close(); b.close()
