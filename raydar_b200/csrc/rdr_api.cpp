@@ -79,7 +79,9 @@ struct RdrRenderer {
     bool has_frame_layout_bvh = false;   // the current frame was packed as a hierarchy (AUTO above the threshold)
     FrameParams params{};
     unsigned char *d_blob = nullptr; size_t blob_capacity = 0;
-    std::vector<unsigned char> host_blob;   // the packed scene of the current frame (kept: its upload is asynchronous)
+    std::vector<unsigned char> host_blob;   // the packed scene of the current frame
+    unsigned char *pinned_blob = nullptr; size_t pinned_capacity = 0;   // ... and its pinned copy: the upload is a true asynchronous DMA
+    int smem_optin = 0, smem_sm = 0;        // device limits, read once
     rdr::f4 *d_accum = nullptr; uchar4 *d_rgba = nullptr; size_t pixel_capacity = 0;
     rdr::f4 *d_primary = nullptr; int32_t *d_primary_idx = nullptr;   // the frame's primary table (primary_kernel)
     uint32_t *d_counter = nullptr;       // pixel hand-out counter of the persistent render kernel
@@ -288,6 +290,7 @@ void rdr_destroy(RdrRenderer *r)
     rdr_peer_detach(r);
     cudaSetDevice(r->device);
     if (r->d_blob) cudaFree(r->d_blob);
+    if (r->pinned_blob) cudaFreeHost(r->pinned_blob);
     if (r->d_accum) cudaFree(r->d_accum);
     if (r->d_rgba) cudaFree(r->d_rgba);
     if (r->d_primary) cudaFree(r->d_primary);
@@ -319,9 +322,11 @@ int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene)
     if ((st = pack_scene(r, scene, blob, P)) != RDR_OK) { r->has_frame = false; return st; }
 
     // stage the blob in shared memory when it leaves room for >= 2 resident CTAs per SM; the scan always needs it there
-    int smem_optin = 0, smem_sm = 0;
-    RDR_CUDA(r, cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, r->device));
-    RDR_CUDA(r, cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, r->device));
+    if (r->smem_optin == 0) {
+        RDR_CUDA(r, cudaDeviceGetAttribute(&r->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, r->device));
+        RDR_CUDA(r, cudaDeviceGetAttribute(&r->smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, r->device));
+    }
+    const int smem_optin = r->smem_optin, smem_sm = r->smem_sm;
     const size_t staged_need = rdr::scene_smem_bytes(P.lay, true, RDR_BLOCK);
     if (P.lay.mode == 1u) {
         P.staged = (staged_need + 1024u) * 2u <= (size_t)smem_sm && staged_need <= (size_t)smem_optin ? 1u : 0u;
@@ -342,7 +347,14 @@ int rdr_new_frame(RdrRenderer *r, const RdrSceneFlat *scene)
         RDR_CUDA(r, cudaMalloc(&r->d_blob, blob.size()));
         r->blob_capacity = blob.size();
     }
-    RDR_CUDA(r, cudaMemcpyAsync(r->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, r->stream));
+    if (blob.size() > r->pinned_capacity) {
+        if (r->pinned_blob) cudaFreeHost(r->pinned_blob);
+        r->pinned_blob = nullptr; r->pinned_capacity = 0;
+        RDR_CUDA(r, cudaHostAlloc((void **)&r->pinned_blob, blob.size(), cudaHostAllocDefault));
+        r->pinned_capacity = blob.size();
+    }
+    memcpy(r->pinned_blob, blob.data(), blob.size());      // the stream was drained above: the previous upload is done
+    RDR_CUDA(r, cudaMemcpyAsync(r->d_blob, r->pinned_blob, blob.size(), cudaMemcpyHostToDevice, r->stream));
 
     // frame_buffer()/blank_frame_buffer(), cpu.rs:400-423: reallocate on a resolution change, zero-fill
     const size_t n_pixels = (size_t)scene->width * scene->height;

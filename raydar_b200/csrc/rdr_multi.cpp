@@ -238,12 +238,28 @@ static int render_shares(RdrRenderer *owner, MultiGpu *m, const std::vector<uint
     return st != RDR_OK ? st : finish_shares(owner, m, share);
 }
 
+// n more samples of the frame over the devices (SAMPLES: n in total, as evenly as the devices' remaining shares allow;
+// STRIPES: n on every device, each for its own rows)
 static std::vector<uint32_t> split_samples(const MultiGpu *m, uint32_t n)
 {
     const uint32_t G = (uint32_t)m->child.size();
-    std::vector<uint32_t> share(G, 0);
-    const bool stripes = m->frame_partition == RDR_PARTITION_STRIPES;
-    for (uint32_t g = 0; g < G; ++g) share[g] = std::min(stripes ? n : n / G + (g < n % G ? 1u : 0u), api_samples_left(m->child[g]));
+    std::vector<uint32_t> share(G, 0), left(G, 0);
+    if (m->frame_partition == RDR_PARTITION_STRIPES) {
+        for (uint32_t g = 0; g < G; ++g) share[g] = std::min(n, api_samples_left(m->child[g]));
+        return share;
+    }
+    uint64_t total_left = 0;
+    for (uint32_t g = 0; g < G; ++g) { left[g] = api_samples_left(m->child[g]); total_left += left[g]; }
+    uint64_t todo = std::min<uint64_t>(n, total_left);
+    while (todo > 0u) {                              // every pass hands each device with room an equal part of what is still to do
+        uint32_t open = 0;
+        for (uint32_t g = 0; g < G; ++g) open += left[g] > share[g] ? 1u : 0u;
+        const uint64_t part = std::max<uint64_t>(1u, todo / open);
+        for (uint32_t g = 0; g < G && todo > 0u; ++g) {
+            const uint64_t take = std::min<uint64_t>(std::min<uint64_t>(part, left[g] - share[g]), todo);
+            share[g] += (uint32_t)take; todo -= take;
+        }
+    }
     return share;
 }
 

@@ -76,6 +76,13 @@ def test_multi_gpu_matches_single(rb, orc, benchmark_scene, n_dev, combine):
     assert calls == spp
     assert np.allclose(multi.read_accum(), acc1, rtol=1e-5, atol=1e-5)
     assert np.abs(last.astype(int) - img1.astype(int)).max() <= 1
+    # render_samples(n) renders exactly n more samples while the frame has them, whatever the devices' shares look like
+    multi.new_frame(scene)
+    multi.render_samples(5); assert multi.sample_count() == 5
+    multi.render_samples(3); assert multi.sample_count() == 8
+    multi.render_samples(1000); assert multi.sample_count() == spp
+    assert np.allclose(multi.read_accum(), acc1, rtol=1e-5, atol=1e-5)
+    assert np.array_equal(multi.read_accum()[..., 3], acc1[..., 3])
     one.close(); multi.close()
 
 
