@@ -327,32 +327,23 @@ __device__ __forceinline__ Hit trace_fused(const FusedView &V, const FrameParams
     //      full groups of 32 survivors, and on whatever is left after the last round ----
     const uint32_t per_round = CAP8 ? 1u : (P.lay.fused_cap >> 3);   // 8 members (4 pairs) per step; C is a multiple of 8
     uint32_t t0 = 0u, g = 0u;
-    // a task's ray constants, block pointer and descriptor: fetched at the first 8-member step of a task round and kept
-    // for its other steps (clusters of 16 / 24 / 32 members: CAP8 == false); with CAP8 every round is a first step
-    bool has = false;
-    uint32_t owner = 0u, desc = 0u;
-    float qx = 0.0f, qy = 0.0f, qz = 0.0f, mx = 0.0f, my = 0.0f, mz = 0.0f;
-    f32x2 rho2 = 0ull;
-    const f4 *blk = V.pair_block;
 #pragma unroll 1
     for (;;) {
         const bool last = t0 >= total;
         if (!last) {
             RDR_FSTAT(member_rounds, 1u);
-            if (CAP8 || g == 0u) {
-                const uint32_t t = t0 + lane;
-                has = t < total;
-                const uint32_t task = has ? (uint32_t)ws.tasks[t] : (lane << 8);
-                owner = task >> 8;
-                qx = __shfl_sync(FULL, rx, owner); qy = __shfl_sync(FULL, ry, owner); qz = __shfl_sync(FULL, rz, owner);
-                mx = __shfl_sync(FULL, nx, owner); my = __shfl_sync(FULL, ny, owner); mz = __shfl_sync(FULL, nz, owner);
-                rho2 = bc2(__shfl_sync(FULL, rho, owner));
-                blk = V.pair_block + (CAP8 ? 13u : P.lay.fused_stride) * (task & 0xffu);
-                if (!CAP8) desc = __float_as_uint(blk[2].z);
-            }
+            const uint32_t t = t0 + lane;
+            const bool has = t < total;
+            const uint32_t task = has ? (uint32_t)ws.tasks[t] : (lane << 8);
+            const uint32_t owner = task >> 8;
+            const float qx = __shfl_sync(FULL, rx, owner), qy = __shfl_sync(FULL, ry, owner), qz = __shfl_sync(FULL, rz, owner);
+            const float mx = __shfl_sync(FULL, nx, owner), my = __shfl_sync(FULL, ny, owner), mz = __shfl_sync(FULL, nz, owner);
+            const f32x2 rho2 = bc2(__shfl_sync(FULL, rho, owner));
+            const f4 *blk = V.pair_block + (CAP8 ? 13u : P.lay.fused_stride) * (task & 0xffu);
             const uint32_t m0 = CAP8 ? 0u : 8u * g;               // first member of this step
             const f4 *pb = blk + 3u * (m0 >> 1);
-            uint32_t bits = 0u;
+            uint32_t bits = 0u, desc = 0u;
+            if (!CAP8) desc = __float_as_uint(blk[2].z);
 #pragma unroll
             for (uint32_t p = 0; p < 4u; ++p) {
                 const f4 q0 = pb[3u * p], q1 = pb[3u * p + 1u];
