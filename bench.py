@@ -294,7 +294,7 @@ def scene_counts(rb, flat):
     return n_sph, flat.n_objects - n_sph
 
 
-def roofline(a, rb, flat, torch, local, kernel_ms, samples_per_launch, traces_per_sample, traces_source):
+def roofline(a, rb, flat, torch, local, kernel_ms, samples_per_launch, traces_per_sample, traces_source, clocks=None):
     peaks, peak_src = measured_peaks()
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     fp32_peak = sm_count * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12      # TFLOP/s
@@ -324,6 +324,10 @@ def roofline(a, rb, flat, torch, local, kernel_ms, samples_per_launch, traces_pe
         # accumulator read + write (16 B each) and the primary-table record (20 B) per pixel per launch
         "hbm_algorithmic_bytes_per_launch": a.width * a.height * 52,
     }
+    if clocks and clocks.get("sm_mhz"):
+        # against the max-clock peak (above) and the peak at the SM clock sampled under load during the timed region
+        out["peak_at_clock_under_load"] = sm_count * 128 * 2 * float(clocks["sm_mhz"]) * 1e6 / 1e12
+        out["frac_at_clock_under_load"] = achieved / out["peak_at_clock_under_load"] if have else None
     if headline and prof.get("executed_fp32_flops_per_sample"):
         ex = prof["executed_fp32_flops_per_sample"] * samples_per_launch / (kernel_ms * 1e-3) / 1e12
         out["executed"] = {"tflops": ex, "frac_of_fp32_peak": ex / fp32_peak,
@@ -450,7 +454,7 @@ def run_single(a, rb, torch, local):
         cpu["single_thread"] = cpu_single_thread(a) if a.config in (2, 3) else None
         if a.config == 4:
             cpu["with_oracle_bvh"] = cpu_bvh_run(a, 5.0)
-    out["roofline"] = roofline(a, rb, flat, torch, local, res["kernel_ms"], n_pixels * a.spp, traces, traces_src)
+    out["roofline"] = roofline(a, rb, flat, torch, local, res["kernel_ms"], n_pixels * a.spp, traces, traces_src, res["clocks"])
     if cpu:
         out["cpu_baseline"] = cpu
     out["render_sample_ms"] = time_progressive(a, r, flat, torch)
@@ -636,7 +640,7 @@ def run_multi(a, rb, torch, dist, world, rank, local):
         }
         traces = TRACES_PER_SAMPLE.get((a.scene_name, a.bounces))
         out["roofline"] = roofline(a, rb, flat, torch, local, kernel_ms, n_pixels * rank_spp, traces,
-                                   "oracle count, DESIGN.md 5 (the CPU leg runs at N = 1 only)" if traces is not None else None)
+                                   "oracle count, DESIGN.md 5 (the CPU leg runs at N = 1 only)" if traces is not None else None, clock_info)
         print(json.dumps(out))
     dist.destroy_process_group()
 
