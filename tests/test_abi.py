@@ -66,6 +66,12 @@ def test_no_cpu_fallback(rb):
     assert L.rdr_new_frame(None, None) == rb.ERR_INVALID
     assert L.rdr_render_samples(None, 1) == rb.ERR_INVALID
     assert L.rdr_sample_count(None) == 0
+    # pinned host images need the CUDA runtime too: an error status, not a crash, and no buffer
+    img = C.POINTER(C.c_uint8)()
+    assert L.rdr_alloc_host_image(64, C.byref(img)) in (rb.ERR_CUDA, rb.ERR_NOMEM) and not img
+    L.rdr_free_host_image(img)                              # NULL / unknown pointers are ignored
+    assert L.rdr_finish_frame(None, None) == rb.ERR_INVALID
+    assert L.rdr_peer_combine(None, 1) == rb.ERR_INVALID
 
 
 def test_product_does_not_reference_the_oracle(rb):
